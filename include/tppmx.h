@@ -1,0 +1,222 @@
+/*
+ * tppmx.h — C ABI of the B200-native PPMx reallocation-sweep / predictive library.
+ *
+ * This is the drop-in boundary for the hot path of mattpedone/treatppmx:
+ *   - collapsed-Gibbs cluster reallocation sweep   reference src/dm_ppmx_ct.cpp:347-860
+ *   - posterior-predictive step for new patients   reference src/dm_ppmx_ct.cpp:1080-1385
+ *   - similarity / linear-predictor helpers        reference src/utils_ct.cpp:161-200, 382-535
+ * The reference reaches that code through ONE .Call entry,
+ *   _treatppmx_dm_ppmx_ct (42 SEXPs)              reference src/RcppExports.cpp:16-65, :187
+ * An Rcpp shim (treatppmx_b200/csrc/rcpp_shim/) keeps that symbol and forwards to
+ * tppmx_dm_ppmx_ct() below; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: ints, doubles, caller-owned pointers.  The library never frees or keeps
+ *     caller memory; all device memory is owned by tppmx_ctx / tppmx_batch.
+ *   - every function returns 0 on success, non-zero on error; tppmx_last_error() gives text.
+ *   - "col-major" = Armadillo / R layout, so the shim passes .memptr() without copies.
+ *   - host-facing chain state uses the REFERENCE's layouts (labels 1-based, cluster-major
+ *     sufficient statistics); the device layout (SoA) is private to the library.
+ */
+#ifndef TPPMX_H
+#define TPPMX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPPMX_VERSION 100          /* 0.1.0 */
+#define TPPMX_MAXD 8               /* outcome categories  (reference dim = y.n_cols, :46)   */
+#define TPPMX_MAXQ 16              /* prognostic covariates (reference Q = z.n_cols, :47)   */
+#define TPPMX_MAXCC 8              /* auxiliary clusters  (reference CC, R/dm_ppmx_ct.R:93) */
+#define TPPMX_MAXT 16              /* treatment arms      (reference A / nT)                */
+
+/* ---- status codes ------------------------------------------------------------------- */
+enum {
+  TPPMX_OK = 0,
+  TPPMX_ERR_ARG = 1,        /* bad argument / unsupported switch combination            */
+  TPPMX_ERR_CUDA = 2,       /* CUDA runtime error (text in tppmx_last_error)             */
+  TPPMX_ERR_CAPACITY = 3,   /* a chain needed more than kcap clusters in one arm         */
+  TPPMX_ERR_NOMEM = 4
+};
+
+/* ---- RNG sites: counter-based Philox4x32-10 ------------------------------------------
+ * The reference draws from R's global RNG (RNGScope, src/RcppExports.cpp:19).  Here every
+ * random number is a pure function of (seed, chain, iteration, site, arm, index, sub):
+ *   key     = (seed_lo, seed_hi)
+ *   counter = (index, sub | site<<16 | arm<<24, iteration, chain)
+ * One Philox block gives two uniforms in (0,1) (52-bit, never 0 or 1) or, by Box-Muller,
+ * two standard normals.  The CPU oracle (oracle/) implements the same mapping, which is
+ * what makes lock-step parity tests possible.  The shim derives `seed` from two
+ * unif_rand() draws so set.seed() still governs a run. */
+enum {
+  TPPMX_SITE_INIT_SS = 1,     /* ss_i ~ Gamma(1, 1/TT_i)               :88-91   index=i          */
+  TPPMX_SITE_INIT_ETA = 2,    /* eta_star ~ U(0,1)                     :140     index=j*D+k, arm */
+  TPPMX_SITE_INIT_EMPTY = 3,  /* eta_empty ~ U(0,1)                    :210     index=mm*D+k,arm */
+  TPPMX_SITE_AUX_SWEEP = 4,   /* reuse==1: CC aux eta ~ N(0,I)         :351-360 index=mm, arm    */
+  TPPMX_SITE_AUX_PATIENT = 5, /* reuse==0: redraw per patient          :605-610 index=i*CC+mm    */
+  TPPMX_SITE_ALLOC_U = 6,     /* uu for the reallocation draw          :805     index=i, arm     */
+  TPPMX_SITE_AUX_REFRESH = 7, /* refresh the aux that was consumed     :844     index=i, arm     */
+  TPPMX_SITE_ETA_PROP = 8,    /* eta_update proposal + accept  utils_ct.cpp:642-676 index=j, arm */
+  TPPMX_SITE_HIER_W = 9,      /* Wishart draw of Lambda                :895     arm              */
+  TPPMX_SITE_HIER_THETA = 10, /* Theta ~ N(fptp, sptp)                 :899     arm              */
+  TPPMX_SITE_SIGKAP = 11,     /* (sigma,kappa) grid draw               :1000    arm              */
+  TPPMX_SITE_BETA = 12,       /* beta_update proposal + accept utils_ct.cpp:761-781 index=k*Q+q  */
+  TPPMX_SITE_HS_LAMBDA = 13,  /* horseshoe lambda slice        utils_ct.cpp:876-894 index=h      */
+  TPPMX_SITE_HS_TAU = 14,     /* horseshoe tau slice           utils_ct.cpp:896-915              */
+  TPPMX_SITE_JJ = 15,         /* JJ_ik ~ Gamma(y+exp(lg), 1/(ss+1))    :1045    index=i*D+k      */
+  TPPMX_SITE_SS = 16,         /* ss_i ~ Gamma(1, 1/TT_i)               :1054    index=i          */
+  TPPMX_SITE_ISPRED = 17,     /* in-sample multinomial draw            :1065    index=i          */
+  TPPMX_SITE_PRED_U = 18,     /* predictive cluster draw               :1351    index=pp, arm    */
+  TPPMX_SITE_PRED_ETA = 19,   /* eta_pred ~ N(Theta_t, Sigma_t)        :1369    index=pp, arm    */
+  TPPMX_SITE_PRED_Y = 20      /* ypred ~ Multinomial(1, pi)            :1381    index=pp, arm    */
+};
+
+/* ---- model switches and hyper-parameters: scalar arguments of dm_ppmx_ct (:10-23) ---- */
+typedef struct tppmx_model {
+  int32_t PPMx;          /* 1: covariate-dependent partition model, 0: plain PPM           */
+  int32_t cohesion;      /* 1: DP (log n_j / log alpha - log CC), 2: NGG (V table)  :559-565 */
+  int32_t similarity;    /* 1: auxiliary, 2: double dipper                         :472-516 */
+  int32_t consim;        /* 1: Normal-Normal, 2: Normal-NormalInverseGamma                  */
+  int32_t calibration;   /* 0: none, 1: standardised similarities :717-788, 2: coarsened    */
+  int32_t coardegree;    /* 1: 1/(P+ncat), 2: 1/sqrt(P+ncat)                       :588-593 */
+  int32_t reuse;         /* 1: Favaro-Teh reuse of auxiliary draws, 0: redraw per patient   */
+  int32_t CC;            /* number of auxiliary clusters (<= TPPMX_MAXCC)                   */
+  int32_t upd_hier;      /* update (Theta,Sigma) hierarchy                         :880     */
+  int32_t hsp;           /* horseshoe prior on beta                                :1029    */
+  int32_t noprog;        /* 1: no prognostic covariates, beta frozen               :1009    */
+  int32_t nolik;         /* 1: drop the response-likelihood term (:570-576) = the prior-only  */
+                         /* sampler prior_ppmx_core (src/prior_ppmx.cpp:101-460); default 0    */
+  double alpha;          /* DP mass (reference `alpha`, R `kappa`)                          */
+  double similparam[7];  /* m0, s20, v, k0, nu0, (unused), dirichlet weight        :220-227 */
+  double hP0_mu0[TPPMX_MAXD];
+  double hP0_nu0, hP0_s0, hP0_Lambda0;
+  double mhtune_eta, mhtune_beta;   /* mhtunepar(0), mhtunepar(1)                            */
+} tppmx_model;
+
+typedef struct tppmx_dims {
+  int32_t nobs;    /* n: historical patients                                                 */
+  int32_t T;       /* arms                                                                   */
+  int32_t D;       /* outcome categories                                                     */
+  int32_t Q;       /* prognostic covariates                                                  */
+  int32_t P;       /* continuous predictive covariates (ncon)                                */
+  int32_t ncat;    /* categorical predictive covariates                                      */
+  int32_t maxC;    /* max_C = max(catvec) (:107); 0 if ncat==0                               */
+  int32_t npred;   /* new patients                                                           */
+  int32_t G;       /* (sigma,kappa) grid points = grid.n_cols (:56); >=1                     */
+  int32_t ntmax;   /* max_t n_t = leading cluster dimension of the reference's state arrays  */
+  int32_t kcap;    /* device cluster capacity per arm, 1..ntmax (0 => ntmax).  If a chain    */
+                   /* ever needs more, the call returns TPPMX_ERR_CAPACITY.                  */
+  int32_t reserved0;
+} tppmx_dims;
+
+/* Inputs shared by every dataset of a batch. */
+typedef struct tppmx_shared {
+  const int32_t *catvec;  /* [ncat] categories per categorical covariate                     */
+  const double *grid;     /* 2 x G col-major: grid[2g]=sigma_g, grid[2g+1]=kappa_g  (:52-55) */
+  const double *logV;     /* compact NGG table [T][2][ntmax][G]:                              */
+                          /*   logV[((t*2+r)*ntmax + (K-1))*G + g] = log V(n_t-1+r, K; g)     */
+                          /* i.e. r=1 is log Vwm(n_t-1,K-1,g), r=0 is log Vwm(n_t-2,K-1,g)    */
+                          /* of the reference's dense cube (:563).  NULL if cohesion==1.      */
+} tppmx_shared;
+
+/* One dataset (replicate).  Layouts are the ones dm_ppmx_ct receives (:10-23). */
+typedef struct tppmx_dataset {
+  const int32_t *treat;   /* [nobs] arm of each patient, 0-based (`treatments`)              */
+  const double *y;        /* nobs x D col-major, one-hot outcome                              */
+  const double *z;        /* nobs x Q col-major, prognostic covariates                        */
+  const double *xcon;     /* nobs x P ROW-major (xcon[i*P+p], R: as.vector(t(xcon)))          */
+  const int32_t *xcat;    /* nobs x ncat row-major, categories 0-based                        */
+  const double *zpred;    /* npred x Q col-major                                              */
+  const double *xconp;    /* npred x P row-major                                              */
+  const int32_t *xcatp;   /* npred x ncat row-major                                           */
+} tppmx_dataset;
+
+/* Chain state in the REFERENCE's layouts (all caller-owned host memory).
+ * Used to upload / download one chain; any pointer may be NULL to skip that field. */
+typedef struct tppmx_state {
+  int32_t *labels;     /* T x ntmax col-major: curr_clu(t,it), 1-based (:113)                */
+  int32_t *nj;         /* T x ntmax col-major: nj_curr(t,j) (:114)                           */
+  int32_t *nclu;       /* [T] nclu_curr (:115)                                               */
+  double *sumx;        /* T x (ntmax*P) col-major: sumx(t, j*P+p) (:179)                     */
+  double *sumx2;       /* same (:180)                                                        */
+  int32_t *njc;        /* T x (ntmax*ncat*maxC) col-major: njc(t,(j*ncat+p)*maxC+c) (:181)   */
+  double *eta_star;    /* D x ntmax x T col-major cube: eta_star_curr(k,j,t) (:140)          */
+  double *eta_empty;   /* D x CC x T col-major cube (:210)                                   */
+  double *JJ;          /* nobs x D col-major (:70)                                           */
+  double *ss;          /* [nobs] (:88)                                                       */
+  double *loggamma;    /* nobs x D col-major (:161)                                          */
+  double *beta;        /* [Q*D], index h = k + q*D (utils_ct.cpp:524)                        */
+  double *sigma;       /* [T] (:50)                                                          */
+  double *kappa;       /* [T] (:51)                                                          */
+  int32_t *idxs;       /* [1] shared grid index (:45,:49) -- quirk: one scalar for all arms  */
+  double *Theta;       /* D x T col-major (:271)                                             */
+  double *Sigma;       /* D x D x T col-major cube (:272)                                    */
+  double *lambda;      /* [Q*D] horseshoe local scales (:154)                                */
+  double *tau;         /* [1] horseshoe global scale (:155)                                  */
+  double *sigma_beta;  /* [Q*D] (:153)                                                       */
+} tppmx_state;
+
+typedef struct tppmx_ctx tppmx_ctx;
+typedef struct tppmx_batch tppmx_batch;
+
+/* ---- context ------------------------------------------------------------------------ */
+int tppmx_version(void);
+int tppmx_create(tppmx_ctx **ctx, int device);
+int tppmx_destroy(tppmx_ctx *ctx);
+const char *tppmx_last_error(const tppmx_ctx *ctx);
+
+/* ---- batch of chains ---------------------------------------------------------------- */
+/* chain c runs on dataset chain_dataset[c] and uses Philox stream id chain_id[c]
+ * (NULL => c).  All datasets share dims; copies everything it needs to the device. */
+int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, const tppmx_dims *dims,
+                       const tppmx_shared *shared, int32_t n_datasets,
+                       const tppmx_dataset *datasets, int32_t n_chains,
+                       const int32_t *chain_dataset, const int32_t *chain_id,
+                       tppmx_batch **out);
+int tppmx_batch_destroy(tppmx_batch *b);
+
+/* State initialisation exactly as the reference's prologue (:49-236): JJ=max(y,1e-100),
+ * ss~Gamma, eta_star/eta_empty~U(0,1), beta=initbeta, Sigma=I, sufficient statistics
+ * from the initial partition.  init_labels: n_datasets x (T x ntmax col-major) 1-based
+ * labels (`curr_cluster`), init_nclu: n_datasets x T.  initbeta: [Q*D]. */
+int tppmx_batch_init(tppmx_batch *b, uint64_t seed, const int32_t *init_labels,
+                     const int32_t *init_nclu, const double *initbeta);
+
+int tppmx_batch_set_state(tppmx_batch *b, int32_t chain, const tppmx_state *s);
+int tppmx_batch_get_state(tppmx_batch *b, int32_t chain, tppmx_state *s);
+
+/* ---- hot path 1: reallocation sweep (:347-860) -------------------------------------- */
+/* Parity hook.  Takes patient `it` (position inside arm `arm`) of chain `chain` out of its
+ * cluster (:368-457) on a scratch copy of the arm and returns the K+CC log-weights
+ * (:460-788, before the max-shift) and normalised probabilities (:791-802).  The chain
+ * state is NOT modified.  K_out = occupied clusters after the removal. */
+int tppmx_score_patient(tppmx_batch *b, int32_t chain, int32_t arm, int32_t it,
+                        uint64_t seed, int32_t iter, double *logw_out, double *prob_out,
+                        int32_t *K_out);
+
+/* n_sweeps Gibbs sweeps over all arms and patients of every chain; everything that the
+ * sweep does not update (eta_star of occupied clusters, beta, JJ, ss, sigma, idxs) stays
+ * frozen.  Iteration numbers iter0..iter0+n_sweeps-1 key the RNG.  */
+int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps);
+
+/* Device time (ms, CUDA events on the launching stream) and kernel launches of the last
+ * tppmx_batch_sweep / tppmx_batch_predict / tppmx_batch_run call. */
+int tppmx_batch_last_timing(const tppmx_batch *b, double *ms, int32_t *launches);
+
+/* ---- hot path 2: posterior predictive (:1080-1385) ---------------------------------- */
+/* For every chain, arm and new patient: score K+CC clusters on covariates only, draw the
+ * cluster, take its eta (or N(Theta,Sigma) for an auxiliary pick), pi = softmax(eta+beta'z),
+ * one multinomial draw.  Outputs (any may be NULL), chain-major:
+ *   pipred    [n_chains][npred x D x T col-major]   (reference pii_pred,  :296)
+ *   ypred     [n_chains][npred x D x T col-major]   (reference ppred,     :300)
+ *   predclass [n_chains][npred x T col-major]       (reference predclass, :301) */
+int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, double *pipred,
+                        double *ypred, int32_t *predclass);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPPMX_H */

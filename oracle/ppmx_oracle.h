@@ -1,0 +1,74 @@
+/*
+ * ppmx_oracle.h — CPU oracle for the treatppmx hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of the reference's algorithm, used as the parity checker by tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Nothing in
+ * treatppmx_b200/ (the product) may include, link or call this.
+ *
+ * Parity pin status: the reference ships NO tests, golden vectors or fixtures for this path
+ *  and cannot be compiled here (needs R, Rcpp, RcppArmadillo, libRmath), so the
+ * oracle is pinned by closed-form known-answer tests instead (tests/test_oracle_kat.py):
+ * NN / NNIG / DM marginals against scipy, and the CRP cluster-count law for the sweep.
+ * With respect to reference-produced outputs it is "parity unpinned".
+ *
+ * State and inputs use the structs of include/tppmx.h (reference layouts).
+ */
+#ifndef PPMX_ORACLE_H
+#define PPMX_ORACLE_H
+#include "../include/tppmx.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* bundle of the read-only inputs of one chain */
+typedef struct oracle_problem {
+  tppmx_model model;
+  tppmx_dims dims;
+  tppmx_shared shared;
+  tppmx_dataset data;
+} oracle_problem;
+
+/* helpers, exported for the known-answer tests (reference src/utils_ct.cpp) */
+double oracle_dnorm_log(double x, double mu, double sigma);                       /* R::dnorm(.,1) */
+double oracle_dinvgamma(double y, double alpha, double beta, int logout);         /* :161-176 */
+double oracle_dN_IG(double mu, double sig2, double mu0, double k0, double a0, double b0,
+                    int logout);                                                  /* :181-200 */
+double oracle_gsimconNN(double m0, double v2, double s20, double sumx, double sumx2, int n,
+                        int DD, int logout);                                      /* :382-405 */
+double oracle_gsimconNNIG(double m0, double k0, double nu0, double s20, double sumx,
+                          double sumx2, int n, int DD, int logout);               /* :427-459 */
+double oracle_gsimcatDM(const double *nobsj, const double *dirweights, int C, int DD,
+                        int logout);                                              /* :468-495 */
+
+/* RNG contract probes (for the device/host RNG agreement test) */
+void oracle_rng_u2(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t site, uint32_t arm,
+                   uint32_t index, uint32_t sub, double *out2);
+void oracle_rng_n2(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t site, uint32_t arm,
+                   uint32_t index, uint32_t sub, double *out2);
+double oracle_rng_gamma(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t site,
+                        uint32_t arm, uint32_t index, double shape);
+
+/* prologue of dm_ppmx_ct (src/dm_ppmx_ct.cpp:49-236) */
+int oracle_init_state(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,
+                      const int32_t *init_labels, const int32_t *init_nclu,
+                      const double *initbeta);
+
+/* remove patient (arm,it) on a private copy, return log-weights / probabilities */
+int oracle_score_patient(const oracle_problem *pb, const tppmx_state *s, int32_t arm,
+                         int32_t it, uint64_t seed, uint32_t chain_id, int32_t iter,
+                         double *logw_out, double *prob_out, int32_t *K_out);
+
+/* n_sweeps passes of src/dm_ppmx_ct.cpp:349-860 with everything else frozen */
+int oracle_sweep(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,
+                 int32_t iter0, int32_t n_sweeps);
+
+/* src/dm_ppmx_ct.cpp:1081-1384 */
+int oracle_predict(const oracle_problem *pb, const tppmx_state *s, uint64_t seed,
+                   uint32_t chain_id, int32_t iter, double *pipred, double *ypred,
+                   int32_t *predclass);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
