@@ -1,0 +1,162 @@
+// predict.cuh — posterior-predictive step for new patients.
+//
+// B200-first restatement of /root/reference/src/dm_ppmx_ct.cpp:1080-1385.  New patients are
+// independent given the chain state, so one THREAD owns one (chain, arm, new patient): it
+// streams over the K+CC clusters twice (pass 1: running max / normaliser, pass 2: inverse-CDF
+// scan with the same weights), so no per-patient weight vector is ever stored.  Cluster
+// statistics are read by all threads of a block at the same address (broadcast loads).
+#pragma once
+#include "layout.h"
+#include "rng.cuh"
+#include "sim.cuh"
+#include "sweep.cuh"
+
+namespace tppmx {
+
+struct PredW {  // weight of cluster j for one new patient, plus the raw similarities
+  double w, gN, gY;
+};
+
+__device__ inline PredW pred_weight(const DevBatch &b, const SimConst &s, const ArmView &A, int j,
+                                    const double *x, const double *x2, const int *xc_train,
+                                    const int *xc_new, double sigma, double dV,
+                                    double log_alpha_cc) {
+  const bool occ = j < A.K;
+  const int n = occ ? A.nj[j] : 0;
+  double lgN, lgY;
+  // quirk (:1157): an occupied cluster's "with" count uses the TRAINING xcat row indexed by the
+  // prediction index; auxiliary clusters use xcatp (:1238).
+  sim_terms(b, s, A.sumx + j, A.sumx2 + j, A.njc + j, A.ks, n, occ, x, x2, occ ? xc_train : xc_new,
+            lgN, lgY);
+  PredW r;
+  r.gN = occ ? lgN : lgY;
+  r.gY = lgY;
+  r.w = cohesion_term(s, occ, n, sigma, dV, log_alpha_cc);
+  if (!(s.calibration == 1 && s.PPMx)) {
+    const double d = lgY - lgN;
+    r.w += (s.calibration == 2 && s.PPMx) ? s.calscale * d : d;
+  }
+  return r;
+}
+
+// grid = (chains, T); threads stride over new patients
+__global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed, int iter,
+                                                      double *pipred, double *ypred,
+                                                      int *predclass) {
+  const int chain = blockIdx.x, tt = blockIdx.y;
+  const int ds = b.chain_ds[chain];
+  const SimConst s = make_simconst(b);
+  const Rng rng = make_rng(seed, b.chain_id[chain]);
+  const ArmView A = arm_view_global(b, chain, tt, ds);
+  const int K = A.K, CC = b.CC, ntot = K + CC, D = b.D, npred = b.npred;
+  const double sigma = b.sigma[(size_t)chain * b.T + tt];
+  const int idxs = b.idxs[chain];
+  const double log_alpha_cc = log(b.model.alpha) - log((double)CC);
+  const bool cal1 = (s.calibration == 1) && s.PPMx;
+  double dV = 0.0;
+  if (s.cohesion == 2 && K >= 1) {
+    const size_t base = ((size_t)tt * 2) * b.ntmax;
+    dV = b.logV[(base + b.ntmax + (K - 1)) * b.G + idxs] - b.logV[(base + (K - 1)) * b.G + idxs];
+  }
+  const double *beta = b.beta + (size_t)chain * b.Q * D;
+  const double *Theta = b.Theta + ((size_t)chain * b.T + tt) * D;
+  const double *Sigma = b.Sigma + ((size_t)chain * b.T + tt) * D * D;
+  const size_t obase = (size_t)chain * npred * D * b.T;
+  const int nc1 = b.ncat > 0 ? b.ncat : 1;
+
+  for (int pp = threadIdx.x; pp < npred; pp += blockDim.x) {
+    const double *x = b.xp + ((size_t)ds * npred + pp) * b.P;
+    const double *x2 = b.xp2 + ((size_t)ds * npred + pp) * b.P;
+    const int *xc_new = b.xcatp + ((size_t)ds * npred + pp) * nc1;
+    // quirk 6: training row `pp` (requires pp < nobs when ncat > 0; checked on the host)
+    const int *xc_train = b.xcat + ((size_t)ds * b.nobs + (pp < b.nobs ? pp : 0)) * nc1;
+
+    double mN = -INFINITY, sN = 0.0, mY = -INFINITY, sY = 0.0;
+    if (cal1) {  // :1282-1307 log-softmax normalisers of gtilN (all) and gtilY (occupied)
+      for (int j = 0; j < ntot; j++) {
+        const PredW r = pred_weight(b, s, A, j, x, x2, xc_train, xc_new, sigma, dV, log_alpha_cc);
+        double m2 = fmax(mN, r.gN);
+        sN = sN * exp(mN - m2) + exp(r.gN - m2);
+        mN = m2;
+        if (j < K) {
+          m2 = fmax(mY, r.gY);
+          sY = sY * exp(mY - m2) + exp(r.gY - m2);
+          mY = m2;
+        }
+      }
+    }
+    const double lsN = log(sN), lsY = log(sY);
+    auto weight_of = [&](int j) {
+      const PredW r = pred_weight(b, s, A, j, x, x2, xc_train, xc_new, sigma, dV, log_alpha_cc);
+      if (!cal1) return r.w;
+      const double lgtilNk = (r.gN - mN) - lsN;
+      return (j < K) ? r.w + ((r.gY - mY) - lsY) - lgtilNk : r.w + lgtilNk;
+    };
+
+    double wmax = -INFINITY, den = 0.0;  // :1337-1345
+    for (int j = 0; j < ntot; j++) {
+      const double w = weight_of(j);
+      const double m2 = fmax(wmax, w);
+      den = den * exp(wmax - m2) + exp(w - m2);
+      wmax = m2;
+    }
+    double uu, u1;
+    rng_u2(rng, iter, TPPMX_SITE_PRED_U, tt, (uint32_t)pp, 0, uu, u1);
+    int newci = ntot;  // reference quirk 7 (:1351-1360): no default; see DESIGN.md
+    double cweight = 0.0;
+    for (int j = 0; j < ntot; j++) {
+      cweight += exp(weight_of(j) - wmax) / den;
+      if (uu < cweight) {
+        newci = j + 1;
+        break;
+      }
+    }
+
+    double eta_pred[TPPMX_MAXD];
+    if (newci <= K) {  // :1366-1370
+      for (int k = 0; k < D; k++) eta_pred[k] = A.eta[(size_t)k * A.ks + newci - 1];
+    } else {
+      double zn[TPPMX_MAXD], L[TPPMX_MAXD * TPPMX_MAXD];
+      rng_normals(rng, iter, TPPMX_SITE_PRED_ETA, tt, (uint32_t)pp, D, zn, 1);
+      for (int a = 0; a < D; a++)
+        for (int c = 0; c <= a; c++) {
+          double sum = Sigma[a + D * c];
+          for (int k = 0; k < c; k++) sum -= L[a + D * k] * L[c + D * k];
+          L[a + D * c] = (a == c) ? sqrt(sum) : sum / L[c + D * c];
+        }
+      for (int k = 0; k < D; k++) {
+        double acc = Theta[k];
+        for (int r = 0; r <= k; r++) acc += L[k + D * r] * zn[r];
+        eta_pred[k] = acc;
+      }
+    }
+    // :1373-1379 softmax(eta_pred + beta' zpred) without max-shift, as the reference
+    const double *zp = b.zpred + ((size_t)ds * npred + pp) * b.Q;
+    double pi_row[TPPMX_MAXD], sumrow = 0.0;
+    for (int k = 0; k < D; k++) {
+      double lg = eta_pred[k];
+      for (int q = 0; q < b.Q; q++) lg += beta[k + q * D] * zp[q];
+      pi_row[k] = exp(lg);
+      sumrow += pi_row[k];
+    }
+    for (int k = 0; k < D; k++) pi_row[k] = pi_row[k] / sumrow;
+    double uy, uy1, cw = 0.0;  // :1381 rmultinom(1, pi)
+    rng_u2(rng, iter, TPPMX_SITE_PRED_Y, tt, (uint32_t)pp, 0, uy, uy1);
+    int pick = D - 1;
+    for (int k = 0; k < D; k++) {
+      cw += pi_row[k];
+      if (uy < cw) {
+        pick = k;
+        break;
+      }
+    }
+    for (int k = 0; k < D; k++) {
+      const size_t o = obase + pp + (size_t)npred * (k + (size_t)D * tt);
+      if (pipred) pipred[o] = pi_row[k];
+      if (ypred) ypred[o] = (k == pick) ? 1.0 : 0.0;
+    }
+    if (predclass) predclass[(size_t)chain * npred * b.T + pp + (size_t)npred * tt] = newci;
+  }
+}
+
+}  // namespace tppmx

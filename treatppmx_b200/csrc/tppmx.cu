@@ -1,0 +1,766 @@
+// tppmx.cu — C ABI (include/tppmx.h) over the sm_100a kernels.  Host side: argument checks,
+// layout conversion between the reference's Armadillo layouts and the device SoA layout,
+// device memory ownership, launches and timing.  No compute happens on the host.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "layout.h"
+#include "predict.cuh"
+#include "rng.cuh"
+#include "sim.cuh"
+#include "sweep.cuh"
+
+using namespace tppmx;
+
+struct tppmx_ctx {
+  int device;
+  cudaStream_t stream;
+  std::string err;
+};
+
+struct tppmx_batch {
+  tppmx_ctx *ctx;
+  DevBatch d;  // device pointers + dims
+  tppmx_dims dims;
+  std::vector<void *> allocs;
+  std::vector<int> arm_n;     // [nd][T]
+  std::vector<int> chain_ds;  // [nc+1]
+  cudaEvent_t ev0, ev1;
+  double last_ms;
+  int last_launches;
+  int scratch_chain;  // slot index n_chains
+};
+
+#define CK(ctx, call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                    \
+      return TPPMX_ERR_CUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+
+static int fail(tppmx_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+extern "C" int tppmx_version(void) { return TPPMX_VERSION; }
+
+extern "C" int tppmx_create(tppmx_ctx **out, int device) {
+  if (!out) return TPPMX_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return TPPMX_ERR_CUDA;
+  tppmx_ctx *c = new tppmx_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess) {
+    delete c;
+    return TPPMX_ERR_CUDA;
+  }
+  *out = c;
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_destroy(tppmx_ctx *c) {
+  if (!c) return TPPMX_OK;
+  cudaSetDevice(c->device);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return TPPMX_OK;
+}
+
+extern "C" const char *tppmx_last_error(const tppmx_ctx *c) { return c ? c->err.c_str() : "no context"; }
+
+// ---- allocation helpers -------------------------------------------------------------------
+template <class T>
+static int dev_alloc(tppmx_batch *b, T **p, size_t n, bool zero = true) {
+  void *q = nullptr;
+  if (n == 0) n = 1;
+  CK(b->ctx, cudaMalloc(&q, n * sizeof(T)));
+  b->allocs.push_back(q);
+  if (zero) CK(b->ctx, cudaMemsetAsync(q, 0, n * sizeof(T), b->ctx->stream));
+  *p = (T *)q;
+  return TPPMX_OK;
+}
+template <class T>
+static int dev_upload(tppmx_batch *b, const T **p, const std::vector<T> &h) {
+  T *q = nullptr;
+  int rc = dev_alloc(b, &q, h.size(), false);
+  if (rc) return rc;
+  if (!h.empty()) CK(b->ctx, cudaMemcpyAsync(q, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, b->ctx->stream));
+  CK(b->ctx, cudaStreamSynchronize(b->ctx->stream));  // h may be a temporary
+  *p = q;
+  return TPPMX_OK;
+}
+#define RC(x)            \
+  do {                   \
+    int rc__ = (x);      \
+    if (rc__) return rc__; \
+  } while (0)
+
+// per-n constants of the Normal-Normal similarity (sim.cuh), reference utils_ct.cpp:389-400
+static std::vector<NNRow> build_nn_tab(const tppmx_model &m, int ntmax) {
+  const double m0 = m.similparam[0], s20 = m.similparam[1], v2 = m.similparam[2];
+  std::vector<NNRow> t((size_t)ntmax + 2);
+  const double sd0 = sqrt(s20);
+  const double z0 = m0 / sd0;
+  const double ld2 = -(TPPMX_LN_SQRT_2PI + 0.5 * z0 * z0 + log(sd0));
+  for (int n = 0; n <= ntmax + 1; n++) {
+    const double s2s = 1 / ((n / v2) + (1 / s20));
+    const double s2ss = 1 / ((n / v2) + (1 / s2s));
+    const double c1 = -0.5 * n * log(2 * M_PI * v2);
+    NNRow r;
+    r.A0 = c1 + ld2 + TPPMX_LN_SQRT_2PI + 0.5 * log(s2s);
+    r.H = 0.5 * s2s;
+    r.B0 = c1 - 0.5 * log(s2s) + 0.5 * log(s2ss);
+    r.H2 = 0.5 * s2ss;
+    t[n] = r;
+  }
+  return t;
+}
+
+extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, const tppmx_dims *dims,
+                                  const tppmx_shared *shared, int32_t n_datasets,
+                                  const tppmx_dataset *datasets, int32_t n_chains,
+                                  const int32_t *chain_dataset, const int32_t *chain_id,
+                                  tppmx_batch **out) {
+  if (!ctx) return TPPMX_ERR_ARG;
+  if (!model || !dims || !shared || !datasets || !out || n_datasets < 1 || n_chains < 1)
+    return fail(ctx, TPPMX_ERR_ARG, "null or empty argument");
+  const tppmx_dims &dm = *dims;
+  if (dm.nobs < 1 || dm.T < 1 || dm.T > TPPMX_MAXT || dm.D < 1 || dm.D > TPPMX_MAXD || dm.Q < 0 ||
+      dm.Q > TPPMX_MAXQ || dm.P < 0 || dm.ncat < 0 || dm.npred < 0 || dm.G < 1 || dm.ntmax < 1)
+    return fail(ctx, TPPMX_ERR_ARG, "dims out of range");
+  if (model->CC < 1 || model->CC > TPPMX_MAXCC) return fail(ctx, TPPMX_ERR_ARG, "CC out of range");
+  if (model->cohesion != 1 && model->cohesion != 2) return fail(ctx, TPPMX_ERR_ARG, "cohesion must be 1|2");
+  if (model->cohesion == 2 && !shared->logV) return fail(ctx, TPPMX_ERR_ARG, "cohesion 2 needs logV");
+  if (model->PPMx == 1 && (model->consim < 1 || model->consim > 2 || model->similarity < 1 || model->similarity > 2))
+    return fail(ctx, TPPMX_ERR_ARG, "consim/similarity must be 1|2");
+  if (dm.ncat > 0 && (dm.maxC < 1 || !shared->catvec)) return fail(ctx, TPPMX_ERR_ARG, "catvec/maxC");
+  if (dm.ncat > 0 && dm.npred > dm.nobs)
+    return fail(ctx, TPPMX_ERR_ARG, "ncat>0 needs npred<=nobs (reference indexes xcat with pp, dm_ppmx_ct.cpp:1157)");
+  CK(ctx, cudaSetDevice(ctx->device));
+
+  tppmx_batch *b = new tppmx_batch();
+  b->ctx = ctx;
+  b->dims = dm;
+  if (b->dims.kcap <= 0 || b->dims.kcap > dm.ntmax) b->dims.kcap = dm.ntmax;
+  b->last_ms = 0;
+  b->last_launches = 0;
+  b->scratch_chain = n_chains;
+  cudaEventCreate(&b->ev0);
+  cudaEventCreate(&b->ev1);
+  DevBatch &d = b->d;
+  memset(&d, 0, sizeof(d));
+  d.model = *model;
+  d.nobs = dm.nobs; d.T = dm.T; d.D = dm.D; d.Q = dm.Q; d.P = dm.P; d.ncat = dm.ncat;
+  d.maxC = dm.ncat > 0 ? dm.maxC : 0; d.npred = dm.npred; d.G = dm.G; d.ntmax = dm.ntmax;
+  d.kcap = b->dims.kcap; d.CC = model->CC; d.n_chains = n_chains; d.n_datasets = n_datasets;
+  const int nobs = d.nobs, T = d.T, D = d.D, Q = d.Q, P = d.P, ncat = d.ncat, npred = d.npred;
+  const int nc1 = ncat > 0 ? ncat : 1;
+  int rc = TPPMX_OK;
+#define TRY(x)                 \
+  do {                         \
+    rc = (x);                  \
+    if (rc) goto bad;          \
+  } while (0)
+
+  {
+    // shared
+    std::vector<int> catvec(nc1, 0);
+    for (int p = 0; p < ncat; p++) catvec[p] = shared->catvec[p];
+    std::vector<double> grid(shared->grid, shared->grid + 2 * (size_t)d.G);
+    TRY(dev_upload(b, &d.catvec, catvec));
+    TRY(dev_upload(b, &d.grid, grid));
+    if (model->cohesion == 2) {
+      std::vector<double> lv(shared->logV, shared->logV + (size_t)T * 2 * d.ntmax * d.G);
+      TRY(dev_upload(b, &d.logV, lv));
+    }
+    std::vector<NNRow> tab = build_nn_tab(*model, d.ntmax);
+    TRY(dev_upload(b, &d.nn_tab, tab));
+
+    // datasets
+    std::vector<int> arm_n((size_t)n_datasets * T, 0), arm_pat((size_t)n_datasets * T * d.ntmax, 0);
+    std::vector<int> treat((size_t)n_datasets * nobs), xcat((size_t)n_datasets * nobs * nc1, 0);
+    std::vector<double> x((size_t)n_datasets * nobs * P), x2(x.size()), z((size_t)n_datasets * nobs * Q);
+    std::vector<double> y((size_t)n_datasets * nobs * D);
+    std::vector<double> zp((size_t)n_datasets * npred * Q), xp((size_t)n_datasets * npred * P), xp2(xp.size());
+    std::vector<int> xcp((size_t)n_datasets * npred * nc1, 0);
+    for (int ds = 0; ds < n_datasets; ds++) {
+      const tppmx_dataset &s = datasets[ds];
+      if (!s.treat || !s.y || (Q > 0 && !s.z) || (P > 0 && !s.xcon) || (ncat > 0 && !s.xcat)) {
+        rc = fail(ctx, TPPMX_ERR_ARG, "dataset has null arrays");
+        goto bad;
+      }
+      for (int i = 0; i < nobs; i++) {
+        const int t = s.treat[i];
+        if (t < 0 || t >= T) { rc = fail(ctx, TPPMX_ERR_ARG, "treat out of range"); goto bad; }
+        int &na = arm_n[(size_t)ds * T + t];
+        if (na >= d.ntmax) { rc = fail(ctx, TPPMX_ERR_ARG, "an arm has more than ntmax patients"); goto bad; }
+        arm_pat[((size_t)ds * T + t) * d.ntmax + na] = i;
+        na++;
+        treat[(size_t)ds * nobs + i] = t;
+        for (int p = 0; p < P; p++) {
+          const double v = s.xcon[(size_t)i * P + p];
+          x[((size_t)ds * nobs + i) * P + p] = v;
+          x2[((size_t)ds * nobs + i) * P + p] = v * v;
+        }
+        for (int p = 0; p < ncat; p++) {
+          const int cv = s.xcat[(size_t)i * ncat + p];
+          if (cv < 0 || cv >= d.maxC) { rc = fail(ctx, TPPMX_ERR_ARG, "xcat out of range"); goto bad; }
+          xcat[((size_t)ds * nobs + i) * nc1 + p] = cv;
+        }
+        for (int q = 0; q < Q; q++) z[((size_t)ds * nobs + i) * Q + q] = s.z[i + (size_t)nobs * q];
+        for (int k = 0; k < D; k++) y[((size_t)ds * nobs + i) * D + k] = s.y[i + (size_t)nobs * k];
+      }
+      if (npred > 0 && ((Q > 0 && !s.zpred) || (P > 0 && !s.xconp) || (ncat > 0 && !s.xcatp))) {
+        rc = fail(ctx, TPPMX_ERR_ARG, "npred>0 but prediction arrays are null");
+        goto bad;
+      }
+      for (int pp = 0; pp < npred; pp++) {
+        for (int q = 0; q < Q; q++) zp[((size_t)ds * npred + pp) * Q + q] = s.zpred[pp + (size_t)npred * q];
+        for (int p = 0; p < P; p++) {
+          const double v = s.xconp[(size_t)pp * P + p];
+          xp[((size_t)ds * npred + pp) * P + p] = v;
+          xp2[((size_t)ds * npred + pp) * P + p] = v * v;
+        }
+        for (int p = 0; p < ncat; p++) {
+          const int cv = s.xcatp[(size_t)pp * ncat + p];
+          if (cv < 0 || cv >= d.maxC) { rc = fail(ctx, TPPMX_ERR_ARG, "xcatp out of range"); goto bad; }
+          xcp[((size_t)ds * npred + pp) * nc1 + p] = cv;
+        }
+      }
+    }
+    b->arm_n = arm_n;
+    TRY(dev_upload(b, &d.arm_n, arm_n));
+    TRY(dev_upload(b, &d.arm_pat, arm_pat));
+    TRY(dev_upload(b, &d.treat, treat));
+    TRY(dev_upload(b, &d.x, x));
+    TRY(dev_upload(b, &d.x2, x2));
+    TRY(dev_upload(b, &d.xcat, xcat));
+    TRY(dev_upload(b, &d.z, z));
+    TRY(dev_upload(b, &d.y, y));
+    TRY(dev_upload(b, &d.zpred, zp));
+    TRY(dev_upload(b, &d.xp, xp));
+    TRY(dev_upload(b, &d.xp2, xp2));
+    TRY(dev_upload(b, &d.xcatp, xcp));
+
+    // chains
+    const size_t ns = (size_t)n_chains + 1;
+    std::vector<int> cds(ns, 0);
+    std::vector<uint32_t> cid(ns, 0);
+    for (int c = 0; c < n_chains; c++) {
+      cds[c] = chain_dataset ? chain_dataset[c] : 0;
+      if (cds[c] < 0 || cds[c] >= n_datasets) { rc = fail(ctx, TPPMX_ERR_ARG, "chain_dataset out of range"); goto bad; }
+      cid[c] = chain_id ? (uint32_t)chain_id[c] : (uint32_t)c;
+    }
+    b->chain_ds = cds;
+    {
+      int *p1 = nullptr;
+      uint32_t *p2 = nullptr;
+      TRY(dev_alloc(b, &p1, ns, false));
+      TRY(dev_alloc(b, &p2, ns, false));
+      CK(ctx, cudaMemcpy(p1, cds.data(), ns * sizeof(int), cudaMemcpyHostToDevice));
+      CK(ctx, cudaMemcpy(p2, cid.data(), ns * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      d.chain_ds = p1;
+      d.chain_id = p2;
+    }
+    TRY(dev_alloc(b, &d.labels, ns * st_labels(d)));
+    TRY(dev_alloc(b, &d.nj, ns * st_nj(d)));
+    TRY(dev_alloc(b, &d.nclu, ns * T));
+    TRY(dev_alloc(b, &d.njc, ns * st_njc(d)));
+    TRY(dev_alloc(b, &d.idxs, ns));
+    TRY(dev_alloc(b, &d.status, ns));
+    TRY(dev_alloc(b, &d.sumx, ns * st_sumx(d)));
+    TRY(dev_alloc(b, &d.sumx2, ns * st_sumx(d)));
+    TRY(dev_alloc(b, &d.eta, ns * st_eta(d)));
+    TRY(dev_alloc(b, &d.etae, ns * st_etae(d)));
+    TRY(dev_alloc(b, &d.JJ, ns * st_pat(d)));
+    TRY(dev_alloc(b, &d.ss, ns * nobs));
+    TRY(dev_alloc(b, &d.lg, ns * st_pat(d)));
+    TRY(dev_alloc(b, &d.beta, ns * Q * D));
+    TRY(dev_alloc(b, &d.sigma, ns * T));
+    TRY(dev_alloc(b, &d.kappa, ns * T));
+    TRY(dev_alloc(b, &d.Theta, ns * T * D));
+    TRY(dev_alloc(b, &d.Sigma, ns * T * D * D));
+    TRY(dev_alloc(b, &d.lambda, ns * Q * D));
+    TRY(dev_alloc(b, &d.tau, ns));
+    TRY(dev_alloc(b, &d.sigma_beta, ns * Q * D));
+    TRY(dev_alloc(b, &d.zb, ns * st_pat(d)));
+    TRY(dev_alloc(b, &d.ljj, ns * st_pat(d)));
+    TRY(dev_alloc(b, &d.cpat, ns * nobs));
+    TRY(dev_alloc(b, &d.wbuf, ns * st_wbuf(d)));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  *out = b;
+  return TPPMX_OK;
+bad:
+  tppmx_batch_destroy(b);
+  return rc;
+#undef TRY
+}
+
+extern "C" int tppmx_batch_destroy(tppmx_batch *b) {
+  if (!b) return TPPMX_OK;
+  cudaSetDevice(b->ctx->device);
+  for (void *p : b->allocs) cudaFree(p);
+  cudaEventDestroy(b->ev0);
+  cudaEventDestroy(b->ev1);
+  delete b;
+  return TPPMX_OK;
+}
+
+// ---- state initialisation, reference src/dm_ppmx_ct.cpp:49-236 ------------------------------
+__global__ void init_kernel(DevBatch b, uint64_t seed, const int *init_labels, const int *init_nclu,
+                            const double *initbeta) {
+  const int chain = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int ds = b.chain_ds[chain];
+  const Rng rng = make_rng(seed, b.chain_id[chain]);
+  const int nobs = b.nobs, T = b.T, D = b.D, Q = b.Q, P = b.P, ks = b.kcap, CC = b.CC;
+  const int P1 = P > 0 ? P : 1, nc1 = b.ncat > 0 ? b.ncat * b.maxC : 1;
+  int *labels = b.labels + (size_t)chain * st_labels(b);
+  int *nj = b.nj + (size_t)chain * st_nj(b);
+  double *eta = b.eta + (size_t)chain * st_eta(b);
+  double *beta = b.beta + (size_t)chain * Q * D;
+
+  // :75-91 JJ = max(y, 1e-100), ss ~ Gamma(1, scale 1/TT)
+  for (int i = tid; i < nobs; i += nth) {
+    double TT = 0.0;
+    for (int k = 0; k < D; k++) {
+      double v = b.y[((size_t)ds * nobs + i) * D + k];
+      if (v < 1e-100) v = 1e-100;
+      b.JJ[((size_t)chain * nobs + i) * D + k] = v;
+      TT += v;
+    }
+    b.ss[(size_t)chain * nobs + i] = rng_gamma(rng, 0, TPPMX_SITE_INIT_SS, 0, (uint32_t)i, 1.0) * (1.0 / TT);
+  }
+  // :113-115 partition
+  for (int e = tid; e < T * b.ntmax; e += nth) labels[e] = init_labels[(size_t)ds * T * b.ntmax + e];
+  for (int e = tid; e < T; e += nth) {
+    b.nclu[(size_t)chain * T + e] = init_nclu[(size_t)ds * T + e];
+    b.sigma[(size_t)chain * T + e] = b.grid[0];  // :52-55
+    b.kappa[(size_t)chain * T + e] = b.grid[1];
+  }
+  if (tid == 0) {
+    b.idxs[chain] = 0;  // :49
+    b.tau[chain] = 1.0;
+    b.status[chain] = 0;
+  }
+  // :140 eta_star ~ U(0,1); :210 eta_empty ~ U(0,1)
+  for (int e = tid; e < T * D * ks; e += nth) {
+    const int t = e / (D * ks), k = (e / ks) % D, j = e % ks;
+    double u0, u1;
+    rng_u2(rng, 0, TPPMX_SITE_INIT_ETA, t, (uint32_t)(j * D + k), 0, u0, u1);
+    eta[e] = u0;
+  }
+  for (int e = tid; e < T * D * CC; e += nth) {
+    const int t = e / (D * CC), k = (e / CC) % D, mm = e % CC;
+    double u0, u1;
+    rng_u2(rng, 0, TPPMX_SITE_INIT_EMPTY, t, (uint32_t)(mm * D + k), 0, u0, u1);
+    b.etae[(size_t)chain * st_etae(b) + e] = u0;
+  }
+  // :149-155 beta, horseshoe scales; :271-278 Theta = 0, Sigma = I
+  for (int e = tid; e < Q * D; e += nth) {
+    beta[e] = initbeta[e];
+    b.sigma_beta[(size_t)chain * Q * D + e] = 1.0;
+    b.lambda[(size_t)chain * Q * D + e] = 1.0;
+  }
+  for (int e = tid; e < T * D; e += nth) b.Theta[(size_t)chain * T * D + e] = 0.0;
+  for (int e = tid; e < T * D * D; e += nth) {
+    const int a = e % D, c = (e / D) % D;
+    b.Sigma[(size_t)chain * T * D * D + e] = (a == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  // cluster sizes and sufficient statistics of the initial partition (:187-204); patients are
+  // accumulated in arm order so the sums are bit-identical to a sequential pass.
+  for (int e = tid; e < T * ks; e += nth) {
+    const int t = e / ks, j = e % ks;
+    const int nt = b.arm_n[(size_t)ds * T + t];
+    int cnt = 0;
+    for (int it = 0; it < nt; it++) cnt += (labels[t * b.ntmax + it] == j + 1);
+    nj[e] = cnt;
+  }
+  for (int e = tid; e < T * P1 * ks; e += nth) {
+    double s1 = 0.0, s2 = 0.0;
+    if (b.model.PPMx == 1 && P > 0) {
+      const int t = e / (P * ks), p = (e / ks) % P, j = e % ks;
+      const int nt = b.arm_n[(size_t)ds * T + t];
+      for (int it = 0; it < nt; it++)
+        if (labels[t * b.ntmax + it] == j + 1) {
+          const int i = b.arm_pat[((size_t)ds * T + t) * b.ntmax + it];
+          s1 = __dadd_rn(s1, b.x[((size_t)ds * nobs + i) * P + p]);
+          s2 = __dadd_rn(s2, b.x2[((size_t)ds * nobs + i) * P + p]);
+        }
+    }
+    b.sumx[(size_t)chain * st_sumx(b) + e] = s1;
+    b.sumx2[(size_t)chain * st_sumx(b) + e] = s2;
+  }
+  for (int e = tid; e < T * nc1 * ks; e += nth) {
+    int cnt = 0;
+    if (b.model.PPMx == 1 && b.ncat > 0) {
+      const int t = e / (nc1 * ks), pc = (e / ks) % nc1, j = e % ks;
+      const int p = pc / b.maxC, c = pc % b.maxC;
+      const int nt = b.arm_n[(size_t)ds * T + t];
+      for (int it = 0; it < nt; it++)
+        if (labels[t * b.ntmax + it] == j + 1) {
+          const int i = b.arm_pat[((size_t)ds * T + t) * b.ntmax + it];
+          cnt += (b.xcat[((size_t)ds * nobs + i) * b.ncat + p] == c);
+        }
+    }
+    b.njc[(size_t)chain * st_njc(b) + e] = cnt;
+  }
+  // :161-173 loggamma (same operation order as calculate_gamma, utils_ct.cpp:514-527)
+  for (int e = tid; e < nobs * D; e += nth) {
+    const int i = e / D, k = e % D;
+    const int t = b.treat[(size_t)ds * nobs + i];
+    int it = 0;  // position of i in its arm
+    const int *pat = b.arm_pat + ((size_t)ds * T + t) * b.ntmax;
+    const int nt = b.arm_n[(size_t)ds * T + t];
+    for (int r = 0; r < nt; r++)
+      if (pat[r] == i) it = r;
+    const int lab = labels[t * b.ntmax + it];
+    double lg = eta[((size_t)t * D + k) * ks + lab - 1];
+    for (int q = 0; q < Q; q++)
+      lg = __dadd_rn(lg, __dmul_rn(beta[k + q * D], b.z[((size_t)ds * nobs + i) * Q + q]));
+    b.lg[((size_t)chain * nobs + i) * D + k] = lg;
+  }
+}
+
+extern "C" int tppmx_batch_init(tppmx_batch *b, uint64_t seed, const int32_t *init_labels,
+                                const int32_t *init_nclu, const double *initbeta) {
+  if (!b) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  if (!init_labels || !init_nclu || (!initbeta && b->d.Q > 0)) return fail(ctx, TPPMX_ERR_ARG, "null init argument");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const DevBatch &d = b->d;
+  const int nd = d.n_datasets, T = d.T, nt = d.ntmax;
+  std::vector<int> lab((size_t)nd * T * nt), ncl((size_t)nd * T);
+  for (int ds = 0; ds < nd; ds++)
+    for (int t = 0; t < T; t++) {
+      const int K = init_nclu[(size_t)ds * T + t];
+      if (K < 1 || K > d.kcap) return fail(ctx, TPPMX_ERR_ARG, "init_nclu out of range (1..kcap)");
+      ncl[(size_t)ds * T + t] = K;
+      const int na = b->arm_n[(size_t)ds * T + t];
+      for (int it = 0; it < nt; it++) {
+        const int v = init_labels[(size_t)ds * T * nt + t + (size_t)T * it];
+        if (it < na && (v < 1 || v > K)) return fail(ctx, TPPMX_ERR_ARG, "init_labels out of range");
+        lab[((size_t)ds * T + t) * nt + it] = v;
+      }
+    }
+  int *dl = nullptr, *dn = nullptr;
+  double *db = nullptr;
+  CK(ctx, cudaMalloc(&dl, lab.size() * sizeof(int)));
+  CK(ctx, cudaMalloc(&dn, ncl.size() * sizeof(int)));
+  CK(ctx, cudaMalloc(&db, (size_t)(d.Q * d.D + 1) * sizeof(double)));
+  CK(ctx, cudaMemcpy(dl, lab.data(), lab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(ctx, cudaMemcpy(dn, ncl.data(), ncl.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (d.Q > 0) CK(ctx, cudaMemcpy(db, initbeta, (size_t)d.Q * d.D * sizeof(double), cudaMemcpyHostToDevice));
+  init_kernel<<<d.n_chains, 128, 0, ctx->stream>>>(d, seed, dl, dn, db);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dl);
+  cudaFree(dn);
+  cudaFree(db);
+  if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("init_kernel: ") + cudaGetErrorString(e));
+  CK(ctx, cudaGetLastError());
+  return TPPMX_OK;
+}
+
+// ---- state upload / download (reference layouts <-> device layouts) --------------------------
+template <class T>
+static int h2d(tppmx_batch *b, T *dst, const std::vector<T> &h) {
+  CK(b->ctx, cudaMemcpy(dst, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return TPPMX_OK;
+}
+template <class T>
+static int d2h(tppmx_batch *b, std::vector<T> &h, const T *src) {
+  CK(b->ctx, cudaMemcpy(h.data(), src, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_set_state(tppmx_batch *b, int32_t chain, const tppmx_state *s) {
+  if (!b || !s) return TPPMX_ERR_ARG;
+  const DevBatch &d = b->d;
+  if (chain < 0 || chain >= d.n_chains) return fail(b->ctx, TPPMX_ERR_ARG, "chain out of range");
+  CK(b->ctx, cudaSetDevice(b->ctx->device));
+  const int T = d.T, nt = d.ntmax, ks = d.kcap, P = d.P, D = d.D, Q = d.Q, n = d.nobs, CC = d.CC;
+  const int ncat = d.ncat, mC = d.maxC;
+  if (s->nclu)
+    for (int t = 0; t < T; t++)
+      if (s->nclu[t] < 0 || s->nclu[t] > ks) return fail(b->ctx, TPPMX_ERR_CAPACITY, "nclu exceeds kcap");
+  if (s->labels) {
+    std::vector<int> h(st_labels(d));
+    for (int t = 0; t < T; t++)
+      for (int it = 0; it < nt; it++) h[(size_t)t * nt + it] = s->labels[t + (size_t)T * it];
+    RC(h2d(b, d.labels + (size_t)chain * st_labels(d), h));
+  }
+  if (s->nj) {
+    std::vector<int> h(st_nj(d));
+    for (int t = 0; t < T; t++)
+      for (int j = 0; j < ks; j++) h[(size_t)t * ks + j] = s->nj[t + (size_t)T * j];
+    RC(h2d(b, d.nj + (size_t)chain * st_nj(d), h));
+  }
+  if (s->nclu) {
+    std::vector<int> h(s->nclu, s->nclu + T);
+    RC(h2d(b, d.nclu + (size_t)chain * T, h));
+  }
+  for (int which = 0; which < 2; which++) {
+    const double *src = which ? s->sumx2 : s->sumx;
+    if (!src || P == 0) continue;
+    std::vector<double> h(st_sumx(d));
+    for (int t = 0; t < T; t++)
+      for (int p = 0; p < P; p++)
+        for (int j = 0; j < ks; j++) h[((size_t)t * P + p) * ks + j] = src[t + (size_t)T * ((size_t)j * P + p)];
+    RC(h2d(b, (which ? d.sumx2 : d.sumx) + (size_t)chain * st_sumx(d), h));
+  }
+  if (s->njc && ncat > 0) {
+    std::vector<int> h(st_njc(d));
+    for (int t = 0; t < T; t++)
+      for (int p = 0; p < ncat; p++)
+        for (int c = 0; c < mC; c++)
+          for (int j = 0; j < ks; j++)
+            h[(((size_t)t * ncat + p) * mC + c) * ks + j] = s->njc[t + (size_t)T * (((size_t)j * ncat + p) * mC + c)];
+    RC(h2d(b, d.njc + (size_t)chain * st_njc(d), h));
+  }
+  if (s->eta_star) {
+    std::vector<double> h(st_eta(d));
+    for (int t = 0; t < T; t++)
+      for (int k = 0; k < D; k++)
+        for (int j = 0; j < ks; j++) h[((size_t)t * D + k) * ks + j] = s->eta_star[k + (size_t)D * (j + (size_t)nt * t)];
+    RC(h2d(b, d.eta + (size_t)chain * st_eta(d), h));
+  }
+  if (s->eta_empty) {
+    std::vector<double> h(st_etae(d));
+    for (int t = 0; t < T; t++)
+      for (int k = 0; k < D; k++)
+        for (int m = 0; m < CC; m++) h[((size_t)t * D + k) * CC + m] = s->eta_empty[k + (size_t)D * (m + (size_t)CC * t)];
+    RC(h2d(b, d.etae + (size_t)chain * st_etae(d), h));
+  }
+  for (int which = 0; which < 2; which++) {
+    const double *src = which ? s->loggamma : s->JJ;
+    if (!src) continue;
+    std::vector<double> h(st_pat(d));
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < D; k++) h[(size_t)i * D + k] = src[i + (size_t)n * k];
+    RC(h2d(b, (which ? d.lg : d.JJ) + (size_t)chain * st_pat(d), h));
+  }
+#define PUT(field, dptr, count)                                                        \
+  if (s->field && (count) > 0) {                                                       \
+    CK(b->ctx, cudaMemcpy((dptr) + (size_t)chain * (count), s->field, sizeof(*s->field) * (count), cudaMemcpyHostToDevice)); \
+  }
+  PUT(ss, d.ss, (size_t)n);
+  PUT(beta, d.beta, (size_t)Q * D);
+  PUT(sigma, d.sigma, (size_t)T);
+  PUT(kappa, d.kappa, (size_t)T);
+  PUT(idxs, d.idxs, (size_t)1);
+  PUT(Theta, d.Theta, (size_t)T * D);
+  PUT(Sigma, d.Sigma, (size_t)T * D * D);
+  PUT(lambda, d.lambda, (size_t)Q * D);
+  PUT(tau, d.tau, (size_t)1);
+  PUT(sigma_beta, d.sigma_beta, (size_t)Q * D);
+#undef PUT
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_get_state(tppmx_batch *b, int32_t chain, tppmx_state *s) {
+  if (!b || !s) return TPPMX_ERR_ARG;
+  const DevBatch &d = b->d;
+  if (chain < 0 || chain >= d.n_chains) return fail(b->ctx, TPPMX_ERR_ARG, "chain out of range");
+  CK(b->ctx, cudaSetDevice(b->ctx->device));
+  CK(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+  const int T = d.T, nt = d.ntmax, ks = d.kcap, P = d.P, D = d.D, Q = d.Q, n = d.nobs, CC = d.CC;
+  const int ncat = d.ncat, mC = d.maxC;
+  if (s->labels) {
+    std::vector<int> h(st_labels(d));
+    RC(d2h(b, h, d.labels + (size_t)chain * st_labels(d)));
+    for (int t = 0; t < T; t++)
+      for (int it = 0; it < nt; it++) s->labels[t + (size_t)T * it] = h[(size_t)t * nt + it];
+  }
+  if (s->nj) {
+    std::vector<int> h(st_nj(d));
+    RC(d2h(b, h, d.nj + (size_t)chain * st_nj(d)));
+    for (int t = 0; t < T; t++)
+      for (int j = 0; j < nt; j++) s->nj[t + (size_t)T * j] = j < ks ? h[(size_t)t * ks + j] : 0;
+  }
+  if (s->nclu) CK(b->ctx, cudaMemcpy(s->nclu, d.nclu + (size_t)chain * T, sizeof(int) * T, cudaMemcpyDeviceToHost));
+  for (int which = 0; which < 2; which++) {
+    double *dst = which ? s->sumx2 : s->sumx;
+    if (!dst || P == 0) continue;
+    std::vector<double> h(st_sumx(d));
+    RC(d2h(b, h, (which ? d.sumx2 : d.sumx) + (size_t)chain * st_sumx(d)));
+    for (int t = 0; t < T; t++)
+      for (int p = 0; p < P; p++)
+        for (int j = 0; j < nt; j++)
+          dst[t + (size_t)T * ((size_t)j * P + p)] = j < ks ? h[((size_t)t * P + p) * ks + j] : 0.0;
+  }
+  if (s->njc && ncat > 0) {
+    std::vector<int> h(st_njc(d));
+    RC(d2h(b, h, d.njc + (size_t)chain * st_njc(d)));
+    for (int t = 0; t < T; t++)
+      for (int p = 0; p < ncat; p++)
+        for (int c = 0; c < mC; c++)
+          for (int j = 0; j < nt; j++)
+            s->njc[t + (size_t)T * (((size_t)j * ncat + p) * mC + c)] =
+                j < ks ? h[(((size_t)t * ncat + p) * mC + c) * ks + j] : 0;
+  }
+  if (s->eta_star) {
+    std::vector<double> h(st_eta(d));
+    RC(d2h(b, h, d.eta + (size_t)chain * st_eta(d)));
+    for (int t = 0; t < T; t++)
+      for (int k = 0; k < D; k++)
+        for (int j = 0; j < nt; j++)
+          s->eta_star[k + (size_t)D * (j + (size_t)nt * t)] = j < ks ? h[((size_t)t * D + k) * ks + j] : 0.0;
+  }
+  if (s->eta_empty) {
+    std::vector<double> h(st_etae(d));
+    RC(d2h(b, h, d.etae + (size_t)chain * st_etae(d)));
+    for (int t = 0; t < T; t++)
+      for (int k = 0; k < D; k++)
+        for (int m = 0; m < CC; m++) s->eta_empty[k + (size_t)D * (m + (size_t)CC * t)] = h[((size_t)t * D + k) * CC + m];
+  }
+  for (int which = 0; which < 2; which++) {
+    double *dst = which ? s->loggamma : s->JJ;
+    if (!dst) continue;
+    std::vector<double> h(st_pat(d));
+    RC(d2h(b, h, (which ? d.lg : d.JJ) + (size_t)chain * st_pat(d)));
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < D; k++) dst[i + (size_t)n * k] = h[(size_t)i * D + k];
+  }
+#define GET(field, dptr, count)                                                        \
+  if (s->field && (count) > 0) {                                                       \
+    CK(b->ctx, cudaMemcpy(s->field, (dptr) + (size_t)chain * (count), sizeof(*s->field) * (count), cudaMemcpyDeviceToHost)); \
+  }
+  GET(ss, d.ss, (size_t)n);
+  GET(beta, d.beta, (size_t)Q * D);
+  GET(sigma, d.sigma, (size_t)T);
+  GET(kappa, d.kappa, (size_t)T);
+  GET(idxs, d.idxs, (size_t)1);
+  GET(Theta, d.Theta, (size_t)T * D);
+  GET(Sigma, d.Sigma, (size_t)T * D * D);
+  GET(lambda, d.lambda, (size_t)Q * D);
+  GET(tau, d.tau, (size_t)1);
+  GET(sigma_beta, d.sigma_beta, (size_t)Q * D);
+#undef GET
+  return TPPMX_OK;
+}
+
+// ---- launches ---------------------------------------------------------------------------------
+static int check_status(tppmx_batch *b) {
+  std::vector<int> st((size_t)b->d.n_chains);
+  CK(b->ctx, cudaMemcpy(st.data(), b->d.status, st.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  for (size_t c = 0; c < st.size(); c++)
+    if (st[c] != 0) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "chain %zu needed more than kcap=%d clusters in one arm", c, b->d.kcap);
+      return fail(b->ctx, st[c], buf);
+    }
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps) {
+  if (!b || n_sweeps < 0) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
+  sweep_kernel<<<b->d.n_chains, 32 * b->d.T, 0, ctx->stream>>>(b->d, seed, iter0, n_sweeps);
+  CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  b->last_ms = ms;
+  b->last_launches = 1;
+  return check_status(b);
+}
+
+extern "C" int tppmx_batch_last_timing(const tppmx_batch *b, double *ms, int32_t *launches) {
+  if (!b) return TPPMX_ERR_ARG;
+  if (ms) *ms = b->last_ms;
+  if (launches) *launches = b->last_launches;
+  return TPPMX_OK;
+}
+
+// copy every per-chain field of `src` into the scratch slot
+static int copy_chain_to_scratch(tppmx_batch *b, int src) {
+  const DevBatch &d = b->d;
+  const int dst = b->scratch_chain;
+  cudaStream_t st = b->ctx->stream;
+#define CP(ptr, count)                                                                         \
+  CK(b->ctx, cudaMemcpyAsync((ptr) + (size_t)dst * (count), (ptr) + (size_t)src * (count),      \
+                             sizeof(*(ptr)) * (count), cudaMemcpyDeviceToDevice, st))
+  CP(d.labels, st_labels(d)); CP(d.nj, st_nj(d)); CP(d.nclu, (size_t)d.T); CP(d.njc, st_njc(d));
+  CP(d.idxs, (size_t)1); CP(d.sumx, st_sumx(d)); CP(d.sumx2, st_sumx(d)); CP(d.eta, st_eta(d));
+  CP(d.etae, st_etae(d)); CP(d.JJ, st_pat(d)); CP(d.ss, (size_t)d.nobs); CP(d.lg, st_pat(d));
+  CP(d.beta, (size_t)d.Q * d.D); CP(d.sigma, (size_t)d.T); CP(d.kappa, (size_t)d.T);
+  CP(d.Theta, (size_t)d.T * d.D); CP(d.Sigma, (size_t)d.T * d.D * d.D);
+#undef CP
+  // the scratch slot reads the same dataset and RNG stream as `src`
+  CK(b->ctx, cudaMemcpyAsync((int *)d.chain_ds + dst, d.chain_ds + src, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  CK(b->ctx, cudaMemcpyAsync((uint32_t *)d.chain_id + dst, d.chain_id + src, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_score_patient(tppmx_batch *b, int32_t chain, int32_t arm, int32_t it,
+                                   uint64_t seed, int32_t iter, double *logw_out, double *prob_out,
+                                   int32_t *K_out) {
+  if (!b) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (chain < 0 || chain >= d.n_chains || arm < 0 || arm >= d.T) return fail(ctx, TPPMX_ERR_ARG, "chain/arm out of range");
+  const int ds = b->chain_ds[chain];
+  if (it < 0 || it >= b->arm_n[(size_t)ds * d.T + arm]) return fail(ctx, TPPMX_ERR_ARG, "it out of range");
+  CK(ctx, cudaSetDevice(ctx->device));
+  RC(copy_chain_to_scratch(b, chain));
+  const int W = d.kcap + d.CC;
+  double *dw = nullptr;
+  int *dk = nullptr;
+  CK(ctx, cudaMalloc(&dw, sizeof(double) * 2 * W));
+  CK(ctx, cudaMalloc(&dk, sizeof(int)));
+  score_kernel<<<1, 32, 0, ctx->stream>>>(d, b->scratch_chain, arm, it, seed, iter, dw, dw + W, dk);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  int K = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&K, dk, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && logw_out) e = cudaMemcpy(logw_out, dw, sizeof(double) * (K + d.CC), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && prob_out) e = cudaMemcpy(prob_out, dw + W, sizeof(double) * (K + d.CC), cudaMemcpyDeviceToHost);
+  cudaFree(dw);
+  cudaFree(dk);
+  if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("score_kernel: ") + cudaGetErrorString(e));
+  if (K_out) *K_out = K;
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, double *pipred,
+                                   double *ypred, int32_t *predclass) {
+  if (!b) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (d.npred < 1) return fail(ctx, TPPMX_ERR_ARG, "batch has npred == 0");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t n1 = (size_t)d.n_chains * d.npred * d.D * d.T, n2 = (size_t)d.n_chains * d.npred * d.T;
+  double *dpi = nullptr, *dy = nullptr;
+  int *dc = nullptr;
+  if (pipred) CK(ctx, cudaMalloc(&dpi, n1 * sizeof(double)));
+  if (ypred) CK(ctx, cudaMalloc(&dy, n1 * sizeof(double)));
+  if (predclass) CK(ctx, cudaMalloc(&dc, n2 * sizeof(int)));
+  CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
+  predict_kernel<<<dim3(d.n_chains, d.T), 128, 0, ctx->stream>>>(d, seed, iter, dpi, dy, dc);
+  CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && pipred) e = cudaMemcpy(pipred, dpi, n1 * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && ypred) e = cudaMemcpy(ypred, dy, n1 * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && predclass) e = cudaMemcpy(predclass, dc, n2 * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(dpi);
+  cudaFree(dy);
+  cudaFree(dc);
+  if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("predict_kernel: ") + cudaGetErrorString(e));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+  b->last_ms = ms;
+  b->last_launches = 1;
+  return TPPMX_OK;
+}

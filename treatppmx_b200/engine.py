@@ -1,0 +1,123 @@
+"""Host-side handles over the C ABI (include/tppmx.h): a device context and a batch of chains.
+Thin: argument marshalling and error mapping only; every number is computed by the CUDA
+library."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._abi import (Dataset, Dims, HostDataset, HostShared, HostState, Model, c_dp, c_ip)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.L = _lib.load()
+        self.h = C.c_void_p()
+        rc = self.L.tppmx_create(C.byref(self.h), device)
+        if rc != 0:
+            raise _lib.TppmxError(rc, "tppmx_create failed (no usable CUDA device?)")
+        self.device = device
+
+    def err(self) -> str:
+        return self.L.tppmx_last_error(self.h).decode()
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise _lib.TppmxError(rc, self.err())
+
+    def close(self):
+        if self.h:
+            self.L.tppmx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """n_chains independent chains over n_datasets replicate datasets on one GPU."""
+
+    def __init__(self, ctx: Context, model: Model, dims: Dims, shared: HostShared,
+                 datasets: list[HostDataset], chain_dataset, chain_id=None):
+        self.ctx, self.model, self.dims, self.shared, self.datasets = ctx, model, dims, shared, datasets
+        self.chain_dataset = np.ascontiguousarray(chain_dataset, dtype=np.int32)
+        self.n_chains = int(self.chain_dataset.size)
+        self.chain_id = (np.arange(self.n_chains, dtype=np.int32) if chain_id is None
+                         else np.ascontiguousarray(chain_id, dtype=np.int32))
+        arr = (Dataset * len(datasets))(*[d.cstruct() for d in datasets])
+        sh = shared.cstruct()
+        self.h = C.c_void_p()
+        ctx.check(ctx.L.tppmx_batch_create(
+            ctx.h, C.byref(model), C.byref(dims), C.byref(sh), len(datasets), arr, self.n_chains,
+            self.chain_dataset.ctypes.data_as(c_ip), self.chain_id.ctypes.data_as(c_ip),
+            C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.ctx.L.tppmx_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self, seed: int, init_labels, init_nclu, initbeta):
+        """init_labels: [n_datasets] x (T x ntmax F-order) or one array broadcast to all."""
+        nd, T, nt = len(self.datasets), self.dims.T, self.dims.ntmax
+        il = np.asarray(init_labels, dtype=np.int32)
+        if il.ndim == 2:
+            il = np.broadcast_to(il, (nd, T, nt))
+        il = np.ascontiguousarray(np.stack([np.asfortranarray(a).ravel(order="F") for a in il]))
+        ic = np.asarray(init_nclu, dtype=np.int32)
+        if ic.ndim == 1:
+            ic = np.broadcast_to(ic, (nd, T))
+        ic = np.ascontiguousarray(ic)
+        ib = np.ascontiguousarray(initbeta, dtype=np.float64)
+        self.ctx.check(self.ctx.L.tppmx_batch_init(
+            self.h, seed, il.ctypes.data_as(c_ip), ic.ctypes.data_as(c_ip), ib.ctypes.data_as(c_dp)))
+
+    def set_state(self, chain: int, st: HostState):
+        cs = st.cstruct()
+        self.ctx.check(self.ctx.L.tppmx_batch_set_state(self.h, chain, C.byref(cs)))
+
+    def get_state(self, chain: int) -> HostState:
+        st = HostState(self.dims, self.model.CC)
+        cs = st.cstruct()
+        self.ctx.check(self.ctx.L.tppmx_batch_get_state(self.h, chain, C.byref(cs)))
+        return st
+
+    def score_patient(self, chain: int, arm: int, it: int, seed: int = 0, iter_: int = 0):
+        n = self.dims.ntmax + self.model.CC
+        logw, prob, K = np.zeros(n), np.zeros(n), C.c_int32(0)
+        self.ctx.check(self.ctx.L.tppmx_score_patient(
+            self.h, chain, arm, it, seed, iter_, logw.ctypes.data_as(c_dp),
+            prob.ctypes.data_as(c_dp), C.byref(K)))
+        k = K.value + self.model.CC
+        return logw[:k], prob[:k], K.value
+
+    def sweep(self, seed: int, iter0: int, n_sweeps: int):
+        self.ctx.check(self.ctx.L.tppmx_batch_sweep(self.h, seed, iter0, n_sweeps))
+
+    def last_timing(self):
+        ms, n = C.c_double(0), C.c_int32(0)
+        self.ctx.check(self.ctx.L.tppmx_batch_last_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def predict(self, seed: int, iter_: int, want=("pipred", "ypred", "predclass")):
+        d, nc = self.dims, self.n_chains
+        pipred = np.zeros((nc, d.T, d.D, d.npred)) if "pipred" in want else None
+        ypred = np.zeros((nc, d.T, d.D, d.npred)) if "ypred" in want else None
+        pc = np.zeros((nc, d.T, d.npred), dtype=np.int32) if "predclass" in want else None
+        f = lambda a, t: a.ctypes.data_as(t) if a is not None else t()
+        self.ctx.check(self.ctx.L.tppmx_batch_predict(
+            self.h, seed, iter_, f(pipred, c_dp), f(ypred, c_dp), f(pc, c_ip)))
+        # C-order [chain][T][D][npred] is the col-major npred x D x T cube of the reference
+        tr = lambda a: None if a is None else a.transpose(0, 3, 2, 1)
+        return tr(pipred), tr(ypred), None if pc is None else pc.transpose(0, 2, 1)
