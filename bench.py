@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the PPMx reallocation sweep (+ predictive step) on B200.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            # the CPU arm (oracle port, all host threads)
+
+Workload (config.workload): genmech-style synthetic data of BASELINE.json's shapes
+(n=152 patients, T=3 arms, P=10 predictive + Q=2 prognostic biomarkers, D=3 outcome
+categories, npred=28 new patients), 1024 independent chains per GPU = 256 replicate datasets
+x 4 chains (the package's simulation-study workload), NGG cohesion, default ppmxct() switches.
+A "step" = `--sweeps` Gibbs reallocation sweeps of every chain (one launch of the persistent
+sweep kernel) ; metric = patient-reallocations / s.
+
+  value  : device-resident — chain state and data already in HBM, CUDA events on the
+           library's launching stream around the sweep kernel, L2 flushed between steps
+  e2e    : the same work through the public host API with HOST buffers: batch create (H2D of
+           every input), init, sweeps, predictive, download of partitions + predictive
+           probabilities (D2H), destroy — wall clock around the whole call
+  roofline / cpu_baseline : see DESIGN.md §Measurement
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "patient_reallocations_per_sec"
+UNIT = "reallocations/s"
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def build_workload(args, rank: int):
+    from treatppmx_b200 import datagen
+    from treatppmx_b200._abi import default_model
+
+    model = default_model(cohesion=args.cohesion)
+    nd = args.datasets
+    dims_kw, dsets, ex = datagen.genmech_synthetic(
+        n=args.n, npred=args.npred, P=args.P, Q=args.Q, T=args.T, n_datasets=nd,
+        seed=20240001 + 1000 * rank, mixture=args.mixture)
+    dims = datagen.make_dims(G=100, kcap=args.kcap, **dims_kw)
+    shared = datagen.make_shared(dims, ex["n_a"], cohesion=model.cohesion,
+                                 kmax=(args.kcap if args.kcap > 0 else None))
+    labels, nclu = datagen.initial_partition(dsets[0].treat, dims.T, dims.ntmax)
+    beta0 = datagen.init_beta(dsets[0])
+    chain_ds = np.repeat(np.arange(nd, dtype=np.int32), args.chains_per_dataset)
+    chain_id = (np.arange(chain_ds.size, dtype=np.int32) + rank * chain_ds.size)
+    return dict(model=model, dims=dims, shared=shared, dsets=dsets, labels=labels, nclu=nclu,
+                beta0=beta0, chain_ds=chain_ds, chain_id=chain_id, n_a=ex["n_a"])
+
+
+def algorithmic_bytes_per_realloc(dims, CC: int, Kbar: float) -> float:
+    """compulsory fp64 state traffic of one Gibbs step."""
+    P, Q, D, ncat, C = dims.P, dims.Q, dims.D, dims.ncat, dims.maxC
+    return (8.0 * (Kbar * (2 * P + 1 + D) + CC * D) + 8.0 * (P + Q + 3 * D + 1)
+            + 4.0 * ncat * (Kbar * C + 1) + 8.0 + 32.0 * P)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (test infrastructure used as the checker/baseline)
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_rate(w, n_threads: int, target_s: float, sweeps_hint: int = 0):
+    """Runs one chain per thread (the reference is single-threaded per chain) for a bounded
+    number of sweeps; returns (reallocations/s aggregate, description, seconds)."""
+    import oracle_binding as ob
+    from concurrent.futures import ThreadPoolExecutor
+
+    model, dims = w["model"], w["dims"]
+    pbs = [ob.Problem(model, dims, w["shared"], w["dsets"][i % len(w["dsets"])]) for i in range(n_threads)]
+    sts = [pbs[i].init_state(7, i, w["labels"], w["nclu"], w["beta0"]) for i in range(n_threads)]
+    t0 = time.perf_counter()
+    pbs[0].sweep(sts[0], 7, 0, 0, 2)  # calibration (also burn-in of 2 sweeps for chain 0)
+    per_sweep = (time.perf_counter() - t0) / 2
+    nsw = sweeps_hint if sweeps_hint > 0 else max(2, int(target_s / max(per_sweep, 1e-6)))
+
+    def work(i):
+        pbs[i].sweep(sts[i], 7, i, 2, nsw)  # ctypes releases the GIL during the call
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as ex:
+        list(ex.map(work, range(n_threads)))
+    dt = time.perf_counter() - t0
+    rate = n_threads * nsw * dims.nobs / dt
+    return rate, f"{n_threads} chains (one per thread) x {nsw} sweeps x {dims.nobs} patients of the bench workload", dt, nsw
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    w = build_workload(args, 0)
+    ncores = os.cpu_count() or 1
+    # each step is a bounded sample: ~ (target) seconds of all-core work
+    total_budget = 60.0
+    per_step = max(1.0, total_budget / max(args.steps + args.warmup, 1))
+    rates, secs, nsw = [], [], 0
+    for s in range(args.warmup + args.steps):
+        r, desc, dt, nsw = cpu_oracle_rate(w, ncores, per_step, sweeps_hint=nsw)
+        if s >= args.warmup:
+            rates.append(r)
+            secs.append(dt)
+    tot_work = len(rates) * ncores * nsw * w["dims"].nobs
+    value = tot_work / sum(secs)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, w),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port",
+                         "sample": desc + f", {len(rates)} timed steps; the reference (R/Rcpp) cannot be built in this image, "
+                         "the port passes arrays by reference and is faster than the real Rcpp build"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, w):
+    d = w["dims"]
+    return {
+        "workload": (f"genmech-synthetic n={d.nobs} T={d.T} P={d.P} Q={d.Q} D={d.D} npred={d.npred}; "
+                     f"{args.datasets} replicate datasets x {args.chains_per_dataset} chains = "
+                     f"{args.datasets * args.chains_per_dataset} chains per GPU; cohesion={'NGG' if args.cohesion == 2 else 'DP'}, "
+                     f"similarity=NN auxiliary, CC=3, reuse=1"),
+        "chains_per_gpu": args.datasets * args.chains_per_dataset,
+        "sweeps_per_step": args.sweeps,
+        "kcap": int(d.kcap) if d.kcap > 0 else int(d.ntmax),
+        "l2": "256 MiB buffer written between timed steps (outside the event brackets)",
+        "sharding": "chains/datasets sharded across ranks, no data-path collective",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------
+def e2e_call(ctx, w, seed: int, n_sweeps: int):
+    """The public call a user makes, with host buffers in and host arrays out."""
+    from treatppmx_b200.engine import Batch
+    b = Batch(ctx, w["model"], w["dims"], w["shared"], w["dsets"], chain_dataset=w["chain_ds"],
+              chain_id=w["chain_id"])
+    b.init(seed, w["labels"], w["nclu"], w["beta0"])
+    b.sweep(seed, 0, n_sweeps)
+    launches = 2  # init + sweep
+    pi = None
+    if w["dims"].npred > 0:
+        pi, _, _ = b.predict(seed, n_sweeps, want=("pipred",))
+        launches += 1
+    lab, ncl = b.get_partitions()
+    b.close()
+    return lab, ncl, pi, launches
+
+
+def e2e_bytes(w, lab, ncl, pi):
+    h2d = 0
+    for ds in w["dsets"]:
+        for a in (ds.treat, ds.y, ds.z, ds.xcon, ds.zpred, ds.xconp):
+            h2d += a.nbytes
+        if w["dims"].ncat > 0:
+            h2d += ds.xcat.nbytes + ds.xcatp.nbytes
+    sh = w["shared"]
+    h2d += sh.grid.nbytes + (sh.logV.nbytes if sh.logV is not None else 0)
+    h2d += w["labels"].nbytes * len(w["dsets"]) + w["nclu"].nbytes * len(w["dsets"]) + w["beta0"].nbytes
+    h2d += w["chain_ds"].nbytes + w["chain_id"].nbytes
+    d2h = lab.nbytes + ncl.nbytes + (pi.nbytes if pi is not None else 0)
+    return int(h2d), int(d2h)
+
+
+def run_native(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CUDA library is the only compute path (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from treatppmx_b200.engine import Batch, Context
+
+    w = build_workload(args, rank)
+    dims, model = w["dims"], w["model"]
+    nchains = int(w["chain_ds"].size)
+    ctx = Context(local_rank)
+    batch = Batch(ctx, model, dims, w["shared"], w["dsets"], chain_dataset=w["chain_ds"], chain_id=w["chain_id"])
+    seed = 20240001
+    batch.init(seed, w["labels"], w["nclu"], w["beta0"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # burn-in so K has settled before anything is timed (not part of warm-up accounting)
+    it = 0
+    batch.sweep(seed, it, args.burn)
+    it += args.burn
+    for _ in range(args.warmup):
+        batch.sweep(seed, it, args.sweeps)
+        it += args.sweeps
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    ms_steps, launches = [], 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        batch.sweep(seed, it, args.sweeps)  # events on the library's stream bracket the kernel
+        ms, nl = batch.last_timing()
+        ms_steps.append(ms)
+        launches += nl
+        it += args.sweeps
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+
+    dev_ms = float(sum(ms_steps))
+    lab, ncl = batch.get_partitions()
+    Kbar = float(ncl.mean())
+
+    # predictive step (device-resident), timed separately
+    pred = None
+    if dims.npred > 0:
+        pms = []
+        for r in range(3):
+            batch.predict(seed, it + r, want=())
+            pms.append(batch.last_timing()[0])
+        pred = {"ms": float(np.median(pms)),
+                "new_patient_arm_scores_per_s": nchains * dims.npred * dims.T / (np.median(pms) * 1e-3)}
+
+    # e2e through the public API with host buffers
+    e2e_call(ctx, w, seed, 2)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    e2e_reps = max(1, min(args.steps, 3))
+    for _ in range(e2e_reps):
+        elab, encl, epi, e2e_launches = e2e_call(ctx, w, seed, args.sweeps)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_reps
+    h2d, d2h = e2e_bytes(w, elab, encl, epi)
+
+    # reduce over ranks: max time, sum work
+    t = torch.tensor([dev_ms, e2e_s, Kbar], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms_max, e2e_s_max, Kbar_all = float(tmax[0]), float(tmax[1]), float(tsum[2]) / world
+    else:
+        dev_ms_max, e2e_s_max, Kbar_all = dev_ms, e2e_s, Kbar
+
+    if rank == 0:
+        reallocs_step = world * nchains * dims.nobs * args.sweeps
+        value = reallocs_step * args.steps / (dev_ms_max * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        B = algorithmic_bytes_per_realloc(dims, model.CC, Kbar_all)
+        # per GPU: the dominant kernel is sweep_kernel, one launch per step
+        achieved = (nchains * dims.nobs * args.sweeps * B) / (dev_ms_max / args.steps * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("sweep_kernel_bytes_per_launch")
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, w),
+            "gibbs_sweeps_per_sec": world * nchains * args.sweeps * args.steps / (dev_ms_max * 1e-3),
+            "mean_clusters_per_arm": Kbar_all,
+            "cluster_scores_per_sec": value * (Kbar_all + model.CC),
+            "predictive": pred,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "bytes_per_reallocation": B,
+                         "note": "cluster state is staged on chip; the sweep is bound by fp64 issue + sequential-step latency, not HBM (DESIGN.md)"},
+            "e2e": {"value": world * nchains * dims.nobs * args.sweeps / e2e_s_max, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s_max * 1e3},
+            "gpu_launches": launches,
+            "wall_s_timed_region": t_wall,
+            "clocks": clocks,
+        }
+        if args.cpu_baseline and world == 1:
+            ncores = os.cpu_count() or 1
+            r, desc, dt, _ = cpu_oracle_rate(w, ncores, 12.0)
+            r1, desc1, dt1, _ = cpu_oracle_rate(w, 1, 4.0)
+            out["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": ncores, "kind": "port",
+                                   "sample": desc + f" ({dt:.1f} s)", "single_core_value": r1}
+        print(json.dumps(out), flush=True)
+    batch.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--sweeps", type=int, default=20, help="Gibbs sweeps per step (one kernel launch)")
+    ap.add_argument("--burn", type=int, default=50, help="untimed burn-in sweeps before warm-up")
+    ap.add_argument("--datasets", type=int, default=256)
+    ap.add_argument("--chains-per-dataset", type=int, default=4)
+    ap.add_argument("--n", type=int, default=152)
+    ap.add_argument("--npred", type=int, default=28)
+    ap.add_argument("--P", type=int, default=10)
+    ap.add_argument("--Q", type=int, default=2)
+    ap.add_argument("--T", type=int, default=3)
+    ap.add_argument("--cohesion", type=int, default=2)
+    ap.add_argument("--kcap", type=int, default=0)
+    ap.add_argument("--mixture", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -188,6 +188,11 @@ int tppmx_batch_init(tppmx_batch *b, uint64_t seed, const int32_t *init_labels,
 int tppmx_batch_set_state(tppmx_batch *b, int32_t chain, const tppmx_state *s);
 int tppmx_batch_get_state(tppmx_batch *b, int32_t chain, tppmx_state *s);
 
+/* Bulk download of every chain's partition (what the reference saves per iteration as
+ * cl_lab / nclus, src/dm_ppmx_ct.cpp:1401-1404).  Either pointer may be NULL.
+ *   labels [n_chains][T x ntmax col-major] 1-based, nclu [n_chains][T] */
+int tppmx_batch_get_partitions(tppmx_batch *b, int32_t *labels, int32_t *nclu);
+
 /* ---- hot path 1: reallocation sweep (:347-860) -------------------------------------- */
 /* Parity hook.  Takes patient `it` (position inside arm `arm`) of chain `chain` out of its
  * cluster (:368-457) on a scratch copy of the arm and returns the K+CC log-weights

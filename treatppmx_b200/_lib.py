@@ -14,7 +14,8 @@ SO_PATH = os.path.join(_HERE, "libtppmx.so")
 SYMBOLS = [
     "tppmx_version", "tppmx_create", "tppmx_destroy", "tppmx_last_error",
     "tppmx_batch_create", "tppmx_batch_destroy", "tppmx_batch_init",
-    "tppmx_batch_set_state", "tppmx_batch_get_state", "tppmx_score_patient",
+    "tppmx_batch_set_state", "tppmx_batch_get_state", "tppmx_batch_get_partitions",
+    "tppmx_score_patient",
     "tppmx_batch_sweep", "tppmx_batch_last_timing", "tppmx_batch_predict",
 ]
 
@@ -49,6 +50,7 @@ def load():
     L.tppmx_batch_init.argtypes = [vp, u64, c_ip, c_ip, c_dp]
     L.tppmx_batch_set_state.argtypes = [vp, i32, C.POINTER(State)]
     L.tppmx_batch_get_state.argtypes = [vp, i32, C.POINTER(State)]
+    L.tppmx_batch_get_partitions.argtypes = [vp, c_ip, c_ip]
     L.tppmx_score_patient.argtypes = [vp, i32, i32, i32, u64, i32, c_dp, c_dp, c_ip]
     L.tppmx_batch_sweep.argtypes = [vp, u64, i32, i32]
     L.tppmx_batch_last_timing.argtypes = [vp, c_dp, c_ip]

@@ -649,6 +649,24 @@ extern "C" int tppmx_batch_get_state(tppmx_batch *b, int32_t chain, tppmx_state 
   return TPPMX_OK;
 }
 
+extern "C" int tppmx_batch_get_partitions(tppmx_batch *b, int32_t *labels, int32_t *nclu) {
+  if (!b) return TPPMX_ERR_ARG;
+  const DevBatch &d = b->d;
+  CK(b->ctx, cudaSetDevice(b->ctx->device));
+  CK(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+  const int T = d.T, nt = d.ntmax;
+  if (labels) {
+    std::vector<int> h((size_t)d.n_chains * st_labels(d));
+    RC(d2h(b, h, d.labels));
+    for (int c = 0; c < d.n_chains; c++)
+      for (int t = 0; t < T; t++)
+        for (int it = 0; it < nt; it++)
+          labels[(size_t)c * T * nt + t + (size_t)T * it] = h[((size_t)c * T + t) * nt + it];
+  }
+  if (nclu) CK(b->ctx, cudaMemcpy(nclu, d.nclu, sizeof(int) * (size_t)d.n_chains * T, cudaMemcpyDeviceToHost));
+  return TPPMX_OK;
+}
+
 // ---- launches ---------------------------------------------------------------------------------
 static int check_status(tppmx_batch *b) {
   std::vector<int> st((size_t)b->d.n_chains);

@@ -93,6 +93,15 @@ class Batch:
         self.ctx.check(self.ctx.L.tppmx_batch_get_state(self.h, chain, C.byref(cs)))
         return st
 
+    def get_partitions(self):
+        """labels [n_chains, T, ntmax] (1-based) and nclu [n_chains, T] of every chain."""
+        d = self.dims
+        lab = np.zeros((self.n_chains, d.ntmax, d.T), dtype=np.int32)  # C-order == col-major T x ntmax
+        ncl = np.zeros((self.n_chains, d.T), dtype=np.int32)
+        self.ctx.check(self.ctx.L.tppmx_batch_get_partitions(
+            self.h, lab.ctypes.data_as(c_ip), ncl.ctypes.data_as(c_ip)))
+        return lab.transpose(0, 2, 1), ncl
+
     def score_patient(self, chain: int, arm: int, it: int, seed: int = 0, iter_: int = 0):
         n = self.dims.ntmax + self.model.CC
         logw, prob, K = np.zeros(n), np.zeros(n), C.c_int32(0)
