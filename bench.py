@@ -247,6 +247,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     ctx = Context(local_rank)
     batch = Batch(ctx, model, dims, w["shared"], w["dsets"], chain_dataset=w["chain_ds"], chain_id=w["chain_id"])
     seed = 20240001
+    batch.set_sweep_impl(args.sweep_impl, args.lpu)
     batch.init(seed, w["labels"], w["nclu"], w["beta0"])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -352,6 +353,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": world * nchains * dims.nobs * args.sweeps / e2e_s_max, "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s_max * 1e3},
             "gpu_launches": launches,
+            "sweep_kernel": {"impl": batch.last_sweep_info()[0], "handovers_last_step": batch.last_sweep_info()[1],
+                             "lanes_per_unit": args.lpu or 16},
             "wall_s_timed_region": t_wall,
             "clocks": clocks,
         }
@@ -386,6 +389,8 @@ def main():
     ap.add_argument("--cohesion", type=int, default=2)
     ap.add_argument("--kcap", type=int, default=0)
     ap.add_argument("--mixture", type=int, default=0)
+    ap.add_argument("--sweep-impl", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--lpu", type=int, default=0, help="lanes per (chain, arm) of the fast kernel: 0=default, 8|16|32")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

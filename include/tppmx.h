@@ -207,6 +207,24 @@ int tppmx_score_patient(tppmx_batch *b, int32_t chain, int32_t arm, int32_t it,
  * frozen.  Iteration numbers iter0..iter0+n_sweeps-1 key the RNG.  */
 int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps);
 
+/* Kernel selection.  The library has two sweep kernels with identical results:
+ *   fast    — default switches (PPMx=1, consim=1, similarity=1, calibration 0|2, ncat=0,
+ *             reuse=1): cluster statistics staged in shared memory, likelihood terms hoisted
+ *             into a parallel pre-pass, TPPMX_OPT_LANES_PER_UNIT (8|16|32) lanes per (chain,arm)
+ *   generic — every switch combination of the reference, one warp per (chain, arm)
+ * TPPMX_OPT_SWEEP_IMPL: 0 = automatic (fast when eligible), 1 = generic, 2 = fast (error if
+ * the model is not eligible).  A (chain, arm) that outgrows the fast kernel's staged cluster
+ * capacity is finished by the generic kernel in the same call (TPPMX_INFO_LAST_HANDOVERS). */
+enum {
+  TPPMX_OPT_SWEEP_IMPL = 1,
+  TPPMX_OPT_LANES_PER_UNIT = 2,
+  TPPMX_OPT_FAST_STAGED_CLUSTERS = 3 /* clusters per arm the fast kernel stages on chip (1..32,
+                                        default min(kcap,32)); set before the first sweep */
+};
+enum { TPPMX_INFO_LAST_SWEEP_IMPL = 1, TPPMX_INFO_LAST_HANDOVERS = 2 };
+int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value);
+int tppmx_batch_get_info(const tppmx_batch *b, int32_t what, int32_t *value);
+
 /* Device time (ms, CUDA events on the launching stream) and kernel launches of the last
  * tppmx_batch_sweep / tppmx_batch_predict / tppmx_batch_run call. */
 int tppmx_batch_last_timing(const tppmx_batch *b, double *ms, int32_t *launches);

@@ -354,17 +354,18 @@ __device__ inline void prep_patients(const DevBatch &b, int chain, int ds) {
   }
 }
 
-// the sweep of one arm for one iteration (:349-860 body for fixed tt)
+// the sweep of one arm for one iteration (:349-860 body for fixed tt), starting at patient it0
+// (it0 > 0 only when a unit is taken over from the fast kernel mid-sweep)
 __device__ inline bool sweep_arm(const DevBatch &b, const SimConst &s, ArmView &A, const Rng &rng,
                                  int chain, int ds, int tt, int iter, double sigma, int idxs,
-                                 int lane) {
-  if (b.model.reuse == 1) {  // :351-360
+                                 int lane, int it0) {
+  if (b.model.reuse == 1 && it0 == 0) {  // :351-360
     for (int mm = lane; mm < b.CC; mm += 32)
       rng_normals(rng, iter, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, b.D, A.etae + mm, b.CC);
     __syncwarp();
   }
   const int *pat = b.arm_pat + ((size_t)ds * b.T + tt) * b.ntmax;
-  for (int it = 0; it < A.nt; it++) {
+  for (int it = it0; it < A.nt; it++) {
     const int i = pat[it];
     const PatientIn pt = patient_in(b, chain, ds, i);
     if (!realloc_step(b, s, A, rng, chain, tt, it, i, iter, pt, sigma, idxs, lane,
@@ -375,23 +376,38 @@ __device__ inline bool sweep_arm(const DevBatch &b, const SimConst &s, ArmView &
 }
 
 // ---- kernels ----------------------------------------------------------------------------------
-// grid = chains, block = 32*T threads: warp tt sweeps arm tt.
+// grid = chains, block = 32*T threads: warp tt sweeps arm tt.  resume_l / resume_it (nullable):
+// per (chain, arm) position at which the fast kernel handed the unit over; -1 = nothing to do.
 __global__ void __launch_bounds__(512, 1) sweep_kernel(DevBatch b, uint64_t seed, int iter0,
-                                                    int n_sweeps) {
+                                                    int n_sweeps, const int *resume_l,
+                                                    const int *resume_it) {
   const int chain = blockIdx.x;
   const int tt = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ds = b.chain_ds[chain];
   const SimConst s = make_simconst(b);
   const Rng rng = make_rng(seed, b.chain_id[chain]);
+  if (resume_l) {  // nothing to do for this chain?
+    bool any = false;
+    for (int t = 0; t < b.T; t++) any |= resume_l[(size_t)chain * b.T + t] >= 0;
+    if (!any) return;
+  }
   prep_patients(b, chain, ds);
   __syncthreads();
   if (tt >= b.T) return;
+  int l0 = iter0, it0 = 0;
+  if (resume_l) {
+    l0 = resume_l[(size_t)chain * b.T + tt];
+    it0 = resume_it[(size_t)chain * b.T + tt];
+    if (l0 < 0) return;
+  }
   ArmView A = arm_view_global(b, chain, tt, ds);
   const double sigma = b.sigma[(size_t)chain * b.T + tt];
   const int idxs = b.idxs[chain];
   bool ok = true;
-  for (int l = iter0; l < iter0 + n_sweeps && ok; l++)
-    ok = sweep_arm(b, s, A, rng, chain, ds, tt, l, sigma, idxs, lane);
+  for (int l = l0; l < iter0 + n_sweeps && ok; l++) {
+    ok = sweep_arm(b, s, A, rng, chain, ds, tt, l, sigma, idxs, lane, it0);
+    it0 = 0;
+  }
   if (lane == 0) {
     b.nclu[(size_t)chain * b.T + tt] = A.K;
     if (!ok) atomicExch(&b.status[chain], TPPMX_ERR_CAPACITY);

@@ -14,6 +14,7 @@
 #include "rng.cuh"
 #include "sim.cuh"
 #include "sweep.cuh"
+#include "sweep_fast.cuh"
 
 using namespace tppmx;
 
@@ -34,6 +35,11 @@ struct tppmx_batch {
   double last_ms;
   int last_launches;
   int scratch_chain;  // slot index n_chains
+  // fast sweep kernel (sweep_fast.cuh)
+  int opt_impl = 0, opt_lpu = 0, opt_ks = 0;
+  FastArgs fa;
+  bool fast_ready = false;
+  int last_impl = 0, last_handovers = 0;
 };
 
 #define CK(ctx, call)                                                                      \
@@ -680,19 +686,116 @@ static int check_status(tppmx_batch *b) {
   return TPPMX_OK;
 }
 
+extern "C" int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value) {
+  if (!b) return TPPMX_ERR_ARG;
+  if (opt == TPPMX_OPT_SWEEP_IMPL && value >= 0 && value <= 2) {
+    b->opt_impl = value;
+    return TPPMX_OK;
+  }
+  if (opt == TPPMX_OPT_LANES_PER_UNIT && (value == 0 || value == 8 || value == 16 || value == 32)) {
+    b->opt_lpu = value;
+    return TPPMX_OK;
+  }
+  if (opt == TPPMX_OPT_FAST_STAGED_CLUSTERS && value >= 0 && value <= TPPMX_FAST_KSMAX && !b->fast_ready) {
+    b->opt_ks = value;
+    return TPPMX_OK;
+  }
+  return fail(b->ctx, TPPMX_ERR_ARG, "unknown option or value");
+}
+
+extern "C" int tppmx_batch_get_info(const tppmx_batch *b, int32_t what, int32_t *value) {
+  if (!b || !value) return TPPMX_ERR_ARG;
+  if (what == TPPMX_INFO_LAST_SWEEP_IMPL) *value = b->last_impl;
+  else if (what == TPPMX_INFO_LAST_HANDOVERS) *value = b->last_handovers;
+  else return TPPMX_ERR_ARG;
+  return TPPMX_OK;
+}
+
+// is the model one the fast kernel implements?
+static bool fast_eligible(const tppmx_batch *b, int lpu) {
+  const DevBatch &d = b->d;
+  const tppmx_model &m = d.model;
+  return m.PPMx == 1 && m.consim == 1 && m.similarity == 1 && (m.calibration == 0 || m.calibration == 2) &&
+         d.ncat == 0 && m.reuse == 1 && d.P >= 1 && d.P <= TPPMX_FAST_XR * lpu;
+}
+
+static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
+  DevBatch &d = b->d;
+  FastArgs &fa = b->fa;
+  if (!b->fast_ready) {
+    memset(&fa, 0, sizeof(fa));
+    fa.KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
+    if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
+    fa.ntp = (d.ntmax + 3) & ~3;
+    fa.ncol = fa.KS + d.CC;
+    fa.n_units = d.n_chains * d.T;
+    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC);
+    fa.tab_bytes = (int)fast_tab_bytes(d.ntmax);
+    RC(dev_alloc(b, &fa.lik, (size_t)fa.n_units * fa.ncol * fa.ntp));
+    RC(dev_alloc(b, &fa.uq, (size_t)fa.n_units * 2 * fa.ntp));
+    RC(dev_alloc(b, &fa.resume_l, (size_t)fa.n_units));
+    RC(dev_alloc(b, &fa.resume_it, (size_t)fa.n_units));
+    RC(dev_alloc(b, &fa.bail_count, 1));
+    b->fast_ready = true;
+  }
+  *smem_out = (size_t)fa.tab_bytes + (size_t)(32 / lpu) * fa.unit_bytes;
+  return TPPMX_OK;
+}
+
+template <int LPU>
+static cudaError_t fast_launch(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int upw = 32 / LPU;
+  const int grid = (b->fa.n_units + upw - 1) / upw;
+  sweep_fast_kernel<LPU><<<grid, 32, smem, b->ctx->stream>>>(b->d, b->fa, seed, iter0, n_sweeps);
+  return cudaGetLastError();
+}
+
 extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps) {
   if (!b || n_sweeps < 0) return TPPMX_ERR_ARG;
   tppmx_ctx *ctx = b->ctx;
   CK(ctx, cudaSetDevice(ctx->device));
+  const int lpu = b->opt_lpu ? b->opt_lpu : 16;
+  size_t smem = 0;
+  bool use_fast = b->opt_impl != 1 && fast_eligible(b, lpu);
+  if (use_fast) {
+    RC(fast_prepare(b, lpu, &smem));
+    if (smem > 200 * 1024) use_fast = false;  // would not fit an SM: generic kernel
+  }
+  if (b->opt_impl == 2 && !use_fast) return fail(ctx, TPPMX_ERR_ARG, "model/shape not eligible for the fast sweep kernel");
+  b->last_handovers = 0;
+  int launches = 0;
   CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
-  sweep_kernel<<<b->d.n_chains, 32 * b->d.T, 0, ctx->stream>>>(b->d, seed, iter0, n_sweeps);
+  if (use_fast) {
+    CK(ctx, cudaMemsetAsync(b->fa.bail_count, 0, sizeof(int), ctx->stream));
+    cudaError_t e = lpu == 8    ? fast_launch<8>(b, smem, seed, iter0, n_sweeps)
+                    : lpu == 32 ? fast_launch<32>(b, smem, seed, iter0, n_sweeps)
+                                : fast_launch<16>(b, smem, seed, iter0, n_sweeps);
+    if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("sweep_fast_kernel: ") + cudaGetErrorString(e));
+    launches++;
+    int nb = 0;
+    CK(ctx, cudaMemcpyAsync(&nb, b->fa.bail_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    b->last_handovers = nb;
+    if (nb > 0) {  // finish the units that outgrew the staged capacity, from their exact position
+      sweep_kernel<<<b->d.n_chains, 32 * b->d.T, 0, ctx->stream>>>(b->d, seed, iter0, n_sweeps, b->fa.resume_l,
+                                                                 b->fa.resume_it);
+      launches++;
+    }
+    b->last_impl = 2;
+  } else {
+    sweep_kernel<<<b->d.n_chains, 32 * b->d.T, 0, ctx->stream>>>(b->d, seed, iter0, n_sweeps, nullptr, nullptr);
+    launches++;
+    b->last_impl = 1;
+  }
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   CK(ctx, cudaGetLastError());
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;
   CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   b->last_ms = ms;
-  b->last_launches = 1;
+  b->last_launches = launches;
   return check_status(b);
 }
 

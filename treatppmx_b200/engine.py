@@ -114,6 +114,22 @@ class Batch:
     def sweep(self, seed: int, iter0: int, n_sweeps: int):
         self.ctx.check(self.ctx.L.tppmx_batch_sweep(self.h, seed, iter0, n_sweeps))
 
+    # kernel selection (include/tppmx.h: TPPMX_OPT_*, TPPMX_INFO_*)
+    IMPL = {"auto": 0, "generic": 1, "fast": 2}
+
+    def set_sweep_impl(self, impl: str = "auto", lanes_per_unit: int = 0, staged_clusters: int = 0):
+        self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 1, self.IMPL[impl]))
+        self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 2, lanes_per_unit))
+        if staged_clusters:
+            self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 3, staged_clusters))
+
+    def last_sweep_info(self):
+        """(kernel used by the last sweep: 'generic'|'fast', units handed over to generic)"""
+        a, c = C.c_int32(0), C.c_int32(0)
+        self.ctx.check(self.ctx.L.tppmx_batch_get_info(self.h, 1, C.byref(a)))
+        self.ctx.check(self.ctx.L.tppmx_batch_get_info(self.h, 2, C.byref(c)))
+        return {1: "generic", 2: "fast"}.get(a.value, "none"), c.value
+
     def last_timing(self):
         ms, n = C.c_double(0), C.c_int32(0)
         self.ctx.check(self.ctx.L.tppmx_batch_last_timing(self.h, C.byref(ms), C.byref(n)))
