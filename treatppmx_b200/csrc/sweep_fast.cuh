@@ -15,13 +15,17 @@
 //      - the Dirichlet-multinomial likelihood term L_i(eta_j) (3 exp + 3 lgamma per cluster)
 //        is hoisted out of the sequential loop: eta* is constant during a sweep, so
 //        Lik[col][it] is filled for all patients x occupied clusters in a fully parallel
-//        pre-pass (lanes over patients) and only a cluster born from a refreshed auxiliary
-//        eta needs a (parallel) column fill inside the loop.  Columns follow cluster
-//        identities through label swaps via a small indirection table.
+//        pre-pass and only a cluster born from a refreshed auxiliary eta needs a (parallel)
+//        column fill inside the loop.  Columns follow cluster identities through label swaps
+//        via a small indirection table.  gamma = exp(eta + zb) is formed as exp(eta)*exp(zb)
+//        and lgamma is a branch-free Stirling evaluation (no divergence across lanes).
 //      - uniforms (Philox) and sum_p x_ip^2 are produced in the same pre-pass.
-//  * cluster sufficient statistics (sumx, sumx2 [P][KS] SoA, n_j, labels) live in shared
-//    memory for the whole launch; the patient row x_i, Lik row, uniform are prefetched one
-//    step ahead into registers, so no global-memory latency sits on the critical path.
+//  * cluster sufficient statistics (sumx, sumx2 [P][33] SoA, n_j, labels) live in shared
+//    memory for the whole launch; the patient row x_i, Lik entry and uniform of the next step
+//    are prefetched one step ahead, so no global-memory latency sits on the critical path.
+//  * the hot loop is kept small (rare paths behind unlikely branches, one lgamma call site):
+//    with one warp per CTA every warp is at a different PC, so instruction-cache footprint is
+//    a first-order cost (profiles/r1_v1_*).
 //  * a unit that would need more than KS (<=32) clusters writes its state back and is
 //    finished by the generic kernel from the exact (sweep, patient) position (counter-based
 //    RNG makes the hand-over exact).
@@ -33,7 +37,7 @@
 namespace tppmx {
 
 #define TPPMX_FAST_KSMAX 32
-#define TPPMX_FAST_XR 4  // x-row registers per lane: P <= XR * LPU
+#define TPPMX_FAST_KSTR 33  // smem stride of the [P][cluster] arrays; column 32 is an all-zero cluster
 
 struct FastArgs {
   double *lik;     // [units][ncol][ntp]   likelihood table (global, L2 resident)
@@ -47,26 +51,27 @@ struct FastArgs {
 
 __host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }
 // bytes of shared memory of one unit
-__host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC) {
-  size_t dbl = (size_t)2 * P * KS + (ntp + 1) + 2 * fast_pp(P) + (KS + CC);
+__host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D) {
+  size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (ntp + 1) + 2 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
   size_t in = (size_t)KS + 2 * (KS + CC) + 2 * ntp;
   return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t fast_tab_bytes(int ntmax) { return (((size_t)3 * (ntmax + 2) * 8) + 15) & ~(size_t)15; }
 
 struct UnitSmem {
-  double *sumx, *sumx2, *logn, *xs, *wsc;
+  double *sumx, *sumx2, *logn, *xs, *wsc, *E;
   int *nj, *col, *freec, *lab, *pat;
 };
 
-__device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int ntp, int CC) {
+__device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int ntp, int CC, int D) {
   UnitSmem U;
   double *d = reinterpret_cast<double *>(base);
-  U.sumx = d; d += (size_t)P * KS;
-  U.sumx2 = d; d += (size_t)P * KS;
+  U.sumx = d; d += (size_t)P * TPPMX_FAST_KSTR;
+  U.sumx2 = d; d += (size_t)P * TPPMX_FAST_KSTR;
   U.logn = d; d += ntp + 1;
   U.xs = d; d += 2 * fast_pp(P);
   U.wsc = d; d += KS + CC;
+  U.E = d; d += (size_t)(KS + CC) * D;
   int *q = reinterpret_cast<int *>(d);
   U.nj = q; q += KS;
   U.col = q; q += KS + CC;
@@ -98,23 +103,101 @@ __device__ __forceinline__ double unit_incl_scan(double v, unsigned um, int ul) 
   return v;
 }
 
-// L_i(eta) without its cluster-independent part (:570-576), see sim.cuh lik_term
-__device__ __forceinline__ double fast_lik_entry(int D, const double *eta, int estride,
-                                                 const double *zb, const double *ljj) {
+// lgamma(x), x > 0, branch-free: shift x < 8 up by 8 with the recurrence, then the Stirling
+// series to y^-13 (truncation < 1e-15 at y >= 8).  |error| <= 7e-15 (1 + |lgamma(x)|) against
+// libm on [e^-12, e^12] (tests/test_oracle_kat.py restates and checks the same formula).
+__device__ __forceinline__ double lgamma_pos(double x) {
+  const bool small = x < 8.0;
+  double p = x * (x + 1.0);
+  p *= (x + 2.0) * (x + 3.0);
+  double q = (x + 4.0) * (x + 5.0);
+  q *= (x + 6.0) * (x + 7.0);
+  p *= q;
+  const double y = small ? x + 8.0 : x;
+  const double r = 1.0 / y, r2 = r * r;
+  double s = 1.0 / 156.0;
+  s = fma(s, r2, -691.0 / 360360.0);
+  s = fma(s, r2, 1.0 / 1188.0);
+  s = fma(s, r2, -1.0 / 1680.0);
+  s = fma(s, r2, 1.0 / 1260.0);
+  s = fma(s, r2, -1.0 / 360.0);
+  s = fma(s, r2, 1.0 / 12.0);
+  const double lg = fma(y - 0.5, log(y), -y) + 0.91893853320467274178 + s * r;
+  return lg - log(small ? p : 1.0);
+}
+
+// L_i(eta) without its cluster-independent part (:570-576):
+//   sum_k [ gamma_k log JJ_ik - lgamma(gamma_k) ],  gamma_k = exp(eta_k) exp(zb_ik)
+// The only call site of the transcendental code (keeps the kernel's instruction footprint small).
+__device__ __noinline__ double fast_lik(const double *E, const double *Z, const double *ljj, int D) {
   double w = 0.0;
-#pragma unroll
-  for (int k = 0; k < TPPMX_MAXD; k++)
-    if (k < D) {
-      const double g = exp(eta[(size_t)k * estride] + zb[k]);
-      w += g * ljj[k] - lgamma(g);
-    }
+  for (int k = 0; k < D; k++) {
+    const double g = E[k] * Z[k];
+    w += fma(g, ljj[k], -lgamma_pos(g));
+  }
   return w;
 }
 
+// cold path: more than LPU candidate clusters.  Scores in chunks through U.wsc; returns newci.
 template <int LPU>
+__device__ __noinline__ int fast_score_multi(UnitSmem U, const double *t_dA, const double *t_HN,
+                                             const double *t_HY, const double *lik, int ntp, int it,
+                                             int K, int CC, int KS, int P, const double *xs, double qx,
+                                             double uu, double dV, double simscale, double iv2,
+                                             double c0, double hiv2, bool nolik, unsigned um, int ul,
+                                             int sub) {
+  const int ntot = K + CC;
+  double wmax = -INFINITY;
+  for (int j = ul; j < ntot; j += LPU) {
+    const bool occ = j < K;
+    const int n = occ ? U.nj[j] : 0;
+    const double *sx = U.sumx + (occ ? j : TPPMX_FAST_KSMAX);
+    double a = 0.0, bb = 0.0;
+    for (int p = 0; p < P; p++) {
+      const double t = fma(sx[p * TPPMX_FAST_KSTR], iv2, c0);
+      a = fma(t, t, a);
+      bb = fma(t, xs[p], bb);
+    }
+    const double tY = a + iv2 * (2.0 * bb + iv2 * qx);
+    const double d = t_dA[n] - hiv2 * qx + (t_HY[n] * tY - t_HN[n] * a);
+    const int c = occ ? U.col[j] : U.col[KS + (j - K)];
+    const double lv = nolik ? 0.0 : lik[(size_t)c * ntp + it];
+    const double w = dV + U.logn[n] + simscale * d + lv;
+    U.wsc[j] = w;
+    wmax = fmax(wmax, w);
+  }
+  wmax = unit_max<LPU>(wmax, um);
+  __syncwarp(um);
+  double den = 0.0;
+  for (int j = ul; j < ntot; j += LPU) {
+    const double e = exp(U.wsc[j] - wmax);
+    U.wsc[j] = e;
+    den += e;
+  }
+  den = unit_sum<LPU>(den, um);
+  __syncwarp(um);
+  int newci = ntot;
+  double carry = 0.0;
+  for (int c0j = 0; c0j < ntot; c0j += LPU) {
+    const int j = c0j + ul;
+    const double pj = (j < ntot) ? U.wsc[j] / den : 0.0;
+    const double cum = carry + unit_incl_scan<LPU>(pj, um, ul);
+    unsigned hit = __ballot_sync(um, (j < ntot) && (uu < cum));
+    hit = (LPU == 32) ? hit : ((hit >> (sub * LPU)) & ((1u << LPU) - 1u));
+    if (hit) {
+      newci = c0j + __ffs(hit);
+      break;
+    }
+    carry = __shfl_sync(um, cum, LPU - 1, LPU);
+  }
+  return newci;
+}
+
+template <int LPU, int XR>
 __global__ void __launch_bounds__(32, 12)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
+  constexpr int KSTR = TPPMX_FAST_KSTR;
   extern __shared__ __align__(16) char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPU, ul = lane % LPU;
@@ -142,7 +225,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const int ds = b.chain_ds[chain];
   const int nt = b.arm_n[(size_t)ds * b.T + tt];
   const Rng rng = make_rng(seed, b.chain_id[chain]);
-  UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC);
+  const UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC, D);
 
   // global state of this unit
   double *g_sumx = b.sumx + ((size_t)chain * b.T + tt) * P * kcap;
@@ -155,23 +238,22 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const double *g_x = b.x + (size_t)ds * b.nobs * P;
   double *lik = fa.lik + (size_t)unit * fa.ncol * ntp;
   double *uq = fa.uq + (size_t)unit * 2 * ntp;
-  double *g_zb = b.zb + (size_t)chain * b.nobs * D;
+  double *g_ez = b.zb + (size_t)chain * b.nobs * D;   // here: exp(beta'z) (scratch, rebuilt per sweep)
   double *g_ljj = b.ljj + (size_t)chain * b.nobs * D;
   const double *beta = b.beta + (size_t)chain * Q * D;
 
   int K = b.nclu[(size_t)chain * b.T + tt];
   const double sigma = b.sigma[(size_t)chain * b.T + tt];
   const int idxs = b.idxs[chain];
-  const double log_alpha_cc = log(b.model.alpha) - log((double)CC);
   const double iv2 = s.iv2, c0 = s.c0, hiv2 = s.hiv2;
   const double simscale = (s.calibration == 2) ? s.calscale : 1.0;
   const bool nolik = s.nolik != 0;
 
   // ---- stage the unit's state in shared memory
-  for (int e = ul; e < P * KS; e += LPU) {
-    const int p = e / KS, j = e % KS;
-    U.sumx[e] = g_sumx[(size_t)p * kcap + j];
-    U.sumx2[e] = g_sumx2[(size_t)p * kcap + j];
+  for (int e = ul; e < P * KSTR; e += LPU) {
+    const int p = e / KSTR, j = e % KSTR;
+    U.sumx[e] = (j < KS) ? g_sumx[(size_t)p * kcap + j] : 0.0;
+    U.sumx2[e] = (j < KS) ? g_sumx2[(size_t)p * kcap + j] : 0.0;
   }
   for (int j = ul; j < KS; j += LPU) U.nj[j] = g_nj[j];
   for (int it = ul; it < nt; it += LPU) {
@@ -187,6 +269,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     nfree = fa.ncol - Kc - CC;
     for (int f = ul; f < nfree; f += LPU) U.freec[f] = Kc + CC + f;
   }
+  // cohesion by cluster size: logn[0] is the auxiliary-cluster value (:677 / :680)
+  if (ul == 0) U.logn[0] = (s.cohesion == 1) ? log(b.model.alpha) - log((double)CC) : 0.0;
+  for (int n = 1 + ul; n <= nt; n += LPU) U.logn[n] = (s.cohesion == 1) ? log((double)n) : log((double)n - sigma);
   __syncwarp(um);
 
   auto dV_of = [&](int Kcur) -> double {
@@ -208,8 +293,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     // :351-360 auxiliary eta ~ N(0, I)
     for (int mm = ul; mm < CC; mm += LPU)
       rng_normals(rng, l, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, D, g_etae + mm, CC);
-    for (int n = 1 + ul; n <= nt; n += LPU) U.logn[n] = (s.cohesion == 1) ? log((double)n) : log((double)n - sigma);
     __syncwarp(um);
+    // per patient: uniform, sum_p x^2, exp(beta'z), log JJ
     for (int it = ul; it < nt; it += LPU) {
       const int i = U.pat[it];
       const double *xi = g_x + (size_t)i * P;
@@ -220,64 +305,73 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       uq[it] = uu;
       uq[ntp + it] = qx;
       if (!nolik) {
-        double zb[TPPMX_MAXD], ljj[TPPMX_MAXD];
         const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
         const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
-#pragma unroll
-        for (int k = 0; k < TPPMX_MAXD; k++)
-          if (k < D) {
-            double acc = 0.0;
-            for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
-            zb[k] = acc;
-            ljj[k] = log(JJ[k]);
-            g_zb[(size_t)i * D + k] = acc;
-            g_ljj[(size_t)i * D + k] = ljj[k];
-          }
-        for (int j = 0; j < K; j++) lik[(size_t)U.col[j] * ntp + it] = fast_lik_entry(D, g_eta + j, kcap, zb, ljj);
-        for (int m = 0; m < CC; m++) lik[(size_t)U.col[KS + m] * ntp + it] = fast_lik_entry(D, g_etae + m, CC, zb, ljj);
+        for (int k = 0; k < D; k++) {
+          double acc = 0.0;
+          for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
+          g_ez[(size_t)i * D + k] = exp(acc);
+          g_ljj[(size_t)i * D + k] = log(JJ[k]);
+        }
+      }
+    }
+    if (!nolik) {
+      const int ntot = K + CC;
+      // exp(eta) of every candidate cluster, stored by column id
+      for (int e = ul; e < ntot * D; e += LPU) {
+        const int c = e / D, k = e - c * D;
+        const double eta = (c < K) ? g_eta[(size_t)k * kcap + c] : g_etae[k * CC + (c - K)];
+        U.E[colmap(c, K) * D + k] = exp(eta);
+      }
+      __syncwarp(um);
+      // likelihood table: all (candidate cluster, patient) pairs, flattened over the lanes
+      for (int e = ul; e < ntot * nt; e += LPU) {
+        const int c = e / nt, it = e - c * nt;
+        const int cl = colmap(c, K);
+        const int i = U.pat[it];
+        lik[(size_t)cl * ntp + it] = fast_lik(U.E + cl * D, g_ez + (size_t)i * D, g_ljj + (size_t)i * D, D);
       }
     }
     __syncwarp(um);
 
     // =========================== sequential reallocation steps ===========================
     double dV = dV_of(K);
-    // operands of step 0
+    bool act0 = ul < K + CC;
+    const double *likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
     double likv = 0.0, uu = 0.0, qx = 0.0;
-    if (nt > 0) {
+    if (nt > 0) {  // operands of step 0
       const int i0 = U.pat[0];
 #pragma unroll
-      for (int r = 0; r < TPPMX_FAST_XR; r++) {
+      for (int r = 0; r < XR; r++) {
         const int p = ul + r * LPU;
         if (p < P) U.xs[p] = g_x[(size_t)i0 * P + p];
       }
       uu = uq[0];
       qx = uq[ntp];
-      if (!nolik && ul < K + CC) likv = lik[(size_t)colmap(ul, K) * ntp];
+      if (!nolik && act0) likv = likp[0];
     }
     __syncwarp(um);
 
     for (int it = 0; it < nt; it++) {
-      if (K >= KS) {  // a birth could overflow the staged capacity: hand over before touching anything
+      if (__builtin_expect(K >= KS, 0)) {  // a birth could overflow the staged capacity: hand over
         bail_l = l;
         bail_it = it;
         break;
       }
-      const int buf = it & 1;
-      const double *xs = U.xs + buf * Pp;
-      const int i = U.pat[it];
+      const double *xs = U.xs + (it & 1) * Pp;
       // ---- prefetch the operands of step it+1 (addresses do not depend on this step)
       const bool has_next = (it + 1 < nt);
-      double xr_n[TPPMX_FAST_XR], lik_n = 0.0, uu_n = 0.0, qx_n = 0.0;
+      double xr_n[XR], lik_n = 0.0, uu_n = 0.0, qx_n = 0.0;
       if (has_next) {
-        const int i1 = U.pat[it + 1];
+        const double *xrow = g_x + (size_t)U.pat[it + 1] * P;
 #pragma unroll
-        for (int r = 0; r < TPPMX_FAST_XR; r++) {
+        for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
-          xr_n[r] = (p < P) ? g_x[(size_t)i1 * P + p] : 0.0;
+          xr_n[r] = (p < P) ? xrow[p] : 0.0;
         }
         uu_n = uq[it + 1];
         qx_n = uq[ntp + it + 1];
-        if (!nolik && ul < K + CC) lik_n = lik[(size_t)colmap(ul, K) * ntp + it + 1];
+        if (!nolik && act0) lik_n = likp[it + 1];
       }
       bool structural = false;
 
@@ -285,15 +379,15 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       const int zi = U.lab[it] - 1;
       const int nzi = U.nj[zi];
       __syncwarp(um);
-      if (nzi > 1) {
+      if (__builtin_expect(nzi > 1, 1)) {
         if (ul == 0) U.nj[zi] = nzi - 1;
 #pragma unroll
-        for (int r = 0; r < TPPMX_FAST_XR; r++) {
+        for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
           if (p < P) {
             const double xv = xs[p];
-            U.sumx[p * KS + zi] = __dsub_rn(U.sumx[p * KS + zi], xv);
-            U.sumx2[p * KS + zi] = __dsub_rn(U.sumx2[p * KS + zi], __dmul_rn(xv, xv));
+            U.sumx[p * KSTR + zi] = __dsub_rn(U.sumx[p * KSTR + zi], xv);
+            U.sumx2[p * KSTR + zi] = __dsub_rn(U.sumx2[p * KSTR + zi], __dmul_rn(xv, xv));
           }
         }
       } else {  // singleton (:384-457)
@@ -317,12 +411,12 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
             g_eta[(size_t)k * kcap + Kc - 1] = t;
           }
           for (int p = ul; p < P; p += LPU) {
-            double t = U.sumx[p * KS + iaux - 1];
-            U.sumx[p * KS + iaux - 1] = U.sumx[p * KS + Kc - 1];
-            U.sumx[p * KS + Kc - 1] = t;
-            t = U.sumx2[p * KS + iaux - 1];
-            U.sumx2[p * KS + iaux - 1] = U.sumx2[p * KS + Kc - 1];
-            U.sumx2[p * KS + Kc - 1] = t;
+            double t = U.sumx[p * KSTR + iaux - 1];
+            U.sumx[p * KSTR + iaux - 1] = U.sumx[p * KSTR + Kc - 1];
+            U.sumx[p * KSTR + Kc - 1] = t;
+            t = U.sumx2[p * KSTR + iaux - 1];
+            U.sumx2[p * KSTR + iaux - 1] = U.sumx2[p * KSTR + Kc - 1];
+            U.sumx2[p * KSTR + Kc - 1] = t;
           }
           __syncwarp(um);
         }
@@ -334,93 +428,59 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         nfree += 1;
         for (int p = ul; p < P; p += LPU) {
           const double xv = xs[p];
-          U.sumx[p * KS + Kc - 1] = __dsub_rn(U.sumx[p * KS + Kc - 1], xv);
-          U.sumx2[p * KS + Kc - 1] = __dsub_rn(U.sumx2[p * KS + Kc - 1], __dmul_rn(xv, xv));
+          U.sumx[p * KSTR + Kc - 1] = __dsub_rn(U.sumx[p * KSTR + Kc - 1], xv);
+          U.sumx2[p * KSTR + Kc - 1] = __dsub_rn(U.sumx2[p * KSTR + Kc - 1], __dmul_rn(xv, xv));
         }
         K = Kc - 1;
         dV = dV_of(K);
       }
       __syncwarp(um);
-      if (structural && !nolik) likv = (ul < K + CC) ? lik[(size_t)colmap(ul, K) * ntp + it] : 0.0;
+      if (__builtin_expect(structural, 0)) {
+        act0 = ul < K + CC;
+        likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
+        likv = (!nolik && act0) ? likp[it] : 0.0;
+      }
 
-      // ---- :460-802 score the K occupied + CC auxiliary clusters
+      // ---- :460-814 score the K occupied + CC auxiliary clusters, normalise, draw
       const int ntot = K + CC;
-      const bool multi = ntot > LPU;
-      double w0 = -INFINITY, wmax = -INFINITY;
-      for (int c0j = 0; c0j < ntot; c0j += LPU) {
-        const int j = c0j + ul;
-        const bool act = j < ntot, occ = j < K;
-        double w = -INFINITY;
-        if (act) {
-          const int n = occ ? U.nj[j] : 0;
-          const double *sx = U.sumx + (occ ? j : 0);
-          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-          int p = 0;
-          for (; p + 1 < P; p += 2) {
-            const double S0 = occ ? sx[p * KS] : 0.0, S1 = occ ? sx[(p + 1) * KS] : 0.0;
-            const double t0 = fma(S0, iv2, c0), t1 = fma(S1, iv2, c0);
-            a0 = fma(t0, t0, a0);
-            a1 = fma(t1, t1, a1);
-            b0 = fma(t0, xs[p], b0);
-            b1 = fma(t1, xs[p + 1], b1);
-          }
-          if (p < P) {
-            const double S0 = occ ? sx[p * KS] : 0.0;
-            const double t0 = fma(S0, iv2, c0);
-            a0 = fma(t0, t0, a0);
-            b0 = fma(t0, xs[p], b0);
-          }
-          const double a = a0 + a1, bb = b0 + b1;
-          const double tY = a + iv2 * (2.0 * bb + iv2 * qx);
-          const double d = t_dA[n] - hiv2 * qx + (t_HY[n] * tY - t_HN[n] * a);
-          const double coh = (s.cohesion == 1) ? (occ ? U.logn[n] : log_alpha_cc)
-                                               : (occ ? dV + U.logn[n] : dV);
-          double lv = 0.0;
-          if (!nolik) lv = (c0j == 0) ? likv : lik[(size_t)colmap(j, K) * ntp + it];
-          w = coh + simscale * d + lv;
+      int newci;
+      if (__builtin_expect(ntot <= LPU, 1)) {
+        const bool occ = ul < K;
+        const int n = occ ? U.nj[ul] : 0;
+        const double *sx = U.sumx + (occ ? ul : TPPMX_FAST_KSMAX);  // column 32: the empty cluster
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        int p = 0;
+        for (; p + 1 < P; p += 2) {
+          const double t0 = fma(sx[p * KSTR], iv2, c0), t1 = fma(sx[(p + 1) * KSTR], iv2, c0);
+          a0 = fma(t0, t0, a0);
+          a1 = fma(t1, t1, a1);
+          b0 = fma(t0, xs[p], b0);
+          b1 = fma(t1, xs[p + 1], b1);
         }
-        if (multi && act) U.wsc[j] = w;
-        if (c0j == 0) w0 = w;
-        wmax = fmax(wmax, w);
-      }
-      wmax = unit_max<LPU>(wmax, um);
-      double e0 = 0.0, den = 0.0;
-      if (!multi) {
-        e0 = (ul < ntot) ? exp(w0 - wmax) : 0.0;
-        den = e0;
+        if (p < P) {
+          const double t0 = fma(sx[p * KSTR], iv2, c0);
+          a0 = fma(t0, t0, a0);
+          b0 = fma(t0, xs[p], b0);
+        }
+        const double a = a0 + a1, bb = b0 + b1;
+        const double tY = a + iv2 * (2.0 * bb + iv2 * qx);
+        const double d = t_dA[n] - hiv2 * qx + (t_HY[n] * tY - t_HN[n] * a);
+        const double w = act0 ? dV + U.logn[n] + simscale * d + likv : -INFINITY;
+        const double wmax = unit_max<LPU>(w, um);
+        const double e0 = exp(w - wmax);
+        const double den = unit_sum<LPU>(e0, um);
+        const double cum = unit_incl_scan<LPU>(e0 / den, um, ul);
+        unsigned hit = __ballot_sync(um, act0 && (uu < cum));
+        hit = (LPU == 32) ? hit : ((hit >> (sub * LPU)) & ((1u << LPU) - 1u));
+        newci = hit ? __ffs(hit) : ntot;  // :807 default when rounding leaves uu >= total
       } else {
-        __syncwarp(um);
-        for (int j = ul; j < ntot; j += LPU) {
-          const double e = exp(U.wsc[j] - wmax);
-          U.wsc[j] = e;
-          den += e;
-        }
-        __syncwarp(um);
-      }
-      den = unit_sum<LPU>(den, um);
-
-      // ---- :805-814 inverse-CDF draw
-      int newci = ntot;
-      {
-        double carry = 0.0;
-        for (int c0j = 0; c0j < ntot; c0j += LPU) {
-          const int j = c0j + ul;
-          double pj = 0.0;
-          if (j < ntot) pj = (multi ? U.wsc[j] : e0) / den;
-          const double cum = carry + unit_incl_scan<LPU>(pj, um, ul);
-          unsigned hit = __ballot_sync(um, (j < ntot) && (uu < cum));
-          hit = (LPU == 32) ? hit : ((hit >> (sub * LPU)) & ((1u << LPU) - 1u));
-          if (hit) {
-            newci = c0j + __ffs(hit);
-            break;
-          }
-          carry = __shfl_sync(um, cum, LPU - 1, LPU);
-        }
+        newci = fast_score_multi<LPU>(U, t_dA, t_HN, t_HY, lik, ntp, it, K, CC, KS, P, xs, qx, uu, dV,
+                                      simscale, iv2, c0, hiv2, nolik, um, ul, sub);
       }
 
       // ---- :820-856 assign, update sufficient statistics
       int lab;
-      if (newci <= K) {
+      if (__builtin_expect(newci <= K, 1)) {
         lab = newci;
         if (ul == 0) {
           U.lab[it] = lab;
@@ -428,6 +488,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
       } else {  // a new cluster takes the auxiliary eta (:829-845)
         structural = true;
+        const int i = U.pat[it];
         const int m = newci - K - 1;
         lab = K + 1;
         const int newcol = U.freec[nfree - 1];
@@ -444,53 +505,54 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         if (ul == 0) rng_normals(rng, l, TPPMX_SITE_AUX_REFRESH, tt, (uint32_t)i, D, g_etae + m, CC);
         __syncwarp(um);
         if (!nolik) {  // likelihood column of the refreshed auxiliary eta, remaining patients
+          for (int k = ul; k < D; k += LPU) U.E[newcol * D + k] = exp(g_etae[k * CC + m]);
+          __syncwarp(um);
           for (int it2 = it + 1 + ul; it2 < nt; it2 += LPU) {
             const int i2 = U.pat[it2];
-            double zb[TPPMX_MAXD], ljj[TPPMX_MAXD];
-#pragma unroll
-            for (int k = 0; k < TPPMX_MAXD; k++)
-              if (k < D) {
-                zb[k] = g_zb[(size_t)i2 * D + k];
-                ljj[k] = g_ljj[(size_t)i2 * D + k];
-              }
-            lik[(size_t)newcol * ntp + it2] = fast_lik_entry(D, g_etae + m, CC, zb, ljj);
+            lik[(size_t)newcol * ntp + it2] =
+                fast_lik(U.E + newcol * D, g_ez + (size_t)i2 * D, g_ljj + (size_t)i2 * D, D);
           }
         }
         K = lab;
         dV = dV_of(K);
       }
 #pragma unroll
-      for (int r = 0; r < TPPMX_FAST_XR; r++) {
+      for (int r = 0; r < XR; r++) {
         const int p = ul + r * LPU;
         if (p < P) {
           const double xv = xs[p];
-          U.sumx[p * KS + lab - 1] = __dadd_rn(U.sumx[p * KS + lab - 1], xv);
-          U.sumx2[p * KS + lab - 1] = __dadd_rn(U.sumx2[p * KS + lab - 1], __dmul_rn(xv, xv));
+          U.sumx[p * KSTR + lab - 1] = __dadd_rn(U.sumx[p * KSTR + lab - 1], xv);
+          U.sumx2[p * KSTR + lab - 1] = __dadd_rn(U.sumx2[p * KSTR + lab - 1], __dmul_rn(xv, xv));
         }
       }
       // ---- stage the operands of the next step
       if (has_next) {
 #pragma unroll
-        for (int r = 0; r < TPPMX_FAST_XR; r++) {
+        for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
-          if (p < P) U.xs[(buf ^ 1) * Pp + p] = xr_n[r];
+          if (p < P) U.xs[((it + 1) & 1) * Pp + p] = xr_n[r];
         }
         uu = uu_n;
         qx = qx_n;
         likv = lik_n;
       }
       __syncwarp(um);
-      if (has_next && structural && !nolik)
-        likv = (ul < K + CC) ? lik[(size_t)colmap(ul, K) * ntp + it + 1] : 0.0;
+      if (__builtin_expect(structural, 0)) {
+        act0 = ul < K + CC;
+        likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
+        likv = (has_next && !nolik && act0) ? likp[it + 1] : 0.0;
+      }
     }
   }
 
   // ---- write the unit back in the library's global layout
   __syncwarp(um);
-  for (int e = ul; e < P * KS; e += LPU) {
-    const int p = e / KS, j = e % KS;
-    g_sumx[(size_t)p * kcap + j] = U.sumx[e];
-    g_sumx2[(size_t)p * kcap + j] = U.sumx2[e];
+  for (int e = ul; e < P * KSTR; e += LPU) {
+    const int p = e / KSTR, j = e % KSTR;
+    if (j < KS) {
+      g_sumx[(size_t)p * kcap + j] = U.sumx[e];
+      g_sumx2[(size_t)p * kcap + j] = U.sumx2[e];
+    }
   }
   for (int j = ul; j < KS; j += LPU) g_nj[j] = U.nj[j];
   for (int it = ul; it < nt; it += LPU) g_lab[it] = U.lab[it];

@@ -716,7 +716,7 @@ static bool fast_eligible(const tppmx_batch *b, int lpu) {
   const DevBatch &d = b->d;
   const tppmx_model &m = d.model;
   return m.PPMx == 1 && m.consim == 1 && m.similarity == 1 && (m.calibration == 0 || m.calibration == 2) &&
-         d.ncat == 0 && m.reuse == 1 && d.P >= 1 && d.P <= TPPMX_FAST_XR * lpu;
+         d.ncat == 0 && m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
 }
 
 static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
@@ -729,7 +729,7 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     fa.ntp = (d.ntmax + 3) & ~3;
     fa.ncol = fa.KS + d.CC;
     fa.n_units = d.n_chains * d.T;
-    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC);
+    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D);
     fa.tab_bytes = (int)fast_tab_bytes(d.ntmax);
     RC(dev_alloc(b, &fa.lik, (size_t)fa.n_units * fa.ncol * fa.ntp));
     RC(dev_alloc(b, &fa.uq, (size_t)fa.n_units * 2 * fa.ntp));
@@ -742,14 +742,20 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
   return TPPMX_OK;
 }
 
-template <int LPU>
-static cudaError_t fast_launch(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int LPU, int XR>
+static cudaError_t fast_launch2(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (b->fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU><<<grid, 32, smem, b->ctx->stream>>>(b->d, b->fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR><<<grid, 32, smem, b->ctx->stream>>>(b->d, b->fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
+}
+template <int LPU>
+static cudaError_t fast_launch(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
+  // XR = registers per lane that hold the next patient's covariate row (P <= XR * LPU)
+  if (b->d.P <= LPU) return fast_launch2<LPU, 1>(b, smem, seed, iter0, n_sweeps);
+  return fast_launch2<LPU, 4>(b, smem, seed, iter0, n_sweeps);
 }
 
 extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps) {
