@@ -32,6 +32,7 @@
 #pragma once
 #include "layout.h"
 #include "rng.cuh"
+#include "fastmath.cuh"
 #include "sim.cuh"
 
 namespace tppmx {
@@ -40,8 +41,8 @@ namespace tppmx {
 #define TPPMX_FAST_KSTR 33  // smem stride of the [P][cluster] arrays; column 32 is an all-zero cluster
 
 struct FastArgs {
-  double *lik;     // [units][ncol][ntp]   likelihood table (global, L2 resident)
-  double *uq;      // [units][2][ntp]      uniforms, sum_p x_ip^2
+  double *lik;     // [units][ncol][ntp] (+ntp pad)  likelihood table (global, L2 resident)
+  double *uq;      // [units][2][ntp+1]    uniforms, sum_p x_ip^2
   int *resume_l;   // [units] sweep at which the unit handed over to the generic kernel, -1 = done
   int *resume_it;  // [units] patient position of the hand-over
   int *bail_count; // [1]
@@ -53,7 +54,7 @@ __host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }
 // bytes of shared memory of one unit
 __host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D) {
   size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (ntp + 1) + 2 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
-  size_t in = (size_t)KS + 2 * (KS + CC) + 2 * ntp;
+  size_t in = (size_t)KS + 2 * (KS + CC) + 2 * (ntp + 1) + 1;
   return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t fast_tab_bytes(int ntmax) { return (((size_t)3 * (ntmax + 2) * 8) + 15) & ~(size_t)15; }
@@ -76,59 +77,47 @@ __device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int nt
   U.nj = q; q += KS;
   U.col = q; q += KS + CC;
   U.freec = q; q += KS + CC;
-  U.lab = q; q += ntp;
-  U.pat = q;
+  U.lab = q; q += ntp + 1;
+  U.pat = q;  // ntp + 1 entries (the prefetch of step it+1 may read one past the arm)
   return U;
 }
 
+constexpr unsigned TPPMX_FULL = 0xffffffffu;
+
+// The units of a warp run CONVERGED: every collective uses the full mask (width-LPU shuffles
+// keep the units apart) and unit-specific work is predicated.  Rare events (singleton removal,
+// cluster birth, > LPU candidates) are entered warp-uniformly through __any_sync.
 template <int LPU>
-__device__ __forceinline__ double unit_max(double v, unsigned um) {
+__device__ __forceinline__ float unit_maxf(float v) {
 #pragma unroll
-  for (int o = LPU / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(um, v, o, LPU));
+  for (int o = LPU / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(TPPMX_FULL, v, o, LPU));
   return v;
 }
 template <int LPU>
-__device__ __forceinline__ double unit_sum(double v, unsigned um) {
+__device__ __forceinline__ double unit_sum(double v) {
 #pragma unroll
-  for (int o = LPU / 2; o > 0; o >>= 1) v += __shfl_xor_sync(um, v, o, LPU);
+  for (int o = LPU / 2; o > 0; o >>= 1) v += __shfl_xor_sync(TPPMX_FULL, v, o, LPU);
   return v;
 }
 template <int LPU>
-__device__ __forceinline__ double unit_incl_scan(double v, unsigned um, int ul) {
+__device__ __forceinline__ double unit_incl_scan(double v, int ul) {
 #pragma unroll
   for (int o = 1; o < LPU; o <<= 1) {
-    const double t = __shfl_up_sync(um, v, o, LPU);
+    const double t = __shfl_up_sync(TPPMX_FULL, v, o, LPU);
     if (ul >= o) v += t;
   }
   return v;
 }
-
-// lgamma(x), x > 0, branch-free: shift x < 8 up by 8 with the recurrence, then the Stirling
-// series to y^-13 (truncation < 1e-15 at y >= 8).  |error| <= 7e-15 (1 + |lgamma(x)|) against
-// libm on [e^-12, e^12] (tests/test_oracle_kat.py restates and checks the same formula).
-__device__ __forceinline__ double lgamma_pos(double x) {
-  const bool small = x < 8.0;
-  double p = x * (x + 1.0);
-  p *= (x + 2.0) * (x + 3.0);
-  double q = (x + 4.0) * (x + 5.0);
-  q *= (x + 6.0) * (x + 7.0);
-  p *= q;
-  const double y = small ? x + 8.0 : x;
-  const double r = 1.0 / y, r2 = r * r;
-  double s = 1.0 / 156.0;
-  s = fma(s, r2, -691.0 / 360360.0);
-  s = fma(s, r2, 1.0 / 1188.0);
-  s = fma(s, r2, -1.0 / 1680.0);
-  s = fma(s, r2, 1.0 / 1260.0);
-  s = fma(s, r2, -1.0 / 360.0);
-  s = fma(s, r2, 1.0 / 12.0);
-  const double lg = fma(y - 0.5, log(y), -y) + 0.91893853320467274178 + s * r;
-  return lg - log(small ? p : 1.0);
+template <int LPU>
+__device__ __forceinline__ int warp_max_over_units(int v) {
+#pragma unroll
+  for (int o = 16; o >= LPU; o >>= 1) v = max(v, __shfl_xor_sync(TPPMX_FULL, v, o));
+  return v;
 }
 
 // L_i(eta) without its cluster-independent part (:570-576):
 //   sum_k [ gamma_k log JJ_ik - lgamma(gamma_k) ],  gamma_k = exp(eta_k) exp(zb_ik)
-// The only call site of the transcendental code (keeps the kernel's instruction footprint small).
+// The only call site of the lgamma code (keeps the kernel's instruction footprint small).
 __device__ __noinline__ double fast_lik(const double *E, const double *Z, const double *ljj, int D) {
   double w = 0.0;
   for (int k = 0; k < D; k++) {
@@ -138,15 +127,17 @@ __device__ __noinline__ double fast_lik(const double *E, const double *Z, const 
   return w;
 }
 
-// cold path: more than LPU candidate clusters.  Scores in chunks through U.wsc; returns newci.
+// cold path: a unit of the warp has more than LPU candidate clusters (`mine`).  Scores in
+// chunks through U.wsc; returns newci for the units with `mine`.
 template <int LPU>
 __device__ __noinline__ int fast_score_multi(UnitSmem U, const double *t_dA, const double *t_HN,
                                              const double *t_HY, const double *lik, int ntp, int it,
                                              int K, int CC, int KS, int P, const double *xs, double qx,
                                              double uu, double dV, double simscale, double iv2,
-                                             double c0, double hiv2, bool nolik, unsigned um, int ul,
+                                             double c0, double hiv2, bool nolik, bool mine, int ul,
                                              int sub) {
-  const int ntot = K + CC;
+  const int ntot = mine ? K + CC : 0;
+  const int ntot_w = warp_max_over_units<LPU>(ntot);
   double wmax = -INFINITY;
   for (int j = ul; j < ntot; j += LPU) {
     const bool occ = j < K;
@@ -166,34 +157,37 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double *t_dA, con
     U.wsc[j] = w;
     wmax = fmax(wmax, w);
   }
-  wmax = unit_max<LPU>(wmax, um);
-  __syncwarp(um);
+  __syncwarp();
+#pragma unroll
+  for (int o = LPU / 2; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(TPPMX_FULL, wmax, o, LPU));
   double den = 0.0;
   for (int j = ul; j < ntot; j += LPU) {
-    const double e = exp(U.wsc[j] - wmax);
+    const double e = fast_exp(U.wsc[j] - wmax);
     U.wsc[j] = e;
     den += e;
   }
-  den = unit_sum<LPU>(den, um);
-  __syncwarp(um);
+  __syncwarp();
+  den = unit_sum<LPU>(den);
+  const double thr = uu * den;
   int newci = ntot;
+  bool found = false;
   double carry = 0.0;
-  for (int c0j = 0; c0j < ntot; c0j += LPU) {
+  for (int c0j = 0; c0j < ntot_w; c0j += LPU) {
     const int j = c0j + ul;
-    const double pj = (j < ntot) ? U.wsc[j] / den : 0.0;
-    const double cum = carry + unit_incl_scan<LPU>(pj, um, ul);
-    unsigned hit = __ballot_sync(um, (j < ntot) && (uu < cum));
+    const double ej = (j < ntot) ? U.wsc[j] : 0.0;
+    const double cum = carry + unit_incl_scan<LPU>(ej, ul);
+    unsigned hit = __ballot_sync(TPPMX_FULL, (j < ntot) && (thr < cum));
     hit = (LPU == 32) ? hit : ((hit >> (sub * LPU)) & ((1u << LPU) - 1u));
-    if (hit) {
+    if (hit && !found) {
       newci = c0j + __ffs(hit);
-      break;
+      found = true;
     }
-    carry = __shfl_sync(um, cum, LPU - 1, LPU);
+    carry = __shfl_sync(TPPMX_FULL, cum, LPU - 1, LPU);
   }
   return newci;
 }
 
-template <int LPU, int XR>
+template <int LPU, int XR, bool NOLIK>
 __global__ void __launch_bounds__(32, 12)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -201,8 +195,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   extern __shared__ __align__(16) char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPU, ul = lane % LPU;
-  const unsigned um = (LPU == 32) ? 0xffffffffu : (((1u << LPU) - 1u) << (sub * LPU));
-  const int unit = blockIdx.x * UPW + sub;
+  const int unit_raw = blockIdx.x * UPW + sub;
+  const bool valid = unit_raw < fa.n_units;
+  const int unit = valid ? unit_raw : 0;  // lanes of a missing unit shadow unit 0 read-only
   const int P = b.P, D = b.D, Q = b.Q, CC = b.CC, KS = fa.KS, ntp = fa.ntp, kcap = b.kcap;
   const int Pp = fast_pp(P);
   const SimConst s = make_simconst(b);
@@ -218,12 +213,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     t_HN[n] = (n == 0) ? 0.0 : r0.H;
     t_HY[n] = r1.H;
   }
-  __syncwarp();
-  if (unit >= fa.n_units) return;
 
   const int chain = unit / b.T, tt = unit % b.T;
   const int ds = b.chain_ds[chain];
-  const int nt = b.arm_n[(size_t)ds * b.T + tt];
+  const int nt = valid ? b.arm_n[(size_t)ds * b.T + tt] : 0;
+  const int nt_w = warp_max_over_units<LPU>(nt);
   const Rng rng = make_rng(seed, b.chain_id[chain]);
   const UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC, D);
 
@@ -237,7 +231,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const int *g_pat = b.arm_pat + ((size_t)ds * b.T + tt) * b.ntmax;
   const double *g_x = b.x + (size_t)ds * b.nobs * P;
   double *lik = fa.lik + (size_t)unit * fa.ncol * ntp;
-  double *uq = fa.uq + (size_t)unit * 2 * ntp;
+  const int uqs = ntp + 1;
+  double *uq = fa.uq + (size_t)unit * 2 * uqs;
   double *g_ez = b.zb + (size_t)chain * b.nobs * D;   // here: exp(beta'z) (scratch, rebuilt per sweep)
   double *g_ljj = b.ljj + (size_t)chain * b.nobs * D;
   const double *beta = b.beta + (size_t)chain * Q * D;
@@ -247,7 +242,6 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const int idxs = b.idxs[chain];
   const double iv2 = s.iv2, c0 = s.c0, hiv2 = s.hiv2;
   const double simscale = (s.calibration == 2) ? s.calscale : 1.0;
-  const bool nolik = s.nolik != 0;
 
   // ---- stage the unit's state in shared memory
   for (int e = ul; e < P * KSTR; e += LPU) {
@@ -256,9 +250,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     U.sumx2[e] = (j < KS) ? g_sumx2[(size_t)p * kcap + j] : 0.0;
   }
   for (int j = ul; j < KS; j += LPU) U.nj[j] = g_nj[j];
-  for (int it = ul; it < nt; it += LPU) {
-    U.lab[it] = g_lab[it];
-    U.pat[it] = g_pat[it];
+  for (int it = ul; it <= ntp; it += LPU) {
+    U.lab[it] = (it < nt) ? g_lab[it] : 1;
+    U.pat[it] = (it < nt) ? g_pat[it] : 0;
   }
   // column indirection: clusters 0..K-1 -> cols 0..K-1, aux m -> col K+m, the rest is free
   int nfree = 0;
@@ -271,8 +265,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   }
   // cohesion by cluster size: logn[0] is the auxiliary-cluster value (:677 / :680)
   if (ul == 0) U.logn[0] = (s.cohesion == 1) ? log(b.model.alpha) - log((double)CC) : 0.0;
-  for (int n = 1 + ul; n <= nt; n += LPU) U.logn[n] = (s.cohesion == 1) ? log((double)n) : log((double)n - sigma);
-  __syncwarp(um);
+  for (int n = 1 + ul; n <= nt; n += LPU) U.logn[n] = fast_log((s.cohesion == 1) ? (double)n : (double)n - sigma);
+  __syncwarp();
 
   auto dV_of = [&](int Kcur) -> double {
     if (s.cohesion != 2 || Kcur < 1) return 0.0;
@@ -281,50 +275,57 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   };
   auto colmap = [&](int j, int Kcur) -> int { return (j < Kcur) ? U.col[j] : U.col[KS + (j - Kcur)]; };
 
+  bool live = valid;
   int bail_l = -1, bail_it = 0;
 
-  for (int l = iter0; l < iter0 + n_sweeps && bail_l < 0; l++) {
-    if (K > KS) {
+  for (int l = iter0; l < iter0 + n_sweeps; l++) {
+    if (live && K > KS) {
       bail_l = l;
       bail_it = 0;
-      break;
+      live = false;
     }
+    if (!__any_sync(TPPMX_FULL, live)) break;
     // =========================== parallel pre-pass of the sweep ===========================
-    // :351-360 auxiliary eta ~ N(0, I)
-    for (int mm = ul; mm < CC; mm += LPU)
-      rng_normals(rng, l, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, D, g_etae + mm, CC);
-    __syncwarp(um);
-    // per patient: uniform, sum_p x^2, exp(beta'z), log JJ
-    for (int it = ul; it < nt; it += LPU) {
-      const int i = U.pat[it];
-      const double *xi = g_x + (size_t)i * P;
-      double qx = 0.0;
-      for (int p = 0; p < P; p++) qx = fma(xi[p], xi[p], qx);
-      double uu, u1;
-      rng_u2(rng, l, TPPMX_SITE_ALLOC_U, tt, (uint32_t)i, 0, uu, u1);
-      uq[it] = uu;
-      uq[ntp + it] = qx;
-      if (!nolik) {
-        const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
-        const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
-        for (int k = 0; k < D; k++) {
-          double acc = 0.0;
-          for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
-          g_ez[(size_t)i * D + k] = exp(acc);
-          g_ljj[(size_t)i * D + k] = log(JJ[k]);
+    if (live) {
+      // :351-360 auxiliary eta ~ N(0, I)
+      for (int mm = ul; mm < CC; mm += LPU)
+        rng_normals(rng, l, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, D, g_etae + mm, CC);
+      // per patient: uniform, sum_p x^2, exp(beta'z), log JJ
+      for (int it = ul; it < nt; it += LPU) {
+        const int i = U.pat[it];
+        const double *xi = g_x + (size_t)i * P;
+        double qx = 0.0;
+        for (int p = 0; p < P; p++) qx = fma(xi[p], xi[p], qx);
+        double uu, u1;
+        rng_u2(rng, l, TPPMX_SITE_ALLOC_U, tt, (uint32_t)i, 0, uu, u1);
+        uq[it] = uu;
+        uq[uqs + it] = qx;
+        if (!NOLIK) {
+          const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
+          const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
+          for (int k = 0; k < D; k++) {
+            double acc = 0.0;
+            for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
+            g_ez[(size_t)i * D + k] = fast_exp(acc);
+            g_ljj[(size_t)i * D + k] = fast_log(JJ[k]);
+          }
         }
       }
     }
-    if (!nolik) {
+    __syncwarp();
+    if (live && !NOLIK) {
       const int ntot = K + CC;
       // exp(eta) of every candidate cluster, stored by column id
       for (int e = ul; e < ntot * D; e += LPU) {
         const int c = e / D, k = e - c * D;
         const double eta = (c < K) ? g_eta[(size_t)k * kcap + c] : g_etae[k * CC + (c - K)];
-        U.E[colmap(c, K) * D + k] = exp(eta);
+        U.E[colmap(c, K) * D + k] = fast_exp(eta);
       }
-      __syncwarp(um);
+    }
+    __syncwarp();
+    if (live && !NOLIK) {
       // likelihood table: all (candidate cluster, patient) pairs, flattened over the lanes
+      const int ntot = K + CC;
       for (int e = ul; e < ntot * nt; e += LPU) {
         const int c = e / nt, it = e - c * nt;
         const int cl = colmap(c, K);
@@ -332,71 +333,61 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         lik[(size_t)cl * ntp + it] = fast_lik(U.E + cl * D, g_ez + (size_t)i * D, g_ljj + (size_t)i * D, D);
       }
     }
-    __syncwarp(um);
+    __syncwarp();
 
     // =========================== sequential reallocation steps ===========================
     double dV = dV_of(K);
     bool act0 = ul < K + CC;
     const double *likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
-    double likv = 0.0, uu = 0.0, qx = 0.0;
-    if (nt > 0) {  // operands of step 0
+    double likv = 0.0, uu = uq[0], qx = uq[uqs];
+    {  // operands of step 0
       const int i0 = U.pat[0];
 #pragma unroll
       for (int r = 0; r < XR; r++) {
         const int p = ul + r * LPU;
         if (p < P) U.xs[p] = g_x[(size_t)i0 * P + p];
       }
-      uu = uq[0];
-      qx = uq[ntp];
-      if (!nolik && act0) likv = likp[0];
+      if (!NOLIK) likv = likp[0];
     }
-    __syncwarp(um);
+    __syncwarp();
 
-    for (int it = 0; it < nt; it++) {
-      if (__builtin_expect(K >= KS, 0)) {  // a birth could overflow the staged capacity: hand over
+    for (int it = 0; it < nt_w; it++) {
+      bool on = live && it < nt;
+      if (on && K >= KS) {  // a birth could overflow the staged capacity: hand the unit over
         bail_l = l;
         bail_it = it;
-        break;
+        live = false;
+        on = false;
       }
       const double *xs = U.xs + (it & 1) * Pp;
-      // ---- prefetch the operands of step it+1 (addresses do not depend on this step)
-      const bool has_next = (it + 1 < nt);
-      double xr_n[XR], lik_n = 0.0, uu_n = 0.0, qx_n = 0.0;
-      if (has_next) {
+      // ---- prefetch the operands of step it+1 (addresses do not depend on this step; the
+      //      arrays are padded so the last step may read one entry past the arm)
+      double xr_n[XR], lik_n = 0.0;
+      {
         const double *xrow = g_x + (size_t)U.pat[it + 1] * P;
 #pragma unroll
         for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
           xr_n[r] = (p < P) ? xrow[p] : 0.0;
         }
-        uu_n = uq[it + 1];
-        qx_n = uq[ntp + it + 1];
-        if (!nolik && act0) lik_n = likp[it + 1];
       }
+      const double uu_n = uq[it + 1], qx_n = uq[uqs + it + 1];
+      if (!NOLIK) lik_n = likp[it + 1];
       bool structural = false;
 
       // ---- :368-457 take the patient out of its cluster
-      const int zi = U.lab[it] - 1;
+      const int zi = on ? U.lab[it] - 1 : 0;
       const int nzi = U.nj[zi];
-      __syncwarp(um);
-      if (__builtin_expect(nzi > 1, 1)) {
-        if (ul == 0) U.nj[zi] = nzi - 1;
-#pragma unroll
-        for (int r = 0; r < XR; r++) {
-          const int p = ul + r * LPU;
-          if (p < P) {
-            const double xv = xs[p];
-            U.sumx[p * KSTR + zi] = __dsub_rn(U.sumx[p * KSTR + zi], xv);
-            U.sumx2[p * KSTR + zi] = __dsub_rn(U.sumx2[p * KSTR + zi], __dmul_rn(xv, xv));
-          }
-        }
-      } else {  // singleton (:384-457)
-        structural = true;
+      const bool single = on && nzi <= 1;
+      __syncwarp();
+      if (__any_sync(TPPMX_FULL, single)) {  // singleton (:384-457), rare
         const int iaux = zi + 1, Kc = K;
-        if (iaux < Kc) {  // swap with the last cluster
+        const bool swp = single && iaux < Kc;
+        if (swp)  // swap with the last cluster
           for (int ii = ul; ii < nt; ii += LPU)
             if (U.lab[ii] == Kc) U.lab[ii] = iaux;
-          __syncwarp(um);
+        __syncwarp();
+        if (swp) {
           if (ul == 0) {
             U.lab[it] = Kc;
             U.nj[iaux - 1] = U.nj[Kc - 1];
@@ -418,33 +409,47 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
             U.sumx2[p * KSTR + iaux - 1] = U.sumx2[p * KSTR + Kc - 1];
             U.sumx2[p * KSTR + Kc - 1] = t;
           }
-          __syncwarp(um);
         }
-        // empty slot Kc-1 (keeps the rounding residue, as the reference does)
-        if (ul == 0) {
-          U.nj[Kc - 1] -= 1;
-          U.freec[nfree] = U.col[Kc - 1];
+        __syncwarp();
+        if (single) {  // empty slot Kc-1 (keeps the rounding residue, as the reference does)
+          if (ul == 0) {
+            U.nj[Kc - 1] -= 1;
+            U.freec[nfree] = U.col[Kc - 1];
+          }
+          nfree += 1;
+          for (int p = ul; p < P; p += LPU) {
+            const double xv = xs[p];
+            U.sumx[p * KSTR + Kc - 1] = __dsub_rn(U.sumx[p * KSTR + Kc - 1], xv);
+            U.sumx2[p * KSTR + Kc - 1] = __dsub_rn(U.sumx2[p * KSTR + Kc - 1], __dmul_rn(xv, xv));
+          }
+          K = Kc - 1;
+          dV = dV_of(K);
+          structural = true;
         }
-        nfree += 1;
-        for (int p = ul; p < P; p += LPU) {
-          const double xv = xs[p];
-          U.sumx[p * KSTR + Kc - 1] = __dsub_rn(U.sumx[p * KSTR + Kc - 1], xv);
-          U.sumx2[p * KSTR + Kc - 1] = __dsub_rn(U.sumx2[p * KSTR + Kc - 1], __dmul_rn(xv, xv));
-        }
-        K = Kc - 1;
-        dV = dV_of(K);
       }
-      __syncwarp(um);
-      if (__builtin_expect(structural, 0)) {
+      if (on && !single) {
+        if (ul == 0) U.nj[zi] = nzi - 1;
+#pragma unroll
+        for (int r = 0; r < XR; r++) {
+          const int p = ul + r * LPU;
+          if (p < P) {
+            const double xv = xs[p];
+            U.sumx[p * KSTR + zi] = __dsub_rn(U.sumx[p * KSTR + zi], xv);
+            U.sumx2[p * KSTR + zi] = __dsub_rn(U.sumx2[p * KSTR + zi], __dmul_rn(xv, xv));
+          }
+        }
+      }
+      __syncwarp();
+      if (structural) {
         act0 = ul < K + CC;
         likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
-        likv = (!nolik && act0) ? likp[it] : 0.0;
+        if (!NOLIK) likv = likp[it];
       }
 
       // ---- :460-814 score the K occupied + CC auxiliary clusters, normalise, draw
       const int ntot = K + CC;
       int newci;
-      if (__builtin_expect(ntot <= LPU, 1)) {
+      {
         const bool occ = ul < K;
         const int n = occ ? U.nj[ul] : 0;
         const double *sx = U.sumx + (occ ? ul : TPPMX_FAST_KSMAX);  // column 32: the empty cluster
@@ -466,108 +471,122 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         const double tY = a + iv2 * (2.0 * bb + iv2 * qx);
         const double d = t_dA[n] - hiv2 * qx + (t_HY[n] * tY - t_HN[n] * a);
         const double w = act0 ? dV + U.logn[n] + simscale * d + likv : -INFINITY;
-        const double wmax = unit_max<LPU>(w, um);
-        const double e0 = exp(w - wmax);
-        const double den = unit_sum<LPU>(e0, um);
-        const double cum = unit_incl_scan<LPU>(e0 / den, um, ul);
-        unsigned hit = __ballot_sync(um, act0 && (uu < cum));
+        // the shift only has to be common to the unit's lanes and close to the maximum: the
+        // float-rounded maximum costs a quarter of the shuffles of an fp64 max
+        const double wmax = (double)unit_maxf<LPU>((float)w);
+        const double e0 = act0 ? fast_exp(w - wmax) : 0.0;
+        const double cum = unit_incl_scan<LPU>(e0, ul);
+        const double den = __shfl_sync(TPPMX_FULL, cum, LPU - 1, LPU);
+        // uu < cumsum(e)/den  <=>  uu*den < cumsum(e)   (:805-814)
+        unsigned hit = __ballot_sync(TPPMX_FULL, act0 && (uu * den < cum));
         hit = (LPU == 32) ? hit : ((hit >> (sub * LPU)) & ((1u << LPU) - 1u));
         newci = hit ? __ffs(hit) : ntot;  // :807 default when rounding leaves uu >= total
-      } else {
-        newci = fast_score_multi<LPU>(U, t_dA, t_HN, t_HY, lik, ntp, it, K, CC, KS, P, xs, qx, uu, dV,
-                                      simscale, iv2, c0, hiv2, nolik, um, ul, sub);
+      }
+      const bool multi = on && ntot > LPU;
+      if (__any_sync(TPPMX_FULL, multi)) {
+        const int r = fast_score_multi<LPU>(U, t_dA, t_HN, t_HY, lik, ntp, it, K, CC, KS, P, xs, qx, uu, dV,
+                                            simscale, iv2, c0, hiv2, NOLIK, multi, ul, sub);
+        if (multi) newci = r;
       }
 
       // ---- :820-856 assign, update sufficient statistics
-      int lab;
-      if (__builtin_expect(newci <= K, 1)) {
-        lab = newci;
-        if (ul == 0) {
-          U.lab[it] = lab;
-          U.nj[lab - 1] += 1;
+      const bool born = on && newci > K;
+      int lab = newci;
+      if (on && !born && ul == 0) {
+        U.lab[it] = lab;
+        U.nj[lab - 1] += 1;
+      }
+      if (__any_sync(TPPMX_FULL, born)) {  // a new cluster takes the auxiliary eta (:829-845), rare
+        int m = 0, newcol = 0, i = 0;
+        if (born) {
+          i = U.pat[it];
+          m = newci - K - 1;
+          lab = K + 1;
+          newcol = U.freec[nfree - 1];
+          nfree -= 1;
         }
-      } else {  // a new cluster takes the auxiliary eta (:829-845)
-        structural = true;
-        const int i = U.pat[it];
-        const int m = newci - K - 1;
-        lab = K + 1;
-        const int newcol = U.freec[nfree - 1];
-        nfree -= 1;
-        __syncwarp(um);
-        if (ul == 0) {
-          U.lab[it] = lab;
-          U.nj[lab - 1] = 1;
-          U.col[lab - 1] = U.col[KS + m];
-          U.col[KS + m] = newcol;
-        }
-        for (int k = ul; k < D; k += LPU) g_eta[(size_t)k * kcap + lab - 1] = g_etae[k * CC + m];
-        __syncwarp(um);
-        if (ul == 0) rng_normals(rng, l, TPPMX_SITE_AUX_REFRESH, tt, (uint32_t)i, D, g_etae + m, CC);
-        __syncwarp(um);
-        if (!nolik) {  // likelihood column of the refreshed auxiliary eta, remaining patients
-          for (int k = ul; k < D; k += LPU) U.E[newcol * D + k] = exp(g_etae[k * CC + m]);
-          __syncwarp(um);
-          for (int it2 = it + 1 + ul; it2 < nt; it2 += LPU) {
-            const int i2 = U.pat[it2];
-            lik[(size_t)newcol * ntp + it2] =
-                fast_lik(U.E + newcol * D, g_ez + (size_t)i2 * D, g_ljj + (size_t)i2 * D, D);
+        __syncwarp();
+        if (born) {
+          if (ul == 0) {
+            U.lab[it] = lab;
+            U.nj[lab - 1] = 1;
+            U.col[lab - 1] = U.col[KS + m];
+            U.col[KS + m] = newcol;
           }
+          for (int k = ul; k < D; k += LPU) g_eta[(size_t)k * kcap + lab - 1] = g_etae[k * CC + m];
         }
-        K = lab;
-        dV = dV_of(K);
-      }
-#pragma unroll
-      for (int r = 0; r < XR; r++) {
-        const int p = ul + r * LPU;
-        if (p < P) {
-          const double xv = xs[p];
-          U.sumx[p * KSTR + lab - 1] = __dadd_rn(U.sumx[p * KSTR + lab - 1], xv);
-          U.sumx2[p * KSTR + lab - 1] = __dadd_rn(U.sumx2[p * KSTR + lab - 1], __dmul_rn(xv, xv));
+        __syncwarp();
+        if (born && ul == 0) rng_normals(rng, l, TPPMX_SITE_AUX_REFRESH, tt, (uint32_t)i, D, g_etae + m, CC);
+        __syncwarp();
+        if (born && !NOLIK)
+          for (int k = ul; k < D; k += LPU) U.E[newcol * D + k] = fast_exp(g_etae[k * CC + m]);
+        __syncwarp();
+        if (born) {
+          if (!NOLIK)  // likelihood column of the refreshed auxiliary eta, remaining patients
+            for (int it2 = it + 1 + ul; it2 < nt; it2 += LPU) {
+              const int i2 = U.pat[it2];
+              lik[(size_t)newcol * ntp + it2] =
+                  fast_lik(U.E + newcol * D, g_ez + (size_t)i2 * D, g_ljj + (size_t)i2 * D, D);
+            }
+          K = lab;
+          dV = dV_of(K);
+          structural = true;
         }
       }
-      // ---- stage the operands of the next step
-      if (has_next) {
+      if (on) {
 #pragma unroll
         for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
-          if (p < P) U.xs[((it + 1) & 1) * Pp + p] = xr_n[r];
+          if (p < P) {
+            const double xv = xs[p];
+            U.sumx[p * KSTR + lab - 1] = __dadd_rn(U.sumx[p * KSTR + lab - 1], xv);
+            U.sumx2[p * KSTR + lab - 1] = __dadd_rn(U.sumx2[p * KSTR + lab - 1], __dmul_rn(xv, xv));
+          }
         }
-        uu = uu_n;
-        qx = qx_n;
-        likv = lik_n;
       }
-      __syncwarp(um);
-      if (__builtin_expect(structural, 0)) {
+      // ---- stage the operands of the next step
+#pragma unroll
+      for (int r = 0; r < XR; r++) {
+        const int p = ul + r * LPU;
+        if (p < P) U.xs[((it + 1) & 1) * Pp + p] = xr_n[r];
+      }
+      uu = uu_n;
+      qx = qx_n;
+      likv = lik_n;
+      __syncwarp();
+      if (structural) {
         act0 = ul < K + CC;
         likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
-        likv = (has_next && !nolik && act0) ? likp[it + 1] : 0.0;
+        if (!NOLIK) likv = likp[it + 1];
       }
     }
   }
 
   // ---- write the unit back in the library's global layout
-  __syncwarp(um);
-  for (int e = ul; e < P * KSTR; e += LPU) {
-    const int p = e / KSTR, j = e % KSTR;
-    if (j < KS) {
-      g_sumx[(size_t)p * kcap + j] = U.sumx[e];
-      g_sumx2[(size_t)p * kcap + j] = U.sumx2[e];
+  __syncwarp();
+  if (valid) {
+    for (int e = ul; e < P * KSTR; e += LPU) {
+      const int p = e / KSTR, j = e % KSTR;
+      if (j < KS) {
+        g_sumx[(size_t)p * kcap + j] = U.sumx[e];
+        g_sumx2[(size_t)p * kcap + j] = U.sumx2[e];
+      }
+    }
+    for (int j = ul; j < KS; j += LPU) g_nj[j] = U.nj[j];
+    for (int it = ul; it < nt; it += LPU) g_lab[it] = U.lab[it];
+    if (ul == 0) {
+      b.nclu[(size_t)chain * b.T + tt] = K;
+      fa.resume_l[unit] = bail_l;
+      fa.resume_it[unit] = bail_it;
+      if (bail_l >= 0) atomicAdd(fa.bail_count, 1);
     }
   }
-  for (int j = ul; j < KS; j += LPU) g_nj[j] = U.nj[j];
-  for (int it = ul; it < nt; it += LPU) g_lab[it] = U.lab[it];
-  if (ul == 0) {
-    b.nclu[(size_t)chain * b.T + tt] = K;
-    fa.resume_l[unit] = bail_l;
-    fa.resume_it[unit] = bail_it;
-    if (bail_l >= 0) atomicAdd(fa.bail_count, 1);
-  }
-  __syncwarp(um);
+  __syncwarp();
   // loggamma (:825, :839): eta* is constant during the sweep, so the value every patient ends
   // with is eta*[label] + beta'z, evaluated here once in the reference's operation order
   // (utils_ct.cpp:514-527).  A unit that handed over leaves this to the generic kernel for
   // the patients it still has to visit; rewriting the visited ones is value-preserving.
-  if (n_sweeps > 0) {
+  if (valid && n_sweeps > 0) {
     for (int it = ul; it < nt; it += LPU) {
       const int i = U.pat[it];
       const int lb = U.lab[it];

@@ -731,8 +731,8 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     fa.n_units = d.n_chains * d.T;
     fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D);
     fa.tab_bytes = (int)fast_tab_bytes(d.ntmax);
-    RC(dev_alloc(b, &fa.lik, (size_t)fa.n_units * fa.ncol * fa.ntp));
-    RC(dev_alloc(b, &fa.uq, (size_t)fa.n_units * 2 * fa.ntp));
+    RC(dev_alloc(b, &fa.lik, (size_t)fa.n_units * fa.ncol * fa.ntp + fa.ntp + 8));
+    RC(dev_alloc(b, &fa.uq, (size_t)fa.n_units * 2 * (fa.ntp + 1) + 8));
     RC(dev_alloc(b, &fa.resume_l, (size_t)fa.n_units));
     RC(dev_alloc(b, &fa.resume_it, (size_t)fa.n_units));
     RC(dev_alloc(b, &fa.bail_count, 1));
@@ -742,20 +742,24 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
   return TPPMX_OK;
 }
 
-template <int LPU, int XR>
-static cudaError_t fast_launch2(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int LPU, int XR, bool NOLIK>
+static cudaError_t fast_launch3(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, NOLIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (b->fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR><<<grid, 32, smem, b->ctx->stream>>>(b->d, b->fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, NOLIK><<<grid, 32, smem, b->ctx->stream>>>(b->d, b->fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
 }
 template <int LPU>
 static cudaError_t fast_launch(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
   // XR = registers per lane that hold the next patient's covariate row (P <= XR * LPU)
-  if (b->d.P <= LPU) return fast_launch2<LPU, 1>(b, smem, seed, iter0, n_sweeps);
-  return fast_launch2<LPU, 4>(b, smem, seed, iter0, n_sweeps);
+  const bool nolik = b->d.model.nolik != 0;
+  if (b->d.P <= LPU)
+    return nolik ? fast_launch3<LPU, 1, true>(b, smem, seed, iter0, n_sweeps)
+                 : fast_launch3<LPU, 1, false>(b, smem, seed, iter0, n_sweeps);
+  return nolik ? fast_launch3<LPU, 4, true>(b, smem, seed, iter0, n_sweeps)
+               : fast_launch3<LPU, 4, false>(b, smem, seed, iter0, n_sweeps);
 }
 
 extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps) {
