@@ -168,6 +168,10 @@ int tppmx_create(tppmx_ctx **ctx, int device);
 int tppmx_destroy(tppmx_ctx *ctx);
 const char *tppmx_last_error(const tppmx_ctx *ctx);
 
+/* Test hook: evaluates the library's device fp64 math on n inputs (which: 0 = log, 1 = exp,
+ * 2 = lgamma for x > 0, the branch-free versions the fast sweep kernel uses). */
+int tppmx_probe_math(tppmx_ctx *ctx, int32_t which, const double *x, int32_t n, double *out);
+
 /* ---- batch of chains ---------------------------------------------------------------- */
 /* chain c runs on dataset chain_dataset[c] and uses Philox stream id chain_id[c]
  * (NULL => c).  All datasets share dims; copies everything it needs to the device. */

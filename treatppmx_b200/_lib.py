@@ -12,7 +12,7 @@ SO_PATH = os.path.join(_HERE, "libtppmx.so")
 
 # every symbol include/tppmx.h declares
 SYMBOLS = [
-    "tppmx_version", "tppmx_create", "tppmx_destroy", "tppmx_last_error",
+    "tppmx_version", "tppmx_create", "tppmx_destroy", "tppmx_last_error", "tppmx_probe_math",
     "tppmx_batch_create", "tppmx_batch_destroy", "tppmx_batch_init",
     "tppmx_batch_set_state", "tppmx_batch_get_state", "tppmx_batch_get_partitions",
     "tppmx_score_patient",
@@ -45,6 +45,7 @@ def load():
     L.tppmx_destroy.argtypes = [vp]
     L.tppmx_last_error.argtypes = [vp]
     L.tppmx_last_error.restype = C.c_char_p
+    L.tppmx_probe_math.argtypes = [vp, i32, c_dp, i32, c_dp]
     L.tppmx_batch_create.argtypes = [vp, C.POINTER(Model), C.POINTER(Dims), C.POINTER(Shared), i32,
                                      C.POINTER(Dataset), i32, c_ip, c_ip, C.POINTER(vp)]
     L.tppmx_batch_destroy.argtypes = [vp]

@@ -120,9 +120,39 @@ __device__ __forceinline__ int warp_max_over_units(int v) {
 // The only call site of the lgamma code (keeps the kernel's instruction footprint small).
 __device__ __noinline__ double fast_lik(const double *E, const double *Z, const double *ljj, int D) {
   double w = 0.0;
-  for (int k = 0; k < D; k++) {
-    const double g = E[k] * Z[k];
-    w += fma(g, ljj[k], -lgamma_pos(g));
+  // three outcome categories per trip: the three lgamma evaluations are independent straight-line
+  // code, so their dependent fma chains interleave (fp64 latency hiding inside one warp)
+  for (int k = 0; k < D; k += 3) {
+    const bool h1 = k + 1 < D, h2 = k + 2 < D;
+    const double g0 = E[k] * Z[k];
+    const double g1 = h1 ? E[k + 1] * Z[k + 1] : 1.0;
+    const double g2 = h2 ? E[k + 2] * Z[k + 2] : 1.0;
+    const double l0 = lgamma_pos(g0), l1 = lgamma_pos(g1), l2 = lgamma_pos(g2);
+    w += fma(g0, ljj[k], -l0);
+    if (h1) w += fma(g1, ljj[k + 1], -l1);
+    if (h2) w += fma(g2, ljj[k + 2], -l2);
+  }
+  return w;
+}
+
+// Register version for the pre-pass: the patient's exp(zb) / log JJ stay in registers while the
+// lane walks over the candidate clusters (one L2 round trip per patient instead of one per
+// table entry).  DR = 3 or TPPMX_MAXD.
+template <int DR>
+__device__ __forceinline__ double fast_lik_reg(const double *E, const double (&Z)[DR], const double (&ljj)[DR], int D) {
+  double w = 0.0;
+#pragma unroll
+  for (int k = 0; k < DR; k += 3) {
+    if (k < D) {
+      const bool h1 = (k + 1 < DR) && (k + 1 < D), h2 = (k + 2 < DR) && (k + 2 < D);
+      const double g0 = E[k] * Z[k];
+      const double g1 = h1 ? E[k + 1] * Z[(k + 1 < DR) ? k + 1 : k] : 1.0;
+      const double g2 = h2 ? E[k + 2] * Z[(k + 2 < DR) ? k + 2 : k] : 1.0;
+      const double l0 = lgamma_pos(g0), l1 = lgamma_pos(g1), l2 = lgamma_pos(g2);
+      w += fma(g0, ljj[k], -l0);
+      if (h1) w += fma(g1, ljj[(k + 1 < DR) ? k + 1 : k], -l1);
+      if (h2) w += fma(g2, ljj[(k + 2 < DR) ? k + 2 : k], -l2);
+    }
   }
   return w;
 }
@@ -187,7 +217,7 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double *t_dA, con
   return newci;
 }
 
-template <int LPU, int XR, bool NOLIK>
+template <int LPU, int XR, int DR, bool NOLIK>
 __global__ void __launch_bounds__(32, 12)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -286,11 +316,23 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     }
     if (!__any_sync(TPPMX_FULL, live)) break;
     // =========================== parallel pre-pass of the sweep ===========================
-    if (live) {
-      // :351-360 auxiliary eta ~ N(0, I)
+    if (live)  // :351-360 auxiliary eta ~ N(0, I)
       for (int mm = ul; mm < CC; mm += LPU)
         rng_normals(rng, l, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, D, g_etae + mm, CC);
-      // per patient: uniform, sum_p x^2, exp(beta'z), log JJ
+    __syncwarp();
+    if (live && !NOLIK) {  // exp(eta) of every candidate cluster, stored by column id
+      const int ntot = K + CC;
+      for (int e = ul; e < ntot * D; e += LPU) {
+        const int c = e / D, k = e - c * D;
+        const double eta = (c < K) ? g_eta[(size_t)k * kcap + c] : g_etae[k * CC + (c - K)];
+        U.E[colmap(c, K) * D + k] = fast_exp(eta);
+      }
+    }
+    __syncwarp();
+    if (live) {
+      // per patient (one lane each): allocation uniform, sum_p x^2, exp(beta'z), log JJ, and
+      // the likelihood-table entries of every candidate cluster
+      const int ntot = K + CC;
       for (int it = ul; it < nt; it += LPU) {
         const int i = U.pat[it];
         const double *xi = g_x + (size_t)i * P;
@@ -303,34 +345,25 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         if (!NOLIK) {
           const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
           const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
-          for (int k = 0; k < D; k++) {
-            double acc = 0.0;
-            for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
-            g_ez[(size_t)i * D + k] = fast_exp(acc);
-            g_ljj[(size_t)i * D + k] = fast_log(JJ[k]);
+          double Z[DR], ljj[DR];
+#pragma unroll
+          for (int k = 0; k < DR; k++) {
+            Z[k] = 1.0;
+            ljj[k] = 0.0;
+            if (k < D) {
+              double acc = 0.0;
+              for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
+              Z[k] = fast_exp(acc);
+              ljj[k] = fast_log(JJ[k]);
+              g_ez[(size_t)i * D + k] = Z[k];
+              g_ljj[(size_t)i * D + k] = ljj[k];
+            }
+          }
+          for (int c = 0; c < ntot; c++) {
+            const int cl = colmap(c, K);
+            lik[(size_t)cl * ntp + it] = fast_lik_reg<DR>(U.E + cl * D, Z, ljj, D);
           }
         }
-      }
-    }
-    __syncwarp();
-    if (live && !NOLIK) {
-      const int ntot = K + CC;
-      // exp(eta) of every candidate cluster, stored by column id
-      for (int e = ul; e < ntot * D; e += LPU) {
-        const int c = e / D, k = e - c * D;
-        const double eta = (c < K) ? g_eta[(size_t)k * kcap + c] : g_etae[k * CC + (c - K)];
-        U.E[colmap(c, K) * D + k] = fast_exp(eta);
-      }
-    }
-    __syncwarp();
-    if (live && !NOLIK) {
-      // likelihood table: all (candidate cluster, patient) pairs, flattened over the lanes
-      const int ntot = K + CC;
-      for (int e = ul; e < ntot * nt; e += LPU) {
-        const int c = e / nt, it = e - c * nt;
-        const int cl = colmap(c, K);
-        const int i = U.pat[it];
-        lik[(size_t)cl * ntp + it] = fast_lik(U.E + cl * D, g_ez + (size_t)i * D, g_ljj + (size_t)i * D, D);
       }
     }
     __syncwarp();

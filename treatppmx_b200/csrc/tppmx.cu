@@ -18,17 +18,49 @@
 
 using namespace tppmx;
 
+// One device allocation + one pinned host mirror of its upload region per batch.  A destroyed
+// batch leaves its arena with the context, so create/destroy cycles (one batch per group of
+// replicate datasets) cost no cudaMalloc / cudaFree after the first.
+struct Arena {
+  char *dbase = nullptr;
+  size_t dcap = 0;
+  char *hbase = nullptr;  // pinned
+  size_t hcap = 0;
+};
+static void arena_free(Arena &a) {
+  if (a.dbase) cudaFree(a.dbase);
+  if (a.hbase) cudaFreeHost(a.hbase);
+  a = Arena();
+}
+
 struct tppmx_ctx {
   int device;
   cudaStream_t stream;
   std::string err;
+  Arena spare;
+  int live_batches = 0;  // tppmx_destroy is deferred until the last batch is gone
+  bool closed = false;
 };
+static void ctx_release(tppmx_ctx *c) {
+  cudaSetDevice(c->device);
+  cudaStreamDestroy(c->stream);
+  arena_free(c->spare);
+  delete c;
+}
 
 struct tppmx_batch {
   tppmx_ctx *ctx;
   DevBatch d;  // device pointers + dims
   tppmx_dims dims;
-  std::vector<void *> allocs;
+  Arena ar;
+  bool dry = false;                // sizing pass of tppmx_batch_create
+  size_t up_need = 0, st_need = 0; // bytes: upload region, state region
+  size_t up_used = 0, st_used = 0;
+  // scratch reserved at creation (no allocation on the call paths)
+  int *init_lab = nullptr, *init_ncl = nullptr;
+  double *init_beta = nullptr;
+  double *pred_pi = nullptr, *pred_y = nullptr, *score_w = nullptr;
+  int *pred_c = nullptr, *score_k = nullptr;
   std::vector<int> arm_n;     // [nd][T]
   std::vector<int> chain_ds;  // [nc+1]
   cudaEvent_t ev0, ev1;
@@ -75,35 +107,73 @@ extern "C" int tppmx_create(tppmx_ctx **out, int device) {
 
 extern "C" int tppmx_destroy(tppmx_ctx *c) {
   if (!c) return TPPMX_OK;
-  cudaSetDevice(c->device);
-  cudaStreamDestroy(c->stream);
-  delete c;
+  c->closed = true;
+  if (c->live_batches == 0) ctx_release(c);
   return TPPMX_OK;
 }
 
 extern "C" const char *tppmx_last_error(const tppmx_ctx *c) { return c ? c->err.c_str() : "no context"; }
 
+__global__ void probe_math_kernel(int which, const double *x, int n, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = which == 0 ? fast_log(x[i]) : which == 1 ? fast_exp(x[i]) : lgamma_pos(x[i]);
+}
+
+extern "C" int tppmx_probe_math(tppmx_ctx *ctx, int32_t which, const double *x, int32_t n, double *out) {
+  if (!ctx || !x || !out || n < 0 || which < 0 || which > 2) return TPPMX_ERR_ARG;
+  if (n == 0) return TPPMX_OK;
+  CK(ctx, cudaSetDevice(ctx->device));
+  double *dx = nullptr, *dy = nullptr;
+  CK(ctx, cudaMalloc(&dx, sizeof(double) * n));
+  CK(ctx, cudaMalloc(&dy, sizeof(double) * n));
+  cudaError_t e = cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    probe_math_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(which, dx, n, dy);
+    e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dy);
+  if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("probe_math: ") + cudaGetErrorString(e));
+  return TPPMX_OK;
+}
+
 // ---- allocation helpers -------------------------------------------------------------------
+static inline size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
+// state region (zero-initialised by one memset at the end of tppmx_batch_create)
 template <class T>
 static int dev_alloc(tppmx_batch *b, T **p, size_t n, bool zero = true) {
-  void *q = nullptr;
+  (void)zero;
   if (n == 0) n = 1;
-  CK(b->ctx, cudaMalloc(&q, n * sizeof(T)));
-  b->allocs.push_back(q);
-  if (zero) CK(b->ctx, cudaMemsetAsync(q, 0, n * sizeof(T), b->ctx->stream));
-  *p = (T *)q;
+  const size_t bytes = al256(n * sizeof(T));
+  if (b->dry) {
+    b->st_need += bytes;
+    *p = nullptr;
+    return TPPMX_OK;
+  }
+  if (b->st_used + bytes > b->st_need) return TPPMX_ERR_NOMEM;
+  *p = (T *)(b->ar.dbase + b->up_need + b->st_used);
+  b->st_used += bytes;
   return TPPMX_OK;
 }
+// upload region: staged in the pinned mirror, sent with one copy
 template <class T>
 static int dev_upload(tppmx_batch *b, const T **p, const std::vector<T> &h) {
-  T *q = nullptr;
-  int rc = dev_alloc(b, &q, h.size(), false);
-  if (rc) return rc;
-  if (!h.empty()) CK(b->ctx, cudaMemcpyAsync(q, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, b->ctx->stream));
-  CK(b->ctx, cudaStreamSynchronize(b->ctx->stream));  // h may be a temporary
-  *p = q;
+  const size_t bytes = al256((h.empty() ? 1 : h.size()) * sizeof(T));
+  if (b->dry) {
+    b->up_need += bytes;
+    *p = nullptr;
+    return TPPMX_OK;
+  }
+  if (b->up_used + bytes > b->up_need) return TPPMX_ERR_NOMEM;
+  if (!h.empty()) memcpy(b->ar.hbase + b->up_used, h.data(), h.size() * sizeof(T));
+  *p = (const T *)(b->ar.dbase + b->up_used);
+  b->up_used += bytes;
   return TPPMX_OK;
 }
+static bool fast_eligible(const tppmx_batch *b, int lpu);
+static int fast_reserve(tppmx_batch *b);
 #define RC(x)            \
   do {                   \
     int rc__ = (x);      \
@@ -136,7 +206,7 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
                                   const tppmx_dataset *datasets, int32_t n_chains,
                                   const int32_t *chain_dataset, const int32_t *chain_id,
                                   tppmx_batch **out) {
-  if (!ctx) return TPPMX_ERR_ARG;
+  if (!ctx || ctx->closed) return TPPMX_ERR_ARG;
   if (!model || !dims || !shared || !datasets || !out || n_datasets < 1 || n_chains < 1)
     return fail(ctx, TPPMX_ERR_ARG, "null or empty argument");
   const tppmx_dims &dm = *dims;
@@ -155,6 +225,7 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
 
   tppmx_batch *b = new tppmx_batch();
   b->ctx = ctx;
+  ctx->live_batches++;
   b->dims = dm;
   if (b->dims.kcap <= 0 || b->dims.kcap > dm.ntmax) b->dims.kcap = dm.ntmax;
   b->last_ms = 0;
@@ -177,7 +248,23 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
     if (rc) goto bad;          \
   } while (0)
 
-  {
+  // pass 0 sizes the two regions, pass 1 fills them (see Arena)
+  for (int pass = 0; pass < 2; pass++) {
+    b->dry = (pass == 0);
+    if (pass == 1) {
+      Arena &sp = ctx->spare;
+      const size_t need = b->up_need + b->st_need;
+      if (sp.dcap >= need && sp.hcap >= b->up_need) {
+        b->ar = sp;
+        sp = Arena();
+      } else {
+        arena_free(sp);
+        if (cudaMalloc((void **)&b->ar.dbase, need) != cudaSuccess) { rc = fail(ctx, TPPMX_ERR_NOMEM, "cudaMalloc of the batch arena failed"); goto bad; }
+        b->ar.dcap = need;
+        if (cudaHostAlloc((void **)&b->ar.hbase, b->up_need, cudaHostAllocDefault) != cudaSuccess) { rc = fail(ctx, TPPMX_ERR_NOMEM, "cudaHostAlloc of the staging mirror failed"); goto bad; }
+        b->ar.hcap = b->up_need;
+      }
+    }
     // shared
     std::vector<int> catvec(nc1, 0);
     for (int p = 0; p < ncat; p++) catvec[p] = shared->catvec[p];
@@ -198,7 +285,7 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
     std::vector<double> y((size_t)n_datasets * nobs * D);
     std::vector<double> zp((size_t)n_datasets * npred * Q), xp((size_t)n_datasets * npred * P), xp2(xp.size());
     std::vector<int> xcp((size_t)n_datasets * npred * nc1, 0);
-    for (int ds = 0; ds < n_datasets; ds++) {
+    for (int ds = 0; ds < n_datasets && !b->dry; ds++) {
       const tppmx_dataset &s = datasets[ds];
       if (!s.treat || !s.y || (Q > 0 && !s.z) || (P > 0 && !s.xcon) || (ncat > 0 && !s.xcat)) {
         rc = fail(ctx, TPPMX_ERR_ARG, "dataset has null arrays");
@@ -267,16 +354,8 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
       cid[c] = chain_id ? (uint32_t)chain_id[c] : (uint32_t)c;
     }
     b->chain_ds = cds;
-    {
-      int *p1 = nullptr;
-      uint32_t *p2 = nullptr;
-      TRY(dev_alloc(b, &p1, ns, false));
-      TRY(dev_alloc(b, &p2, ns, false));
-      CK(ctx, cudaMemcpy(p1, cds.data(), ns * sizeof(int), cudaMemcpyHostToDevice));
-      CK(ctx, cudaMemcpy(p2, cid.data(), ns * sizeof(uint32_t), cudaMemcpyHostToDevice));
-      d.chain_ds = p1;
-      d.chain_id = p2;
-    }
+    TRY(dev_upload(b, &d.chain_ds, cds));
+    TRY(dev_upload(b, &d.chain_id, cid));
     TRY(dev_alloc(b, &d.labels, ns * st_labels(d)));
     TRY(dev_alloc(b, &d.nj, ns * st_nj(d)));
     TRY(dev_alloc(b, &d.nclu, ns * T));
@@ -302,7 +381,23 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
     TRY(dev_alloc(b, &d.ljj, ns * st_pat(d)));
     TRY(dev_alloc(b, &d.cpat, ns * nobs));
     TRY(dev_alloc(b, &d.wbuf, ns * st_wbuf(d)));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    // scratch of the call paths, reserved here so that no call allocates
+    TRY(dev_alloc(b, &b->init_lab, (size_t)n_datasets * T * d.ntmax));
+    TRY(dev_alloc(b, &b->init_ncl, (size_t)n_datasets * T));
+    TRY(dev_alloc(b, &b->init_beta, (size_t)Q * D + 1));
+    TRY(dev_alloc(b, &b->score_w, (size_t)2 * (d.kcap + d.CC)));
+    TRY(dev_alloc(b, &b->score_k, 1));
+    if (npred > 0) {
+      TRY(dev_alloc(b, &b->pred_pi, (size_t)n_chains * npred * D * T));
+      TRY(dev_alloc(b, &b->pred_y, (size_t)n_chains * npred * D * T));
+      TRY(dev_alloc(b, &b->pred_c, (size_t)n_chains * npred * T));
+    }
+    if (fast_eligible(b, 32)) TRY(fast_reserve(b));
+    if (pass == 1) {
+      CK(ctx, cudaMemcpyAsync(b->ar.dbase, b->ar.hbase, b->up_used, cudaMemcpyHostToDevice, ctx->stream));
+      CK(ctx, cudaMemsetAsync(b->ar.dbase + b->up_need, 0, b->st_used, ctx->stream));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
   }
   *out = b;
   return TPPMX_OK;
@@ -315,10 +410,20 @@ bad:
 extern "C" int tppmx_batch_destroy(tppmx_batch *b) {
   if (!b) return TPPMX_OK;
   cudaSetDevice(b->ctx->device);
-  for (void *p : b->allocs) cudaFree(p);
+  if (b->ar.dbase) {  // leave the arena with the context for the next batch (keep the larger one)
+    Arena &sp = b->ctx->spare;
+    if (b->ar.dcap > sp.dcap || (b->ar.dcap == sp.dcap && b->ar.hcap > sp.hcap)) {
+      arena_free(sp);
+      sp = b->ar;
+    } else {
+      arena_free(b->ar);
+    }
+  }
   cudaEventDestroy(b->ev0);
   cudaEventDestroy(b->ev1);
+  tppmx_ctx *c = b->ctx;
   delete b;
+  if (--c->live_batches == 0 && c->closed) ctx_release(c);
   return TPPMX_OK;
 }
 
@@ -459,19 +564,13 @@ extern "C" int tppmx_batch_init(tppmx_batch *b, uint64_t seed, const int32_t *in
         lab[((size_t)ds * T + t) * nt + it] = v;
       }
     }
-  int *dl = nullptr, *dn = nullptr;
-  double *db = nullptr;
-  CK(ctx, cudaMalloc(&dl, lab.size() * sizeof(int)));
-  CK(ctx, cudaMalloc(&dn, ncl.size() * sizeof(int)));
-  CK(ctx, cudaMalloc(&db, (size_t)(d.Q * d.D + 1) * sizeof(double)));
-  CK(ctx, cudaMemcpy(dl, lab.data(), lab.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CK(ctx, cudaMemcpy(dn, ncl.data(), ncl.size() * sizeof(int), cudaMemcpyHostToDevice));
-  if (d.Q > 0) CK(ctx, cudaMemcpy(db, initbeta, (size_t)d.Q * d.D * sizeof(double), cudaMemcpyHostToDevice));
+  int *dl = b->init_lab, *dn = b->init_ncl;
+  double *db = b->init_beta;
+  CK(ctx, cudaMemcpyAsync(dl, lab.data(), lab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dn, ncl.data(), ncl.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (d.Q > 0) CK(ctx, cudaMemcpyAsync(db, initbeta, (size_t)d.Q * d.D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   init_kernel<<<d.n_chains, 128, 0, ctx->stream>>>(d, seed, dl, dn, db);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(dl);
-  cudaFree(dn);
-  cudaFree(db);
   if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("init_kernel: ") + cudaGetErrorString(e));
   CK(ctx, cudaGetLastError());
   return TPPMX_OK;
@@ -719,11 +818,25 @@ static bool fast_eligible(const tppmx_batch *b, int lpu) {
          d.ncat == 0 && m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
 }
 
+// scratch of the fast sweep kernel, sized for the largest staged capacity (part of the arena)
+static int fast_reserve(tppmx_batch *b) {
+  const DevBatch &d = b->d;
+  FastArgs &fa = b->fa;
+  const size_t KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
+  const size_t ntp = (d.ntmax + 3) & ~3, units = (size_t)d.n_chains * d.T;
+  RC(dev_alloc(b, &fa.lik, units * (KS + d.CC) * ntp + ntp + 8));
+  RC(dev_alloc(b, &fa.uq, units * 2 * (ntp + 1) + 8));
+  RC(dev_alloc(b, &fa.resume_l, units));
+  RC(dev_alloc(b, &fa.resume_it, units));
+  RC(dev_alloc(b, &fa.bail_count, 1));
+  return TPPMX_OK;
+}
+
 static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
   DevBatch &d = b->d;
   FastArgs &fa = b->fa;
+  if (!fa.lik) return fail(b->ctx, TPPMX_ERR_ARG, "fast sweep scratch was not reserved for this batch");
   if (!b->fast_ready) {
-    memset(&fa, 0, sizeof(fa));
     fa.KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
     if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
     fa.ntp = (d.ntmax + 3) & ~3;
@@ -731,35 +844,36 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     fa.n_units = d.n_chains * d.T;
     fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D);
     fa.tab_bytes = (int)fast_tab_bytes(d.ntmax);
-    RC(dev_alloc(b, &fa.lik, (size_t)fa.n_units * fa.ncol * fa.ntp + fa.ntp + 8));
-    RC(dev_alloc(b, &fa.uq, (size_t)fa.n_units * 2 * (fa.ntp + 1) + 8));
-    RC(dev_alloc(b, &fa.resume_l, (size_t)fa.n_units));
-    RC(dev_alloc(b, &fa.resume_it, (size_t)fa.n_units));
-    RC(dev_alloc(b, &fa.bail_count, 1));
     b->fast_ready = true;
   }
   *smem_out = (size_t)fa.tab_bytes + (size_t)(32 / lpu) * fa.unit_bytes;
   return TPPMX_OK;
 }
 
-template <int LPU, int XR, bool NOLIK>
-static cudaError_t fast_launch3(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, NOLIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int LPU, int XR, int DR, bool NOLIK>
+static cudaError_t fast_launch4(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (b->fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, NOLIK><<<grid, 32, smem, b->ctx->stream>>>(b->d, b->fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, DR, NOLIK><<<grid, 32, smem, b->ctx->stream>>>(b->d, b->fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
+}
+template <int LPU, int XR>
+static cudaError_t fast_launch2(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
+  const bool nolik = b->d.model.nolik != 0;
+  // DR = registers of the pre-pass that hold a patient's exp(zb) / log JJ (D <= 3 is the package's case)
+  if (b->d.D <= 3)
+    return nolik ? fast_launch4<LPU, XR, 3, true>(b, smem, seed, iter0, n_sweeps)
+                 : fast_launch4<LPU, XR, 3, false>(b, smem, seed, iter0, n_sweeps);
+  return nolik ? fast_launch4<LPU, XR, TPPMX_MAXD, true>(b, smem, seed, iter0, n_sweeps)
+               : fast_launch4<LPU, XR, TPPMX_MAXD, false>(b, smem, seed, iter0, n_sweeps);
 }
 template <int LPU>
 static cudaError_t fast_launch(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
   // XR = registers per lane that hold the next patient's covariate row (P <= XR * LPU)
-  const bool nolik = b->d.model.nolik != 0;
-  if (b->d.P <= LPU)
-    return nolik ? fast_launch3<LPU, 1, true>(b, smem, seed, iter0, n_sweeps)
-                 : fast_launch3<LPU, 1, false>(b, smem, seed, iter0, n_sweeps);
-  return nolik ? fast_launch3<LPU, 4, true>(b, smem, seed, iter0, n_sweeps)
-               : fast_launch3<LPU, 4, false>(b, smem, seed, iter0, n_sweeps);
+  if (b->d.P <= LPU) return fast_launch2<LPU, 1>(b, smem, seed, iter0, n_sweeps);
+  return fast_launch2<LPU, 4>(b, smem, seed, iter0, n_sweeps);
 }
 
 extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps) {
@@ -848,18 +962,14 @@ extern "C" int tppmx_score_patient(tppmx_batch *b, int32_t chain, int32_t arm, i
   CK(ctx, cudaSetDevice(ctx->device));
   RC(copy_chain_to_scratch(b, chain));
   const int W = d.kcap + d.CC;
-  double *dw = nullptr;
-  int *dk = nullptr;
-  CK(ctx, cudaMalloc(&dw, sizeof(double) * 2 * W));
-  CK(ctx, cudaMalloc(&dk, sizeof(int)));
+  double *dw = b->score_w;
+  int *dk = b->score_k;
   score_kernel<<<1, 32, 0, ctx->stream>>>(d, b->scratch_chain, arm, it, seed, iter, dw, dw + W, dk);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   int K = 0;
   if (e == cudaSuccess) e = cudaMemcpy(&K, dk, sizeof(int), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && logw_out) e = cudaMemcpy(logw_out, dw, sizeof(double) * (K + d.CC), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && prob_out) e = cudaMemcpy(prob_out, dw + W, sizeof(double) * (K + d.CC), cudaMemcpyDeviceToHost);
-  cudaFree(dw);
-  cudaFree(dk);
   if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("score_kernel: ") + cudaGetErrorString(e));
   if (K_out) *K_out = K;
   return TPPMX_OK;
@@ -873,11 +983,8 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
   if (d.npred < 1) return fail(ctx, TPPMX_ERR_ARG, "batch has npred == 0");
   CK(ctx, cudaSetDevice(ctx->device));
   const size_t n1 = (size_t)d.n_chains * d.npred * d.D * d.T, n2 = (size_t)d.n_chains * d.npred * d.T;
-  double *dpi = nullptr, *dy = nullptr;
-  int *dc = nullptr;
-  if (pipred) CK(ctx, cudaMalloc(&dpi, n1 * sizeof(double)));
-  if (ypred) CK(ctx, cudaMalloc(&dy, n1 * sizeof(double)));
-  if (predclass) CK(ctx, cudaMalloc(&dc, n2 * sizeof(int)));
+  double *dpi = pipred ? b->pred_pi : nullptr, *dy = ypred ? b->pred_y : nullptr;
+  int *dc = predclass ? b->pred_c : nullptr;
   CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
   predict_kernel<<<dim3(d.n_chains, d.T), 128, 0, ctx->stream>>>(d, seed, iter, dpi, dy, dc);
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
@@ -885,9 +992,6 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
   if (e == cudaSuccess && pipred) e = cudaMemcpy(pipred, dpi, n1 * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && ypred) e = cudaMemcpy(ypred, dy, n1 * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && predclass) e = cudaMemcpy(predclass, dc, n2 * sizeof(int), cudaMemcpyDeviceToHost);
-  cudaFree(dpi);
-  cudaFree(dy);
-  cudaFree(dc);
   if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("predict_kernel: ") + cudaGetErrorString(e));
   float ms = 0;
   cudaEventElapsedTime(&ms, b->ev0, b->ev1);

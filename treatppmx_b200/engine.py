@@ -27,6 +27,14 @@ class Context:
         if rc != 0:
             raise _lib.TppmxError(rc, self.err())
 
+    def probe_math(self, which: str, x):
+        """Device fp64 log / exp / lgamma of the fast sweep kernel on an array (test hook)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self.check(self.L.tppmx_probe_math(self.h, {"log": 0, "exp": 1, "lgamma": 2}[which],
+                                           x.ctypes.data_as(c_dp), x.size, out.ctypes.data_as(c_dp)))
+        return out
+
     def close(self):
         if self.h:
             self.L.tppmx_destroy(self.h)
