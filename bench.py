@@ -297,6 +297,30 @@ def run_native(args, rank: int, world: int, local_rank: int):
         pred = {"ms": float(np.median(pms)),
                 "new_patient_arm_scores_per_s": nchains * dims.npred * dims.T / (np.median(pms) * 1e-3)}
 
+    # final gather of the posterior summaries (the only cross-GPU step of the path): a few saved
+    # iterations are accumulated on the device, then every rank's per-dataset summaries are
+    # all-gathered (NCCL over NVLink for N > 1); timed with CUDA events on torch's stream
+    gather = None
+    if dims.npred > 0:
+        from treatppmx_b200 import multigpu
+        batch.reset_summaries()
+        for r in range(3):
+            batch.sweep(seed, it, 1)
+            batch.accumulate(seed, it, psm=True, predictive=True)
+            it += 1
+        loc = multigpu.device_summaries_as_torch(batch, [0.0, 40.0, 100.0])
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        allsum = multigpu.gather_summaries(loc, world * len(w["dsets"]))
+        ev1.record()
+        torch.cuda.synchronize()
+        gbytes = sum(v.numel() * v.element_size() for v in allsum.values())
+        gather = {"ms": ev0.elapsed_time(ev1), "bytes_gathered": int(gbytes),
+                  "arrays": {k: list(v.shape) for k, v in allsum.items()},
+                  "backend": "nccl" if world > 1 else "none (single GPU: device copy)"}
+        del allsum, loc
+
     # e2e through the public API with host buffers
     e2e_call(ctx, w, seed, 2)  # warm
     barrier()
@@ -345,6 +369,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
             "mean_clusters_per_arm": Kbar_all,
             "cluster_scores_per_sec": value * (Kbar_all + model.CC),
             "predictive": pred,
+            "summary_gather": gather,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",

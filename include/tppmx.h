@@ -243,6 +243,29 @@ int tppmx_batch_last_timing(const tppmx_batch *b, double *ms, int32_t *launches)
 int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, double *pipred,
                         double *ypred, int32_t *predclass);
 
+/* ---- posterior summaries on the device (what a multi-GPU run gathers) ----------------------
+ * The package returns per-iteration cl_lab / pipred (src/dm_ppmx_ct.cpp:1402-1404, :1396) and
+ * leaves the co-clustering matrix (mcclust::comp.psm, R/treatppmx.R:29) and the treatment
+ * utility sum_k w_k E[pi_k] to user scripts.  For batched chains these are accumulated on the
+ * device per replicate dataset, over all of its chains and all saved iterations:
+ *   tppmx_batch_accumulate   adds the current partition of every chain to its dataset's
+ *                            co-clustering counts (do_psm) and runs the predictive step
+ *                            (RNG keyed by `iter`) adding pipred to the dataset's sums (do_pred)
+ *   tppmx_batch_summaries    means / utilities / chosen arm, copied to host (any pointer NULL):
+ *        psm      [n_datasets][T][ntmax][ntmax]   P(label_a == label_b)
+ *        pi_mean  [n_datasets][npred x D x T col-major]
+ *        utility  [n_datasets][T][npred]           sum_k util_w[k] * pi_mean
+ *        best_arm [n_datasets][npred]              arg max_t utility (0-based)
+ *   tppmx_batch_summaries_device  the same four arrays left on the device (pointers returned),
+ *        for a collective (NCCL) gather without a host round trip
+ *   tppmx_batch_reset_summaries   zero the accumulators */
+int tppmx_batch_accumulate(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t do_psm, int32_t do_pred);
+int tppmx_batch_summaries(tppmx_batch *b, const double *util_w, double *psm, double *pi_mean,
+                          double *utility, int32_t *best_arm);
+int tppmx_batch_summaries_device(tppmx_batch *b, const double *util_w, double **psm, double **pi_mean,
+                                 double **utility, int32_t **best_arm);
+int tppmx_batch_reset_summaries(tppmx_batch *b);
+
 #ifdef __cplusplus
 }
 #endif

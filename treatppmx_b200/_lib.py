@@ -18,6 +18,8 @@ SYMBOLS = [
     "tppmx_score_patient",
     "tppmx_batch_sweep", "tppmx_batch_set_option", "tppmx_batch_get_info",
     "tppmx_batch_last_timing", "tppmx_batch_predict",
+    "tppmx_batch_accumulate", "tppmx_batch_summaries", "tppmx_batch_summaries_device",
+    "tppmx_batch_reset_summaries",
 ]
 
 _lib = None
@@ -59,5 +61,10 @@ def load():
     L.tppmx_batch_get_info.argtypes = [vp, i32, c_ip]
     L.tppmx_batch_last_timing.argtypes = [vp, c_dp, c_ip]
     L.tppmx_batch_predict.argtypes = [vp, u64, i32, c_dp, c_dp, c_ip]
+    L.tppmx_batch_accumulate.argtypes = [vp, u64, i32, i32, i32]
+    L.tppmx_batch_summaries.argtypes = [vp, c_dp, c_dp, c_dp, c_dp, c_ip]
+    L.tppmx_batch_summaries_device.argtypes = [vp, c_dp, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp),
+                                               C.POINTER(c_ip)]
+    L.tppmx_batch_reset_summaries.argtypes = [vp]
     _lib = L
     return L

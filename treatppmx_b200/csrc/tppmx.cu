@@ -14,6 +14,7 @@
 #include "rng.cuh"
 #include "sim.cuh"
 #include "sweep.cuh"
+#include "summary.cuh"
 #include "sweep_fast.cuh"
 
 using namespace tppmx;
@@ -61,6 +62,9 @@ struct tppmx_batch {
   double *init_beta = nullptr;
   double *pred_pi = nullptr, *pred_y = nullptr, *score_w = nullptr;
   int *pred_c = nullptr, *score_k = nullptr;
+  // posterior summaries (summary.cuh); psm_* stay null when the counts would not fit
+  int *psm_cnt = nullptr, *psm_n = nullptr, *pi_n = nullptr, *best_arm = nullptr;
+  double *pi_sum = nullptr, *psm_mean = nullptr, *pi_mean = nullptr, *utility = nullptr, *util_w = nullptr;
   std::vector<int> arm_n;     // [nd][T]
   std::vector<int> chain_ds;  // [nc+1]
   cudaEvent_t ev0, ev1;
@@ -393,6 +397,22 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
       TRY(dev_alloc(b, &b->pred_c, (size_t)n_chains * npred * T));
     }
     if (fast_eligible(b, 32)) TRY(fast_reserve(b));
+    {  // posterior summaries; the co-clustering counts are skipped beyond 2 GiB (large-n config)
+      const size_t npsm = (size_t)n_datasets * T * d.ntmax * d.ntmax;
+      TRY(dev_alloc(b, &b->psm_n, (size_t)n_datasets));
+      TRY(dev_alloc(b, &b->pi_n, (size_t)n_datasets));
+      TRY(dev_alloc(b, &b->util_w, (size_t)TPPMX_MAXD));
+      if (npsm * 12 <= ((size_t)2 << 30)) {
+        TRY(dev_alloc(b, &b->psm_cnt, npsm));
+        TRY(dev_alloc(b, &b->psm_mean, npsm));
+      }
+      if (npred > 0) {
+        TRY(dev_alloc(b, &b->pi_sum, (size_t)n_datasets * npred * D * T));
+        TRY(dev_alloc(b, &b->pi_mean, (size_t)n_datasets * npred * D * T));
+        TRY(dev_alloc(b, &b->utility, (size_t)n_datasets * npred * T));
+        TRY(dev_alloc(b, &b->best_arm, (size_t)n_datasets * npred));
+      }
+    }
     if (pass == 1) {
       CK(ctx, cudaMemcpyAsync(b->ar.dbase, b->ar.hbase, b->up_used, cudaMemcpyHostToDevice, ctx->stream));
       CK(ctx, cudaMemsetAsync(b->ar.dbase + b->up_need, 0, b->st_used, ctx->stream));
@@ -997,5 +1017,93 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
   cudaEventElapsedTime(&ms, b->ev0, b->ev1);
   b->last_ms = ms;
   b->last_launches = 1;
+  return TPPMX_OK;
+}
+
+// ---- posterior summaries ------------------------------------------------------------------------
+extern "C" int tppmx_batch_reset_summaries(tppmx_batch *b) {
+  if (!b) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t npsm = (size_t)d.n_datasets * d.T * d.ntmax * d.ntmax;
+  CK(ctx, cudaMemsetAsync(b->psm_n, 0, sizeof(int) * d.n_datasets, ctx->stream));
+  CK(ctx, cudaMemsetAsync(b->pi_n, 0, sizeof(int) * d.n_datasets, ctx->stream));
+  if (b->psm_cnt) CK(ctx, cudaMemsetAsync(b->psm_cnt, 0, sizeof(int) * npsm, ctx->stream));
+  if (b->pi_sum) CK(ctx, cudaMemsetAsync(b->pi_sum, 0, sizeof(double) * d.n_datasets * d.npred * d.D * d.T, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_accumulate(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t do_psm, int32_t do_pred) {
+  if (!b) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (do_psm && !b->psm_cnt) return fail(ctx, TPPMX_ERR_CAPACITY, "co-clustering counts were not reserved (ntmax too large)");
+  if (do_pred && d.npred < 1) return fail(ctx, TPPMX_ERR_ARG, "batch has npred == 0");
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
+  int launches = 0;
+  if (do_psm) {
+    psm_accumulate_kernel<<<dim3(d.n_chains, d.T), 256, 0, ctx->stream>>>(d, b->psm_cnt);
+    launches++;
+  }
+  if (do_pred) {
+    predict_kernel<<<dim3(d.n_chains, d.T), 128, 0, ctx->stream>>>(d, seed, iter, b->pred_pi, nullptr, nullptr);
+    pi_accumulate_kernel<<<d.n_chains, 256, 0, ctx->stream>>>(d, b->pred_pi, b->pi_sum);
+    launches += 2;
+  }
+  if (do_psm || do_pred) {
+    count_saves_kernel<<<(d.n_chains + 255) / 256, 256, 0, ctx->stream>>>(d, b->psm_n, b->pi_n, do_psm, do_pred);
+    launches++;
+  }
+  CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  b->last_ms = ms;
+  b->last_launches = launches;
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_summaries_device(tppmx_batch *b, const double *util_w, double **psm, double **pi_mean,
+                                            double **utility, int32_t **best_arm) {
+  if (!b) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  CK(ctx, cudaSetDevice(ctx->device));
+  double w[TPPMX_MAXD] = {0};
+  for (int k = 0; k < d.D; k++) w[k] = util_w ? util_w[k] : 0.0;
+  CK(ctx, cudaMemcpyAsync(b->util_w, w, sizeof(w), cudaMemcpyHostToDevice, ctx->stream));
+  summarise_kernel<<<d.n_datasets, 256, 0, ctx->stream>>>(d, b->psm_cnt, b->psm_n, b->pi_sum, b->pi_n, b->util_w,
+                                                         b->psm_cnt ? b->psm_mean : nullptr,
+                                                         d.npred > 0 ? b->pi_mean : nullptr, b->utility, b->best_arm);
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (psm) *psm = b->psm_cnt ? b->psm_mean : nullptr;
+  if (pi_mean) *pi_mean = b->pi_mean;
+  if (utility) *utility = b->utility;
+  if (best_arm) *best_arm = b->best_arm;
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_summaries(tppmx_batch *b, const double *util_w, double *psm, double *pi_mean,
+                                     double *utility, int32_t *best_arm) {
+  if (!b) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  double *dp = nullptr, *dm = nullptr, *du = nullptr;
+  int32_t *db = nullptr;
+  RC(tppmx_batch_summaries_device(b, util_w, &dp, &dm, &du, &db));
+  const size_t npsm = (size_t)d.n_datasets * d.T * d.ntmax * d.ntmax, n1 = (size_t)d.n_datasets * d.npred * d.D * d.T;
+  if (psm) {
+    if (!dp) return fail(ctx, TPPMX_ERR_CAPACITY, "co-clustering counts were not reserved (ntmax too large)");
+    CK(ctx, cudaMemcpy(psm, dp, sizeof(double) * npsm, cudaMemcpyDeviceToHost));
+  }
+  if ((pi_mean || utility || best_arm) && d.npred < 1) return fail(ctx, TPPMX_ERR_ARG, "batch has npred == 0");
+  if (pi_mean) CK(ctx, cudaMemcpy(pi_mean, dm, sizeof(double) * n1, cudaMemcpyDeviceToHost));
+  if (utility) CK(ctx, cudaMemcpy(utility, du, sizeof(double) * d.n_datasets * d.npred * d.T, cudaMemcpyDeviceToHost));
+  if (best_arm) CK(ctx, cudaMemcpy(best_arm, db, sizeof(int32_t) * d.n_datasets * d.npred, cudaMemcpyDeviceToHost));
   return TPPMX_OK;
 }

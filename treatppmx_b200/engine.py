@@ -8,7 +8,19 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._abi import (Dataset, Dims, HostDataset, HostShared, HostState, Model, c_dp, c_ip)
+from ._abi import (MAXD, Dataset, Dims, HostDataset, HostShared, HostState, Model, c_dp, c_ip)
+
+
+class DeviceArray:
+    """A library-owned device buffer exposed through __cuda_array_interface__ (zero-copy view for
+    torch.as_tensor(..., device="cuda") so NCCL can gather it without a host round trip)."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.ptr, self.shape, self.typestr, self._owner = ptr, tuple(int(x) for x in shape), typestr, owner
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.typestr, "data": (self.ptr, False), "version": 2}
 
 
 class Context:
@@ -142,6 +154,47 @@ class Batch:
         ms, n = C.c_double(0), C.c_int32(0)
         self.ctx.check(self.ctx.L.tppmx_batch_last_timing(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    # ---- posterior summaries accumulated on the device (include/tppmx.h) -------------------
+    def reset_summaries(self):
+        self.ctx.check(self.ctx.L.tppmx_batch_reset_summaries(self.h))
+
+    def accumulate(self, seed: int, iter_: int, psm: bool = True, predictive: bool = True):
+        self.ctx.check(self.ctx.L.tppmx_batch_accumulate(self.h, seed, iter_, int(psm), int(predictive)))
+
+    def summaries(self, util_w=None, want=("psm", "pi_mean", "utility", "best_arm")):
+        """Host copies: psm [nd, T, ntmax, ntmax], pi_mean [nd, npred, D, T], utility [nd, T, npred],
+        best_arm [nd, npred]."""
+        d, nd = self.dims, len(self.datasets)
+        uw = np.zeros(MAXD) if util_w is None else np.concatenate([np.asarray(util_w, float), np.zeros(MAXD)])[:MAXD]
+        uw = np.ascontiguousarray(uw)
+        psm = np.zeros((nd, d.T, d.ntmax, d.ntmax)) if "psm" in want else None
+        pim = np.zeros((nd, d.T, d.D, d.npred)) if "pi_mean" in want and d.npred > 0 else None
+        ut = np.zeros((nd, d.T, d.npred)) if "utility" in want and d.npred > 0 else None
+        ba = np.zeros((nd, d.npred), dtype=np.int32) if "best_arm" in want and d.npred > 0 else None
+        f = lambda a, t: a.ctypes.data_as(t) if a is not None else t()
+        self.ctx.check(self.ctx.L.tppmx_batch_summaries(self.h, uw.ctypes.data_as(c_dp), f(psm, c_dp), f(pim, c_dp),
+                                                        f(ut, c_dp), f(ba, c_ip)))
+        return dict(psm=psm, pi_mean=None if pim is None else pim.transpose(0, 3, 2, 1), utility=ut, best_arm=ba)
+
+    def summaries_device(self, util_w=None):
+        """The same arrays left on the device as DeviceArray views (C-order shapes as in summaries(),
+        pi_mean as [nd, T, D, npred])."""
+        d, nd = self.dims, len(self.datasets)
+        uw = np.zeros(MAXD) if util_w is None else np.concatenate([np.asarray(util_w, float), np.zeros(MAXD)])[:MAXD]
+        uw = np.ascontiguousarray(uw)
+        p1, p2, p3, p4 = c_dp(), c_dp(), c_dp(), c_ip()
+        self.ctx.check(self.ctx.L.tppmx_batch_summaries_device(self.h, uw.ctypes.data_as(c_dp), C.byref(p1), C.byref(p2),
+                                                               C.byref(p3), C.byref(p4)))
+        addr = lambda p: C.cast(p, C.c_void_p).value
+        out = {}
+        if addr(p1):
+            out["psm"] = DeviceArray(addr(p1), (nd, d.T, d.ntmax, d.ntmax), "<f8", self)
+        if d.npred > 0:
+            out["pi_mean"] = DeviceArray(addr(p2), (nd, d.T, d.D, d.npred), "<f8", self)
+            out["utility"] = DeviceArray(addr(p3), (nd, d.T, d.npred), "<f8", self)
+            out["best_arm"] = DeviceArray(addr(p4), (nd, d.npred), "<i4", self)
+        return out
 
     def predict(self, seed: int, iter_: int, want=("pipred", "ypred", "predclass")):
         d, nc = self.dims, self.n_chains
