@@ -176,7 +176,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args, w):
@@ -389,14 +389,32 @@ def run_native(args, rank: int, world: int, local_rank: int):
             r1, desc1, dt1, _ = cpu_oracle_rate(w, 1, 4.0)
             out["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": ncores, "kind": "port",
                                    "sample": desc + f" ({dt:.1f} s)", "single_core_value": r1}
-        print(json.dumps(out), flush=True)
+        emit(out)
     batch.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly one JSON line: anything native libraries print to fd 1 (e.g. the NCCL
+    version banner) is sent to stderr instead."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

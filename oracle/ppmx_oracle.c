@@ -151,32 +151,9 @@ double oracle_rng_gamma(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t s
 /* ---------------------------------------------------------------------------------------
  * layout accessors (Armadillo column-major, as declared in include/tppmx.h)
  * ------------------------------------------------------------------------------------- */
-typedef struct o_ctx {
-  const oracle_problem *pb;
-  tppmx_state *s;
-  int nobs, T, D, Q, P, ncat, maxC, npred, G, ntmax, CC;
-  int num_treat[TPPMX_MAXT];
-  double *dirweights; /* [maxC] */
-  double *njctmp;     /* [maxC] */
-  double *weight, *pweight, *gtilN, *gtilY, *lgtilN, *lgtilY; /* [ntmax+CC] per call arm */
-  o_rng rng;
-} o_ctx;
+#include "oracle_internal.h"
 
-#define LAB(t, it) (c->s->labels[(t) + c->T * (it)])
-#define NJ(t, j) (c->s->nj[(t) + c->T * (j)])
-#define SUMX(t, idx) (c->s->sumx[(t) + c->T * (idx)])
-#define SUMX2(t, idx) (c->s->sumx2[(t) + c->T * (idx)])
-#define NJC(t, idx) (c->s->njc[(t) + c->T * (idx)])
-#define ETAS(k, j, t) (c->s->eta_star[(k) + c->D * ((j) + c->ntmax * (t))])
-#define ETAE(k, m, t) (c->s->eta_empty[(k) + c->D * ((m) + c->CC * (t))])
-#define JJm(i, k) (c->s->JJ[(i) + c->nobs * (k)])
-#define LG(i, k) (c->s->loggamma[(i) + c->nobs * (k)])
-#define Ym(i, k) (c->pb->data.y[(i) + c->nobs * (k)])
-#define Zm(i, q) (c->pb->data.z[(i) + c->nobs * (q)])
-#define XCON(idx) (c->pb->data.xcon[(idx)])
-#define XCAT(idx) (c->pb->data.xcat[(idx)])
-
-static int o_ctx_open(o_ctx *c, const oracle_problem *pb, tppmx_state *s, uint64_t seed,
+int o_ctx_open(o_ctx *c, const oracle_problem *pb, tppmx_state *s, uint64_t seed,
                       uint32_t chain_id) {
   memset(c, 0, sizeof(*c));
   c->pb = pb;
@@ -198,7 +175,7 @@ static int o_ctx_open(o_ctx *c, const oracle_problem *pb, tppmx_state *s, uint64
   c->rng.seed = seed; c->rng.chain = chain_id;
   return 0;
 }
-static void o_ctx_close(o_ctx *c) {
+void o_ctx_close(o_ctx *c) {
   free(c->dirweights); free(c->njctmp); free(c->weight);
 }
 
@@ -215,7 +192,7 @@ static double o_calculate_gamma(const o_ctx *c, const double *eta_col, const dou
 }
 
 /* one continuous-covariate similarity term, switch structure of :472-516 */
-static double o_gcon(const o_ctx *c, double sx, double sx2, int n) {
+double o_gcon(const o_ctx *c, double sx, double sx2, int n) {
   const tppmx_model *m = &c->pb->model;
   double m0 = m->similparam[0], s20 = m->similparam[1], v = m->similparam[2];
   double k0 = m->similparam[3], nu0 = m->similparam[4];
@@ -520,7 +497,7 @@ static void o_realloc_patient(o_ctx *c, int tt, int it, int i, int l, int score_
 }
 
 /* the per-arm part of one iteration: :349-860 */
-static void o_sweep_iter(o_ctx *c, int l) {
+void o_sweep_iter(o_ctx *c, int l) {
   const tppmx_model *m = &c->pb->model;
   for (int tt = 0; tt < c->T; tt++) {
     if (m->reuse == 1) { /* :351-360 */
@@ -736,7 +713,7 @@ int oracle_sweep(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32
 /* ---------------------------------------------------------------------------------------
  * posterior predictive, src/dm_ppmx_ct.cpp:1081-1384
  * ------------------------------------------------------------------------------------- */
-static void o_chol_lower(const double *A, int n, double *L) { /* A col-major sym pos-def */
+void o_chol_lower(const double *A, int n, double *L) { /* A col-major sym pos-def */
   memset(L, 0, sizeof(double) * n * n);
   for (int i = 0; i < n; i++)
     for (int j = 0; j <= i; j++) {

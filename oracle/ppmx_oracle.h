@@ -68,6 +68,18 @@ int oracle_predict(const oracle_problem *pb, const tppmx_state *s, uint64_t seed
                    uint32_t chain_id, int32_t iter, double *pipred, double *ypred,
                    int32_t *predclass);
 
+/* ppmx_chain.c: everything of iteration l after the sweep (src/dm_ppmx_ct.cpp:866-1055), and
+ * n_iter full iterations (sweep + updates).  eta_acc: T x ntmax col-major, beta_acc: Q x D
+ * col-major acceptance counters (may be NULL). */
+int oracle_update_iter(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,
+                       int32_t l, int32_t *eta_acc, int32_t *beta_acc);
+int oracle_iterate(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,
+                   int32_t iter0, int32_t n_iter, int32_t *eta_acc, int32_t *beta_acc);
+double oracle_gammainc(double a, double x);
+double oracle_gammaincinv(double a, double p);
+double oracle_dmvnrm_log(const double *x, const double *mean, const double *sigma, int n);
+void oracle_wishart(uint64_t seed, uint32_t chain, int32_t l, const double *S, double df, int n, double *W);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,16 @@ def lib():
                                            c_dp, c_dp, c_ip]
         L.oracle_sweep.argtypes = [P, S, u64, u32, C.c_int32, C.c_int32]
         L.oracle_predict.argtypes = [P, S, u64, u32, C.c_int32, c_dp, c_dp, c_ip]
+        i32p = c_ip
+        L.oracle_update_iter.argtypes = [P, S, u64, u32, C.c_int32, i32p, i32p]
+        L.oracle_iterate.argtypes = [P, S, u64, u32, C.c_int32, C.c_int32, i32p, i32p]
+        L.oracle_gammainc.restype = d
+        L.oracle_gammainc.argtypes = [d, d]
+        L.oracle_gammaincinv.restype = d
+        L.oracle_gammaincinv.argtypes = [d, d]
+        L.oracle_dmvnrm_log.restype = d
+        L.oracle_dmvnrm_log.argtypes = [c_dp, c_dp, c_dp, i]
+        L.oracle_wishart.argtypes = [u64, u32, C.c_int32, c_dp, d, i, c_dp]
         _lib = L
     return _lib
 
@@ -103,6 +113,27 @@ class Problem:
     def sweep(self, s: HostState, seed, chain_id, iter0, n_sweeps):
         cs = s.cstruct()
         rc = lib().oracle_sweep(C.byref(self.c), C.byref(cs), seed, chain_id, iter0, n_sweeps)
+        assert rc == 0, rc
+
+    def new_acc(self):
+        d = self.dims
+        return (np.zeros((d.T, d.ntmax), dtype=np.int32, order="F"),
+                np.zeros((max(d.Q, 1), d.D), dtype=np.int32, order="F"))
+
+    def update_iter(self, s: HostState, seed, chain_id, iter_, acc=None):
+        """Everything of iteration `iter_` after the sweep (src/dm_ppmx_ct.cpp:866-1055)."""
+        cs = s.cstruct()
+        ea, ba = (acc if acc is not None else (None, None))
+        f = lambda a: a.ctypes.data_as(c_ip) if a is not None else c_ip()
+        rc = lib().oracle_update_iter(C.byref(self.c), C.byref(cs), seed, chain_id, iter_, f(ea), f(ba))
+        assert rc == 0, rc
+
+    def iterate(self, s: HostState, seed, chain_id, iter0, n_iter, acc=None):
+        """n_iter full iterations: sweep + updates."""
+        cs = s.cstruct()
+        ea, ba = (acc if acc is not None else (None, None))
+        f = lambda a: a.ctypes.data_as(c_ip) if a is not None else c_ip()
+        rc = lib().oracle_iterate(C.byref(self.c), C.byref(cs), seed, chain_id, iter0, n_iter, f(ea), f(ba))
         assert rc == 0, rc
 
     def predict(self, s: HostState, seed, chain_id, iter_):
