@@ -243,6 +243,22 @@ int tppmx_batch_last_timing(const tppmx_batch *b, double *ms, int32_t *launches)
 int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, double *pipred,
                         double *ypred, int32_t *predclass);
 
+/* ---- the rest of an MCMC iteration and whole runs on the device ------------
+ * tppmx_batch_update: everything of iteration `iter` that follows the sweep, for every chain:
+ *   eta* Metropolis step per cluster (src/utils_ct.cpp:579-702), (Theta,Sigma) hierarchy
+ *   (src/dm_ppmx_ct.cpp:880-902), (sigma,kappa) grid draw (:907-1007; needs ncat == 0 like the
+ *   reference), beta Metropolis + horseshoe (src/utils_ct.cpp:710-800, 876-915),
+ *   JJ / ss gamma draws (:1042-1055).
+ * tppmx_batch_run: iterations iter0 .. iter0+n_iter-1 = sweep + update, and on the reference's
+ *   saved iterations ((l > burn-1) && (l+1) % thin == 0, :1060) tppmx_batch_accumulate with the
+ *   given flags.  Nothing returns to the host in between.
+ * tppmx_batch_get_acceptance: acceptance counters of one chain in the reference's layouts
+ *   (eta_flag T x ntmax, beta_flag Q x D, both col-major; either may be NULL). */
+int tppmx_batch_update(tppmx_batch *b, uint64_t seed, int32_t iter);
+int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_iter, int32_t burn,
+                    int32_t thin, int32_t do_psm, int32_t do_pred);
+int tppmx_batch_get_acceptance(tppmx_batch *b, int32_t chain, int32_t *eta_acc, int32_t *beta_acc);
+
 /* ---- posterior summaries on the device (what a multi-GPU run gathers) ----------------------
  * The package returns per-iteration cl_lab / pipred (src/dm_ppmx_ct.cpp:1402-1404, :1396) and
  * leaves the co-clustering matrix (mcclust::comp.psm, R/treatppmx.R:29) and the treatment

@@ -1,0 +1,121 @@
+"""The remaining per-iteration updates on the device (csrc/update.cuh) and whole
+runs (sweep + updates) against the CPU oracle (oracle/ppmx_chain.c) under shared Philox streams.
+
+Integer state (labels, counts, K, grid index, acceptance counters) must be identical; continuous
+state agrees to 1e-9 relative (device and libm transcendentals differ in the last ulps; nothing
+amplifies them unless a Metropolis / allocation decision flips, which has probability ~1e-13 per
+decision)."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from cases import build_case
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from treatppmx_b200.engine import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _compare(g, o, dims, what):
+    assert (g.nclu == o.nclu).all() and (g.labels == o.labels).all() and (g.idxs == o.idxs).all(), what
+    for t in range(dims.T):
+        K = int(o.nclu[t])
+        assert (g.nj[t, :K] == o.nj[t, :K]).all(), what
+        np.testing.assert_allclose(g.eta_star[:, :K, t], o.eta_star[:, :K, t], rtol=RTOL, atol=1e-12, err_msg=what)
+    for f in ("loggamma", "JJ", "ss", "beta", "sigma", "kappa", "Theta", "Sigma", "lambda_", "tau", "sigma_beta"):
+        np.testing.assert_allclose(getattr(g, f), getattr(o, f), rtol=RTOL, atol=1e-12, err_msg=f"{what}: {f}")
+
+
+CASES_UPD = ["default_ngg", "dp_T3", "Q3_D3", "nnig", "calib2", "categorical", "ppm_only", "noreuse"]
+
+
+@pytest.mark.parametrize("name", CASES_UPD)
+def test_update_step_matches_oracle(ctx, name):
+    from treatppmx_b200.engine import Batch
+    model, dims, shared, dsets, labels, nclu, betas = build_case(name, n_datasets=2)
+    nchains = 3
+    cds = [c % 2 for c in range(nchains)]
+    b = Batch(ctx, model, dims, shared, dsets, chain_dataset=cds)
+    b.init(19, labels, nclu, betas[0])
+    pbs = [ob.Problem(model, dims, shared, d) for d in dsets]
+    sts = [pbs[cds[c]].init_state(19, c, labels, nclu, betas[0]) for c in range(nchains)]
+    accs = [pbs[cds[c]].new_acc() for c in range(nchains)]
+    for l in range(6):
+        b.sweep(19, l, 1)
+        b.update(19, l)
+        for c in range(nchains):
+            pbs[cds[c]].sweep(sts[c], 19, c, l, 1)
+            pbs[cds[c]].update_iter(sts[c], 19, c, l, accs[c])
+            _compare(b.get_state(c), sts[c], dims, f"{name} chain {c} iter {l}")
+    for c in range(nchains):
+        ea, ba = b.get_acceptance(c)
+        assert (ea == accs[c][0]).all() and (ba[: max(dims.Q, 1)] == accs[c][1]).all()
+
+
+@pytest.mark.parametrize("name", ["default_ngg", "dp_T3"])
+def test_run_lockstep_with_oracle(ctx, name):
+    from treatppmx_b200.engine import Batch
+    model, dims, shared, dsets, labels, nclu, betas = build_case(name)
+    nchains, niter = 4, 40
+    b = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0] * nchains)
+    b.init(23, labels, nclu, betas[0])
+    b.run(23, 0, niter)
+    pb = ob.Problem(model, dims, shared, dsets[0])
+    for c in range(nchains):
+        st = pb.init_state(23, c, labels, nclu, betas[0])
+        pb.iterate(st, 23, c, 0, niter)
+        _compare(b.get_state(c), st, dims, f"{name} chain {c} after {niter} iterations")
+
+
+def test_run_accumulates_on_saved_iterations(ctx):
+    from treatppmx_b200.engine import Batch
+    model, dims, shared, dsets, labels, nclu, betas = build_case("default_ngg", n_datasets=2)
+    cds = [0, 0, 1, 1]
+    b = Batch(ctx, model, dims, shared, dsets, chain_dataset=cds)
+    b.init(2, labels, nclu, betas[0])
+    b.reset_summaries()
+    b.run(2, 0, 30, burn=10, thin=4, psm=True, predictive=True)   # saved: l in {11,15,19,23,27}
+    out = b.summaries([0.0, 40.0, 100.0])
+    n_a = np.bincount(dsets[0].treat, minlength=dims.T)
+    for ds in range(2):
+        for t in range(dims.T):
+            d = np.diag(out["psm"][ds, t])[: n_a[t]]
+            assert np.allclose(d, 1.0)
+            assert np.allclose(out["psm"][ds, t] * 10, np.round(out["psm"][ds, t] * 10))  # 5 saves x 2 chains
+    np.testing.assert_allclose(out["pi_mean"].sum(axis=2), 1.0, atol=1e-12)
+
+
+def test_posterior_agrees_with_oracle_chains(ctx):
+    """L3: different seeds, same posterior — the number of clusters per arm from 96 device chains
+    against 6 oracle chains, within Monte-Carlo error."""
+    from treatppmx_b200.engine import Batch
+    model, dims, shared, dsets, labels, nclu, betas = build_case("default_ngg")
+    burn, keep = 150, 150
+    b = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0] * 96)
+    b.init(1001, labels, nclu, betas[0])
+    b.run(1001, 0, burn)
+    Kdev = []
+    for s in range(0, keep, 5):
+        b.run(1001, burn + s, 5)
+        Kdev.append(b.get_partitions()[1].astype(float))
+    Kdev = np.stack(Kdev)                     # [saves, chains, T]
+    pb = ob.Problem(model, dims, shared, dsets[0])
+    Kor = []
+    for c in range(6):
+        st = pb.init_state(77, c, labels, nclu, betas[0])
+        pb.iterate(st, 77, c, 0, burn)
+        for s in range(0, keep, 5):
+            pb.iterate(st, 77, c, burn + s, 5)
+            Kor.append(st.nclu.astype(float).copy())
+    Kor = np.stack(Kor).reshape(6, -1, dims.T)
+    m_dev, m_or = Kdev.mean(axis=(0, 1)), Kor.mean(axis=(0, 1))
+    # between-chain standard error of the oracle mean (chains are independent)
+    se = Kor.mean(axis=1).std(axis=0, ddof=1) / np.sqrt(6) + Kdev.mean(axis=0).std(axis=0, ddof=1) / np.sqrt(96)
+    assert (np.abs(m_dev - m_or) < 4 * se + 0.15).all(), (m_dev, m_or, se)

@@ -19,7 +19,7 @@ SYMBOLS = [
     "tppmx_batch_sweep", "tppmx_batch_set_option", "tppmx_batch_get_info",
     "tppmx_batch_last_timing", "tppmx_batch_predict",
     "tppmx_batch_accumulate", "tppmx_batch_summaries", "tppmx_batch_summaries_device",
-    "tppmx_batch_reset_summaries",
+    "tppmx_batch_reset_summaries", "tppmx_batch_update", "tppmx_batch_run", "tppmx_batch_get_acceptance",
 ]
 
 _lib = None
@@ -66,5 +66,8 @@ def load():
     L.tppmx_batch_summaries_device.argtypes = [vp, c_dp, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp),
                                                C.POINTER(c_ip)]
     L.tppmx_batch_reset_summaries.argtypes = [vp]
+    L.tppmx_batch_update.argtypes = [vp, u64, i32]
+    L.tppmx_batch_run.argtypes = [vp, u64, i32, i32, i32, i32, i32, i32]
+    L.tppmx_batch_get_acceptance.argtypes = [vp, i32, c_ip, c_ip]
     _lib = L
     return L

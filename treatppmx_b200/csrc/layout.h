@@ -48,6 +48,8 @@ struct DevBatch {
   int *labels, *nj, *nclu, *njc, *idxs, *status;
   double *sumx, *sumx2, *eta, *etae, *JJ, *ss, *lg, *beta, *sigma, *kappa, *Theta, *Sigma;
   double *lambda, *tau, *sigma_beta;
+  int *eta_flag;   // [nc][T][kcap]  eta* acceptances per cluster slot (reference eta_flag, :145)
+  int *beta_flag;  // [nc][Q*D]      beta acceptances, index q + Q*k (reference beta_flag(q,k), :150)
   // per-chain scratch
   double *zb;    // [nc][nobs][D]   sum_q beta[k+qD] z_iq
   double *ljj;   // [nc][nobs][D]   log JJ_ik

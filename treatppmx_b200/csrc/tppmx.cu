@@ -16,6 +16,7 @@
 #include "sweep.cuh"
 #include "summary.cuh"
 #include "sweep_fast.cuh"
+#include "update.cuh"
 
 using namespace tppmx;
 
@@ -74,6 +75,7 @@ struct tppmx_batch {
   // fast sweep kernel (sweep_fast.cuh)
   int opt_impl = 0, opt_lpu = 0, opt_ks = 0;
   FastArgs fa;
+  UpdArgs ua;
   bool fast_ready = false;
   int last_impl = 0, last_handovers = 0;
 };
@@ -385,6 +387,12 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
     TRY(dev_alloc(b, &d.ljj, ns * st_pat(d)));
     TRY(dev_alloc(b, &d.cpat, ns * nobs));
     TRY(dev_alloc(b, &d.wbuf, ns * st_wbuf(d)));
+    TRY(dev_alloc(b, &d.eta_flag, ns * T * d.kcap));
+    TRY(dev_alloc(b, &d.beta_flag, ns * Q * D));
+    TRY(dev_alloc(b, &b->ua.eta2, (size_t)n_chains * T * 2 * D * d.kcap));
+    TRY(dev_alloc(b, &b->ua.pat2, (size_t)n_chains * 2 * T * d.ntmax));
+    TRY(dev_alloc(b, &b->ua.os, (size_t)n_chains * T * d.G));
+    TRY(dev_alloc(b, &b->ua.acc, (size_t)n_chains * T * d.kcap));
     // scratch of the call paths, reserved here so that no call allocates
     TRY(dev_alloc(b, &b->init_lab, (size_t)n_datasets * T * d.ntmax));
     TRY(dev_alloc(b, &b->init_ncl, (size_t)n_datasets * T));
@@ -896,51 +904,138 @@ static cudaError_t fast_launch(tppmx_batch *b, size_t smem, uint64_t seed, int i
   return fast_launch2<LPU, 4>(b, smem, seed, iter0, n_sweeps);
 }
 
-extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps) {
-  if (!b || n_sweeps < 0) return TPPMX_ERR_ARG;
+// Launches the sweep kernels for iterations iter0..iter0+n_sweeps-1 on the context's stream.
+// sync_handover: read the hand-over count back and launch the generic finisher only if needed
+// (one host sync); otherwise the finisher is always launched (it exits at once for chains with
+// nothing to resume), so a whole run needs no host round trip.
+static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps, bool sync_handover, int *launches) {
   tppmx_ctx *ctx = b->ctx;
-  CK(ctx, cudaSetDevice(ctx->device));
   const int lpu = b->opt_lpu ? b->opt_lpu : 16;
   size_t smem = 0;
-  bool use_fast = b->opt_impl != 1 && fast_eligible(b, lpu);
+  bool use_fast = b->opt_impl != 1 && fast_eligible(b, lpu) && b->fa.lik;
   if (use_fast) {
     RC(fast_prepare(b, lpu, &smem));
     if (smem > 200 * 1024) use_fast = false;  // would not fit an SM: generic kernel
   }
   if (b->opt_impl == 2 && !use_fast) return fail(ctx, TPPMX_ERR_ARG, "model/shape not eligible for the fast sweep kernel");
-  b->last_handovers = 0;
-  int launches = 0;
-  CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
   if (use_fast) {
     CK(ctx, cudaMemsetAsync(b->fa.bail_count, 0, sizeof(int), ctx->stream));
     cudaError_t e = lpu == 8    ? fast_launch<8>(b, smem, seed, iter0, n_sweeps)
                     : lpu == 32 ? fast_launch<32>(b, smem, seed, iter0, n_sweeps)
                                 : fast_launch<16>(b, smem, seed, iter0, n_sweeps);
     if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("sweep_fast_kernel: ") + cudaGetErrorString(e));
-    launches++;
-    int nb = 0;
-    CK(ctx, cudaMemcpyAsync(&nb, b->fa.bail_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    b->last_handovers = nb;
+    (*launches)++;
+    int nb = 1;
+    if (sync_handover) {
+      CK(ctx, cudaMemcpyAsync(&nb, b->fa.bail_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      b->last_handovers = nb;
+    }
     if (nb > 0) {  // finish the units that outgrew the staged capacity, from their exact position
       sweep_kernel<<<b->d.n_chains, 32 * b->d.T, 0, ctx->stream>>>(b->d, seed, iter0, n_sweeps, b->fa.resume_l,
                                                                  b->fa.resume_it);
-      launches++;
+      (*launches)++;
     }
     b->last_impl = 2;
   } else {
     sweep_kernel<<<b->d.n_chains, 32 * b->d.T, 0, ctx->stream>>>(b->d, seed, iter0, n_sweeps, nullptr, nullptr);
-    launches++;
+    (*launches)++;
     b->last_impl = 1;
   }
-  CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   CK(ctx, cudaGetLastError());
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps) {
+  if (!b || n_sweeps < 0) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  CK(ctx, cudaSetDevice(ctx->device));
+  b->last_handovers = 0;
+  int launches = 0;
+  CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
+  RC(sweep_launch(b, seed, iter0, n_sweeps, true, &launches));
+  CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;
   CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   b->last_ms = ms;
   b->last_launches = launches;
   return check_status(b);
+}
+
+static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launches) {
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (d.model.cohesion == 2 && d.ncat > 0)
+    return fail(ctx, TPPMX_ERR_ARG, "the (sigma,kappa) update needs ncat == 0 (as the reference, dm_ppmx_ct.cpp:942)");
+  const int nth = 256;
+  const size_t smem = sizeof(double) * (2 * nth + (size_t)d.T * d.D * d.D + 16) + sizeof(int) * d.T;
+  update_kernel<<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
+  (*launches)++;
+  CK(ctx, cudaGetLastError());
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_batch_update(tppmx_batch *b, uint64_t seed, int32_t iter) {
+  if (!b) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  CK(ctx, cudaSetDevice(ctx->device));
+  int launches = 0;
+  CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
+  RC(update_launch(b, seed, iter, &launches));
+  CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  b->last_ms = ms;
+  b->last_launches = launches;
+  return TPPMX_OK;
+}
+
+static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do_psm, int do_pred, int *launches);
+
+extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_iter, int32_t burn,
+                               int32_t thin, int32_t do_psm, int32_t do_pred) {
+  if (!b || n_iter < 0 || thin < 1) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (do_psm && !b->psm_cnt) return fail(ctx, TPPMX_ERR_CAPACITY, "co-clustering counts were not reserved (ntmax too large)");
+  if (do_pred && d.npred < 1) return fail(ctx, TPPMX_ERR_ARG, "batch has npred == 0");
+  CK(ctx, cudaSetDevice(ctx->device));
+  b->last_handovers = 0;
+  int launches = 0;
+  CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
+  for (int l = iter0; l < iter0 + n_iter; l++) {
+    RC(sweep_launch(b, seed, l, 1, false, &launches));
+    RC(update_launch(b, seed, l, &launches));
+    if ((do_psm || do_pred) && (l > burn - 1) && ((l + 1) % thin == 0))  // :1060
+      RC(accumulate_launch(b, seed, l, do_psm, do_pred, &launches));
+  }
+  CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  b->last_ms = ms;
+  b->last_launches = launches;
+  return check_status(b);
+}
+
+extern "C" int tppmx_batch_get_acceptance(tppmx_batch *b, int32_t chain, int32_t *eta_acc, int32_t *beta_acc) {
+  if (!b) return TPPMX_ERR_ARG;
+  const DevBatch &d = b->d;
+  if (chain < 0 || chain >= d.n_chains) return fail(b->ctx, TPPMX_ERR_ARG, "chain out of range");
+  CK(b->ctx, cudaSetDevice(b->ctx->device));
+  CK(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+  const int T = d.T, ks = d.kcap, nt = d.ntmax;
+  if (eta_acc) {
+    std::vector<int> h((size_t)T * ks);
+    RC(d2h(b, h, d.eta_flag + (size_t)chain * T * ks));
+    for (int t = 0; t < T; t++)
+      for (int j = 0; j < nt; j++) eta_acc[t + (size_t)T * j] = j < ks ? h[(size_t)t * ks + j] : 0;
+  }
+  if (beta_acc && d.Q > 0)
+    CK(b->ctx, cudaMemcpy(beta_acc, d.beta_flag + (size_t)chain * d.Q * d.D, sizeof(int) * d.Q * d.D, cudaMemcpyDeviceToHost));
+  return TPPMX_OK;
 }
 
 extern "C" int tppmx_batch_last_timing(const tppmx_batch *b, double *ms, int32_t *launches) {
@@ -1035,6 +1130,26 @@ extern "C" int tppmx_batch_reset_summaries(tppmx_batch *b) {
   return TPPMX_OK;
 }
 
+static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do_psm, int do_pred, int *launches) {
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (do_psm) {
+    psm_accumulate_kernel<<<dim3(d.n_chains, d.T), 256, 0, ctx->stream>>>(d, b->psm_cnt);
+    (*launches)++;
+  }
+  if (do_pred) {
+    predict_kernel<<<dim3(d.n_chains, d.T), 128, 0, ctx->stream>>>(d, seed, iter, b->pred_pi, nullptr, nullptr);
+    pi_accumulate_kernel<<<d.n_chains, 256, 0, ctx->stream>>>(d, b->pred_pi, b->pi_sum);
+    (*launches) += 2;
+  }
+  if (do_psm || do_pred) {
+    count_saves_kernel<<<(d.n_chains + 255) / 256, 256, 0, ctx->stream>>>(d, b->psm_n, b->pi_n, do_psm, do_pred);
+    (*launches)++;
+  }
+  CK(ctx, cudaGetLastError());
+  return TPPMX_OK;
+}
+
 extern "C" int tppmx_batch_accumulate(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t do_psm, int32_t do_pred) {
   if (!b) return TPPMX_ERR_ARG;
   tppmx_ctx *ctx = b->ctx;
@@ -1044,21 +1159,8 @@ extern "C" int tppmx_batch_accumulate(tppmx_batch *b, uint64_t seed, int32_t ite
   CK(ctx, cudaSetDevice(ctx->device));
   CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
   int launches = 0;
-  if (do_psm) {
-    psm_accumulate_kernel<<<dim3(d.n_chains, d.T), 256, 0, ctx->stream>>>(d, b->psm_cnt);
-    launches++;
-  }
-  if (do_pred) {
-    predict_kernel<<<dim3(d.n_chains, d.T), 128, 0, ctx->stream>>>(d, seed, iter, b->pred_pi, nullptr, nullptr);
-    pi_accumulate_kernel<<<d.n_chains, 256, 0, ctx->stream>>>(d, b->pred_pi, b->pi_sum);
-    launches += 2;
-  }
-  if (do_psm || do_pred) {
-    count_saves_kernel<<<(d.n_chains + 255) / 256, 256, 0, ctx->stream>>>(d, b->psm_n, b->pi_n, do_psm, do_pred);
-    launches++;
-  }
+  RC(accumulate_launch(b, seed, iter, do_psm, do_pred, &launches));
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
-  CK(ctx, cudaGetLastError());
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;
   CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));

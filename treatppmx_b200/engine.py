@@ -155,6 +155,23 @@ class Batch:
         self.ctx.check(self.ctx.L.tppmx_batch_last_timing(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    # ---- full iterations on the device (sweep + the remaining updates) ---------------------------
+    def update(self, seed: int, iter_: int):
+        self.ctx.check(self.ctx.L.tppmx_batch_update(self.h, seed, iter_))
+
+    def run(self, seed: int, iter0: int, n_iter: int, burn: int = 0, thin: int = 1, psm: bool = False,
+            predictive: bool = False):
+        """n_iter full iterations; saved iterations ((l > burn-1) and (l+1) % thin == 0) feed the
+        device summaries."""
+        self.ctx.check(self.ctx.L.tppmx_batch_run(self.h, seed, iter0, n_iter, burn, thin, int(psm), int(predictive)))
+
+    def get_acceptance(self, chain: int):
+        d = self.dims
+        ea = np.zeros((d.T, d.ntmax), dtype=np.int32, order="F")
+        ba = np.zeros((max(d.Q, 1), d.D), dtype=np.int32, order="F")
+        self.ctx.check(self.ctx.L.tppmx_batch_get_acceptance(self.h, chain, ea.ctypes.data_as(c_ip), ba.ctypes.data_as(c_ip)))
+        return ea, ba
+
     # ---- posterior summaries accumulated on the device (include/tppmx.h) -------------------
     def reset_summaries(self):
         self.ctx.check(self.ctx.L.tppmx_batch_reset_summaries(self.h))
