@@ -257,9 +257,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # burn-in so K has settled before anything is timed (not part of warm-up accounting)
+    # burn-in with FULL iterations (sweep + eta/hierarchy/sigma-kappa/beta/JJ-ss updates) so that the
+    # partitions the timed sweeps see are posterior draws, not the frozen initial eta (untimed)
     it = 0
-    batch.sweep(seed, it, args.burn)
+    batch.run(seed, it, args.burn)
     it += args.burn
     for _ in range(args.warmup):
         batch.sweep(seed, it, args.sweeps)
@@ -286,6 +287,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     dev_ms = float(sum(ms_steps))
     lab, ncl = batch.get_partitions()
     Kbar = float(ncl.mean())
+    Kmax = int(ncl.max())
 
     # predictive step (device-resident), timed separately
     pred = None
@@ -296,6 +298,29 @@ def run_native(args, rank: int, world: int, local_rank: int):
             pms.append(batch.last_timing()[0])
         pred = {"ms": float(np.median(pms)),
                 "new_patient_arm_scores_per_s": nchains * dims.npred * dims.T / (np.median(pms) * 1e-3)}
+
+    # full iterations (SURVEY §8d "Gibbs sweeps/s"): sweep + every other update of the reference's
+    # iteration, with the predictive step and the co-clustering counts on EVERY iteration (thin=1)
+    full = None
+    if dims.npred > 0:
+        nfull = args.sweeps
+        batch.reset_summaries()
+        batch.run(seed, it, 3, burn=0, thin=1, psm=True, predictive=True)
+        it += 3
+        fms, fl = [], 0
+        for _ in range(max(2, min(args.steps, 5))):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            batch.run(seed, it, nfull, burn=0, thin=1, psm=True, predictive=True)
+            ms, nl = batch.last_timing()
+            fms.append(ms)
+            fl += nl
+            it += nfull
+        fmed = float(np.median(fms))
+        full = {"gibbs_iterations_per_sec": nchains * nfull / (fmed * 1e-3), "ms_per_iteration_all_chains": fmed / nfull,
+                "reallocations_per_sec": nchains * dims.nobs * nfull / (fmed * 1e-3),
+                "includes": "sweep + eta MH + (Theta,Sigma) + (sigma,kappa) + beta MH + horseshoe + JJ/ss + predictive + co-clustering, every iteration",
+                "launches_per_iteration": fl / (len(fms) * nfull)}
 
     # final gather of the posterior summaries (the only cross-GPU step of the path): a few saved
     # iterations are accumulated on the device, then every rank's per-dataset summaries are
@@ -366,9 +391,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, w),
             "gibbs_sweeps_per_sec": world * nchains * args.sweeps * args.steps / (dev_ms_max * 1e-3),
-            "mean_clusters_per_arm": Kbar_all,
+            "mean_clusters_per_arm": Kbar_all, "max_clusters_per_arm_rank0": Kmax,
             "cluster_scores_per_sec": value * (Kbar_all + model.CC),
             "predictive": pred,
+            "full_iteration": full,
             "summary_gather": gather,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,

@@ -179,6 +179,11 @@ static int dev_upload(tppmx_batch *b, const T **p, const std::vector<T> &h) {
   return TPPMX_OK;
 }
 static bool fast_eligible(const tppmx_batch *b, int lpu);
+// one thread per new patient of an (chain, arm) block: no more threads than patients
+static inline int predict_threads(const DevBatch &d) {
+  const int t = ((d.npred + 31) / 32) * 32;
+  return t < 32 ? 32 : (t > 128 ? 128 : t);
+}
 static int fast_reserve(tppmx_batch *b);
 #define RC(x)            \
   do {                   \
@@ -968,9 +973,12 @@ static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launc
   const DevBatch &d = b->d;
   if (d.model.cohesion == 2 && d.ncat > 0)
     return fail(ctx, TPPMX_ERR_ARG, "the (sigma,kappa) update needs ncat == 0 (as the reference, dm_ppmx_ct.cpp:942)");
-  const int nth = 256;
-  const size_t smem = sizeof(double) * (2 * nth + (size_t)d.T * d.D * d.D + 16) + sizeof(int) * d.T;
-  update_kernel<<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
+  const int nth = 128;  // 3 worker warps + 1 serial warp (update.cuh)
+  const size_t smem = sizeof(double) * (64 + (size_t)d.T * d.D * d.D + 16);
+  if (d.D == 3)
+    update_kernel<3><<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
+  else
+    update_kernel<0><<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
   (*launches)++;
   CK(ctx, cudaGetLastError());
   return TPPMX_OK;
@@ -1101,7 +1109,7 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
   double *dpi = pipred ? b->pred_pi : nullptr, *dy = ypred ? b->pred_y : nullptr;
   int *dc = predclass ? b->pred_c : nullptr;
   CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
-  predict_kernel<<<dim3(d.n_chains, d.T), 128, 0, ctx->stream>>>(d, seed, iter, dpi, dy, dc);
+  predict_kernel<<<dim3(d.n_chains, d.T), predict_threads(d), 0, ctx->stream>>>(d, seed, iter, dpi, dy, dc);
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess && pipred) e = cudaMemcpy(pipred, dpi, n1 * sizeof(double), cudaMemcpyDeviceToHost);
@@ -1138,7 +1146,7 @@ static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do
     (*launches)++;
   }
   if (do_pred) {
-    predict_kernel<<<dim3(d.n_chains, d.T), 128, 0, ctx->stream>>>(d, seed, iter, b->pred_pi, nullptr, nullptr);
+    predict_kernel<<<dim3(d.n_chains, d.T), predict_threads(d), 0, ctx->stream>>>(d, seed, iter, b->pred_pi, nullptr, nullptr);
     pi_accumulate_kernel<<<d.n_chains, 256, 0, ctx->stream>>>(d, b->pred_pi, b->pi_sum);
     (*launches) += 2;
   }
