@@ -395,7 +395,7 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
     TRY(dev_alloc(b, &d.eta_flag, ns * T * d.kcap));
     TRY(dev_alloc(b, &d.beta_flag, ns * Q * D));
     TRY(dev_alloc(b, &b->ua.eta2, (size_t)n_chains * T * 2 * D * d.kcap));
-    TRY(dev_alloc(b, &b->ua.pat2, (size_t)n_chains * 2 * T * d.ntmax));
+    TRY(dev_alloc(b, &b->ua.pat2, (size_t)n_chains * 3 * T * d.ntmax));
     TRY(dev_alloc(b, &b->ua.os, (size_t)n_chains * T * d.G));
     TRY(dev_alloc(b, &b->ua.acc, (size_t)n_chains * T * d.kcap));
     // scratch of the call paths, reserved here so that no call allocates

@@ -20,7 +20,7 @@ namespace tppmx {
 
 struct UpdArgs {
   double *eta2;  // [nc][T][2][D][kcap]  old / proposed eta*
-  double *pat2;  // [nc][2][T][ntmax]    per-patient current / proposed likelihood sums
+  double *pat2;  // [nc][3][T][ntmax]    per-patient current / proposed likelihood sums (+ log JJ)
   double *os;    // [nc][T][G]           (sigma,kappa) grid weights
   int *acc;      // [nc][T][kcap]        accept flags of this iteration
 };
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128, 5) update_kernel(DevBatch b, UpdArgs ua, 
   double *Theta = b.Theta + (size_t)chain * T * D;
   double *Sigma = b.Sigma + (size_t)chain * T * D * D;
   double *eold = ua.eta2 + (size_t)chain * T * 2 * D * ks;
-  double *cur = ua.pat2 + (size_t)chain * 2 * T * ntm;
+  double *cur = ua.pat2 + (size_t)chain * 3 * T * ntm;
   double *prop = cur + (size_t)T * ntm;
   int *acc = ua.acc + (size_t)chain * T * ks;
   const int *arm_n = b.arm_n + (size_t)ds * T;
@@ -217,18 +217,19 @@ __global__ void __launch_bounds__(128, 5) update_kernel(DevBatch b, UpdArgs ua, 
         const int nt = arm_n[t];
         const double dn = (double)nt, nu0 = b.model.hP0_nu0;
         double em[DM], ecov[DM * DM], S[DM * DM];
+        // eta_i = eta*[label_i] (:885): mean and covariance over patients are sums over the K
+        // clusters weighted by their sizes (same value, K instead of n_t terms)
+        const int K = nclu[t];
         for (int k = 0; k < D; k++) {
           double a = 0.0;
-          for (int i = 0; i < nt; i++) a += eta[((size_t)t * D + k) * ks + labels[t * ntm + i] - 1];
+          for (int j = 0; j < K; j++) a += (double)njv[t * ks + j] * eta[((size_t)t * D + k) * ks + j];
           em[k] = a / dn;
         }
         for (int k = 0; k < D; k++)
           for (int r = 0; r < D; r++) {
             double a = 0.0;
-            for (int i = 0; i < nt; i++) {
-              const int j = labels[t * ntm + i] - 1;
-              a += (eta[((size_t)t * D + k) * ks + j] - em[k]) * (eta[((size_t)t * D + r) * ks + j] - em[r]);
-            }
+            for (int j = 0; j < K; j++)
+              a += (double)njv[t * ks + j] * ((eta[((size_t)t * D + k) * ks + j] - em[k]) * (eta[((size_t)t * D + r) * ks + j] - em[r]));
             ecov[k + D * r] = a / dn;
           }
         const double fplp = b.model.hP0_s0 + (dn * .5);
@@ -362,25 +363,40 @@ __global__ void __launch_bounds__(128, 5) update_kernel(DevBatch b, UpdArgs ua, 
   }
 
   // ================= beta Metropolis steps, utils_ct.cpp:750-791 =================
+  // The "current" sum of category kk (log_den's data part) is the same for q = 0..Q-1 until a
+  // proposal is accepted, and then equals the accepted proposal's sum: the per-patient terms are
+  // kept in scratch (ljs, cu, pr) so that each (kk, q) step costs one exp + one lgamma per patient.
   if (b.model.noprog != 1) {
     const double *sigma_beta = b.sigma_beta + (size_t)chain * Q * D;
-    for (int kk = 0; kk < D; kk++)
+    double *ljs = cur, *cu = prop, *pr = prop + (size_t)T * ntm;  // >= nobs entries each
+    for (int kk = 0; kk < D; kk++) {
+      double sd = 0.0, dummy = 0.0;
+      for (int i = tid; i < nobs; i += nw) {
+        const double lj = fast_log(JJ[(size_t)i * D + kk]);
+        const double g0 = fast_exp(lg[(size_t)i * D + kk]);
+        const double c = g0 * lj - lgamma_pos(g0);
+        ljs[i] = lj;
+        cu[i] = c;
+        sd += c;
+      }
+      workers_sum2(sd, dummy, red, nw);
       for (int q = 0; q < Q; q++) {
         const int h = kk + q * D;
         const double bh = beta[h];
         double n0, n1;
         rng_n2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)(kk * Q + q), 0, n0, n1);
         const double beta_p = bh + mh_beta * n0;
-        double sd = 0.0, sn = 0.0;
+        double sn = 0.0;
+        dummy = 0.0;
         for (int i = tid; i < nobs; i += nw) {
-          const double lgv = lg[(size_t)i * D + kk], lj = fast_log(JJ[(size_t)i * D + kk]);
           const double zq = z[(size_t)i * Q + q];
-          const double lgp = __dadd_rn(__dsub_rn(lgv, __dmul_rn(bh, zq)), __dmul_rn(beta_p, zq));  // :764
-          const double g0 = fast_exp(lgv), g1 = fast_exp(lgp);
-          sd += g0 * lj - lgamma_pos(g0);
-          sn += g1 * lj - lgamma_pos(g1);
+          const double lgp = __dadd_rn(__dsub_rn(lg[(size_t)i * D + kk], __dmul_rn(bh, zq)), __dmul_rn(beta_p, zq));  // :764
+          const double g1 = fast_exp(lgp);
+          const double c = g1 * ljs[i] - lgamma_pos(g1);
+          pr[i] = c;
+          sn += c;
         }
-        workers_sum2(sd, sn, red, nw);
+        workers_sum2(sn, dummy, red, nw);
         const double sb = sigma_beta[h];
         const double log_den = sd + dnorm_log(bh, 0.0, sb), log_num = sn + dnorm_log(beta_p, 0.0, sb);
         double u0, u1;
@@ -389,7 +405,9 @@ __global__ void __launch_bounds__(128, 5) update_kernel(DevBatch b, UpdArgs ua, 
           for (int i = tid; i < nobs; i += nw) {
             const double zq = z[(size_t)i * Q + q];
             lg[(size_t)i * D + kk] = __dadd_rn(__dsub_rn(lg[(size_t)i * D + kk], __dmul_rn(bh, zq)), __dmul_rn(beta_p, zq));
+            cu[i] = pr[i];
           }
+          sd = sn;
           if (tid == 0) {
             beta[h] = beta_p;
             b.beta_flag[(size_t)chain * Q * D + q + Q * kk] += 1;
@@ -397,6 +415,7 @@ __global__ void __launch_bounds__(128, 5) update_kernel(DevBatch b, UpdArgs ua, 
         }
         bar_workers(nw);
       }
+    }
   }
   __threadfence_block();
   bar_arrive2(nth);  // beta is final: the serial warp may run the horseshoe
