@@ -149,6 +149,32 @@ def cpu_oracle_rate(w, n_threads: int, target_s: float, sweeps_hint: int = 0):
     return rate, f"{n_threads} chains (one per thread) x {nsw} sweeps x {dims.nobs} patients of the bench workload", dt, nsw
 
 
+def cpu_oracle_full_rate(w, n_threads: int, target_s: float):
+    """Full iterations (sweep + updates + predictive) of the oracle port, one chain per thread."""
+    import oracle_binding as ob
+    from concurrent.futures import ThreadPoolExecutor
+
+    model, dims = w["model"], w["dims"]
+    pbs = [ob.Problem(model, dims, w["shared"], w["dsets"][i % len(w["dsets"])]) for i in range(n_threads)]
+    sts = [pbs[i].init_state(7, i, w["labels"], w["nclu"], w["beta0"]) for i in range(n_threads)]
+    t0 = time.perf_counter()
+    pbs[0].iterate(sts[0], 7, 0, 0, 3)
+    pbs[0].predict(sts[0], 7, 0, 3)
+    per_it = (time.perf_counter() - t0) / 3
+    nit = max(3, int(target_s / max(per_it, 1e-6)))
+
+    def work(i):
+        for l in range(nit):
+            pbs[i].iterate(sts[i], 7, i, 3 + l, 1)
+            pbs[i].predict(sts[i], 7, i, 3 + l)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as ex:
+        list(ex.map(work, range(n_threads)))
+    dt = time.perf_counter() - t0
+    return n_threads * nit / dt, f"{n_threads} chains (one per thread) x {nit} full iterations incl. predictive ({dt:.1f} s)"
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
@@ -415,6 +441,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
             r1, desc1, dt1, _ = cpu_oracle_rate(w, 1, 4.0)
             out["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": ncores, "kind": "port",
                                    "sample": desc + f" ({dt:.1f} s)", "single_core_value": r1}
+            if full is not None:
+                fr, fdesc = cpu_oracle_full_rate(w, ncores, 6.0)
+                full["cpu_port_gibbs_iterations_per_sec"] = fr
+                full["cpu_port_sample"] = fdesc
         emit(out)
     batch.close()
     ctx.close()

@@ -103,7 +103,7 @@ __device__ inline void workers_sum2(double &a, double &b, double *red, int nw) {
 // DD = 3 (the package's outcome dimension: loops unroll, the small matrices live in registers)
 // or 0 (generic, D <= TPPMX_MAXD).  dynamic smem: (64 + T*D*D + 16) doubles + T ints
 template <int DD>
-__global__ void __launch_bounds__(128, 5) update_kernel(DevBatch b, UpdArgs ua, uint64_t seed, int l) {
+__global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, uint64_t seed, int l) {
   extern __shared__ double sm[];
   const int chain = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int nw = nth - 32;           // worker threads
