@@ -51,7 +51,7 @@ def build_workload(args, rank: int):
     nd = args.datasets
     dims_kw, dsets, ex = datagen.genmech_synthetic(
         n=args.n, npred=args.npred, P=args.P, Q=args.Q, T=args.T, n_datasets=nd,
-        seed=20240001 + 1000 * rank, mixture=args.mixture)
+        seed=20240001, mixture=args.mixture, first_replicate=rank * nd)  # one study, ranks take slices
     dims = datagen.make_dims(G=100, kcap=args.kcap, **dims_kw)
     shared = datagen.make_shared(dims, ex["n_a"], cohesion=model.cohesion,
                                  kmax=(args.kcap if args.kcap > 0 else None))
@@ -360,14 +360,21 @@ def run_native(args, rank: int, world: int, local_rank: int):
             batch.accumulate(seed, it, psm=True, predictive=True)
             it += 1
         loc = multigpu.device_summaries_as_torch(batch, [0.0, 40.0, 100.0])
+        if world > 1:  # first collective of the communicator: connection set-up, not part of the gather
+            warm = torch.zeros(world * 4, device="cuda")
+            dist.all_gather_into_tensor(warm, torch.ones(4, device="cuda"))
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        allsum = multigpu.gather_summaries(loc, world * len(w["dsets"]))
-        ev1.record()
-        torch.cuda.synchronize()
+        gms = []
+        for rep in range(3):   # the first call also pays NCCL's lazy channel set-up for this size
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            allsum = multigpu.gather_summaries(loc, world * len(w["dsets"]))
+            ev1.record()
+            torch.cuda.synchronize()
+            gms.append(ev0.elapsed_time(ev1))
         gbytes = sum(v.numel() * v.element_size() for v in allsum.values())
-        gather = {"ms": ev0.elapsed_time(ev1), "bytes_gathered": int(gbytes),
+        gather = {"ms": float(min(gms)), "ms_first_call": float(gms[0]), "bytes_gathered": int(gbytes),
                   "arrays": {k: list(v.shape) for k, v in allsum.items()},
                   "backend": "nccl" if world > 1 else "none (single GPU: device copy)"}
         del allsum, loc
@@ -384,13 +391,22 @@ def run_native(args, rank: int, world: int, local_rank: int):
     h2d, d2h = e2e_bytes(w, elab, encl, epi)
 
     # reduce over ranks: max time, sum work
-    t = torch.tensor([dev_ms, e2e_s, Kbar], dtype=torch.float64, device="cuda")
+    full_ms = (nchains * 1e3 / full["gibbs_iterations_per_sec"]) if full else 0.0   # ms per iteration of all chains
+    t = torch.tensor([dev_ms, e2e_s, Kbar, full_ms], dtype=torch.float64, device="cuda")
+    by_rank = None
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        by_rank = {"ms_per_step": [float(x[0]) / args.steps for x in allt], "mean_clusters_per_arm": [float(x[2]) for x in allt]}
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms_max, e2e_s_max, Kbar_all = float(tmax[0]), float(tmax[1]), float(tsum[2]) / world
+        if full:  # max over ranks, like every multi-GPU time
+            full["ms_per_iteration_all_chains"] = float(tmax[3])
+            full["gibbs_iterations_per_sec"] = nchains * 1e3 / float(tmax[3])
+            full["reallocations_per_sec"] = full["gibbs_iterations_per_sec"] * dims.nobs
     else:
         dev_ms_max, e2e_s_max, Kbar_all = dev_ms, e2e_s, Kbar
 
@@ -416,7 +432,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, w),
-            "gibbs_sweeps_per_sec": world * nchains * args.sweeps * args.steps / (dev_ms_max * 1e-3),
+            "reallocation_sweeps_per_sec": world * nchains * args.sweeps * args.steps / (dev_ms_max * 1e-3),
+            "gibbs_sweeps_per_sec": (world * full["gibbs_iterations_per_sec"]) if full else None,
             "mean_clusters_per_arm": Kbar_all, "max_clusters_per_arm_rank0": Kmax,
             "cluster_scores_per_sec": value * (Kbar_all + model.CC),
             "predictive": pred,
@@ -434,6 +451,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
                              "lanes_per_unit": args.lpu or 16},
             "wall_s_timed_region": t_wall,
             "clocks": clocks,
+            "by_rank": by_rank,
         }
         if args.cpu_baseline and world == 1:
             ncores = os.cpu_count() or 1

@@ -120,7 +120,7 @@ def _spearman_fdr_beta(y: np.ndarray, Z: np.ndarray) -> np.ndarray:
 
 def genmech_synthetic(n: int = 152, npred: int = 28, P: int = 10, Q: int = 2, T: int = 2,
                       n_datasets: int = 1, seed: int = 20240001, ncat: int = 0, maxC: int = 3,
-                      mixture: int = 0):
+                      mixture: int = 0, first_replicate: int | None = None):
     """genmech-style replicate datasets (R/gendata.R:134-254): one covariate matrix, fresh
     outcomes per replicate.  Returns (dims_kwargs, [HostDataset...], extras).
 
@@ -128,7 +128,11 @@ def genmech_synthetic(n: int = 152, npred: int = 28, P: int = 10, Q: int = 2, T:
     `mixture`-component Gaussian mixture in the first 5 columns (config 4).  Z: N(0,1).
     Outcome: D=3 ordinal logit on metx built from the first two principal components
     (genoutcome, :30-47), product with the prognostic-only probabilities (:187-193).
-    Arms cycle 0..T-1 (trtsgn, :196)."""
+    Arms cycle 0..T-1 (trtsgn, :196).
+
+    first_replicate: if given, replicate k (k = first_replicate + 0, 1, ...) draws its outcomes
+    from its own stream keyed by (seed, k), so the ranks of a multi-GPU run can each build their
+    slice of ONE simulation study (same covariates, disjoint replicates)."""
     rng = np.random.default_rng(seed)
     ntot = n + npred
     e = rng.standard_normal((ntot, P))
@@ -178,11 +182,17 @@ def genmech_synthetic(n: int = 152, npred: int = 28, P: int = 10, Q: int = 2, T:
         xcat_all = np.zeros((ntot, 1), dtype=np.int32)
 
     datasets = []
-    for _ in range(n_datasets):
+    cum = [np.cumsum(mp / mp.sum(1, keepdims=True), axis=1) for mp in myprob]
+    for r in range(n_datasets):
         y = np.zeros((n, 3))
-        for i in range(n):
-            pr = myprob[treat[i]][i]
-            y[i, rng.choice(3, p=pr / pr.sum())] = 1.0
+        if first_replicate is None:
+            for i in range(n):
+                pr = myprob[treat[i]][i]
+                y[i, rng.choice(3, p=pr / pr.sum())] = 1.0
+        else:
+            u = np.random.default_rng([seed, first_replicate + r]).random(n)
+            for i in range(n):
+                y[i, min(int(np.searchsorted(cum[treat[i]][i], u[i], side="right")), 2)] = 1.0
         datasets.append(HostDataset(
             treat=treat, y=y, z=Z[:n], xcon=X[:n],
             xcat=xcat_all[:n, : max(ncat, 1)], zpred=Z[n:] if npred else np.zeros((1, Q)),
