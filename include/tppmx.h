@@ -259,6 +259,75 @@ int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_iter
                     int32_t thin, int32_t do_psm, int32_t do_pred);
 int tppmx_batch_get_acceptance(tppmx_batch *b, int32_t chain, int32_t *eta_acc, int32_t *beta_acc);
 
+/* ---- drop-in for the reference's entry point -------------------------------------------------
+ * tppmx_dm_ppmx_ct runs what dm_ppmx_ct() runs (src/dm_ppmx_ct.cpp:10-1472) for ONE chain,
+ * entirely on the device, from the same 42 arguments (in the reference's order and layouts:
+ * doubles, col-major matrices, row-major flattened covariates, exactly what
+ * _treatppmx_dm_ppmx_ct receives, src/RcppExports.cpp:16-65) into the same 18 outputs
+ * (src/dm_ppmx_ct.cpp:1453-1471), caller-allocated and col-major so an Rcpp shim wraps them
+ * without reshuffling.  nout = (iter - burn) / thin.  Any output pointer may be NULL.
+ * Extra inputs: the leading dimensions Armadillo carries implicitly, `seed` (the shim draws it
+ * from unif_rand() so set.seed() governs the run), and optionally the compact log V table
+ * (logV_compact, layout of tppmx_shared.logV) instead of the dense Vwm cube. */
+typedef struct tppmx_ppmxct_args {
+  int32_t iter, burn, thin, nobs;
+  const double *treatments;    /* [nobs], 0-based arm of each patient                    */
+  int32_t PPMx, ncon, ncat;
+  const double *catvec;        /* [ncat]                                                 */
+  double alpha;
+  const double *grid;          /* 2 x G col-major                                        */
+  int32_t G;
+  const double *Vwm;           /* Vwm_rows x Vwm_cols x G col-major cube (R/dm_ppmx_ct.R:243) or NULL */
+  int32_t Vwm_rows, Vwm_cols;
+  const double *logV_compact;  /* [A][2][ntmax][G] or NULL (used when Vwm == NULL)       */
+  int32_t cohesion, CC, reuse, consim, similarity, calibration, coardegree;
+  const double *y;             /* nobs x D col-major                                     */
+  int32_t D;
+  const double *z;             /* nobs x Q col-major                                     */
+  int32_t Q;
+  const double *zpred;         /* npred x Q col-major                                    */
+  int32_t noprog;
+  const double *xcon, *xcat, *xconp, *xcatp; /* row-major flattened (as.vector(t(.)))     */
+  int32_t npred;
+  const double *similparam;    /* [7]                                                    */
+  const double *hP0_mu0;       /* [D]                                                    */
+  double hP0_nu0, hP0_s0, hP0_Lambda0;
+  int32_t upd_hier;
+  const double *initbeta;      /* [Q*D]                                                  */
+  int32_t hsp;
+  const double *mhtunepar;     /* [2]                                                    */
+  int32_t A;
+  const double *n_a;           /* [A]                                                    */
+  const double *curr_cluster;  /* A x ntmax col-major, 1-based labels                    */
+  const double *card_cluster;  /* A x ntmax col-major (recomputed from curr_cluster)     */
+  int32_t ntmax;               /* = ncol(curr_cluster) = max n_a                         */
+  const double *ncluster_curr; /* [A]                                                    */
+  uint64_t seed;
+} tppmx_ppmxct_args;
+
+typedef struct tppmx_ppmxct_out { /* names of the returned list, :1453-1471 */
+  double *eta;         /* field nout x A of D x ntmax matrices: block (ll + nout*t)        */
+  double *beta;        /* (Q*D) x nout                                                     */
+  double *sigma_ngg;   /* A x nout                                                         */
+  double *kappa_ngg;   /* A x nout                                                         */
+  double *eta_acc;     /* A x ntmax : eta_flag / sumtotclu (:1432-1434)                    */
+  double *beta_acc;    /* Q x D     : beta_flag (raw counts, as the reference returns)     */
+  double *cl_lab;      /* A x ntmax x nout                                                 */
+  double *num_treat;   /* [A]                                                              */
+  double *pi;          /* nobs x D x nout                                                  */
+  double *pipred;      /* nout blocks of npred x D x A                                     */
+  double *yispred;     /* nobs x D x nout                                                  */
+  double *ypred;       /* nout blocks of npred x D x A                                     */
+  double *clupred;     /* (nout*npred) x A                                                 */
+  double *nclus;       /* A x nout                                                         */
+  double *WAIC;        /* [1]                                                              */
+  double *lpml;        /* [nout]                                                           */
+  double *theta_prior; /* D x A                                                            */
+  double *sigma_prior; /* D x D x A                                                        */
+} tppmx_ppmxct_out;
+
+int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *in, tppmx_ppmxct_out *out);
+
 /* ---- posterior summaries on the device (what a multi-GPU run gathers) ----------------------
  * The package returns per-iteration cl_lab / pipred (src/dm_ppmx_ct.cpp:1402-1404, :1396) and
  * leaves the co-clustering matrix (mcclust::comp.psm, R/treatppmx.R:29) and the treatment

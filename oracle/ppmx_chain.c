@@ -400,3 +400,47 @@ void oracle_wishart(uint64_t seed, uint32_t chain, int32_t l, const double *S, d
   o_rng g = {seed, chain};
   o_wishart(&g, l, 0, S, df, n, W);
 }
+
+/* utils_ct.cpp:842-874 */
+static double o_dmultinom(const double *x_in, int size, const double *prob_in, int K, int Log) {
+  double prob[TPPMX_MAXD], x[TPPMX_MAXD];
+  double s = 0.0;
+  for (int i = 0; i < K; i++) s += prob_in[i];
+  for (int i = 0; i < K; i++) prob[i] = prob_in[i] / s;
+  for (int i = 0; i < K; i++) x[i] = floor(x_in[i] + .5);
+  double r = lgamma(size + 1);
+  for (int i = 0; i < K; i++) {
+    /* the reference evaluates x*log(prob) for every i; with x == 0 the term is 0 as long as
+     * prob > 0, which JJ >= 1e-100 guarantees */
+    if (x[i] != 0.0) r += x[i] * log(prob[i]) - lgamma(x[i] + 1);
+  }
+  return Log ? r : exp(r);
+}
+
+/* in-sample fit of a saved iteration, src/dm_ppmx_ct.cpp:1060-1075.
+ * pi, ispred: nobs x D col-major; like: [nobs].  rmultinom(1, pii) is one inverse-CDF uniform. */
+int oracle_insample(const oracle_problem *pb, const tppmx_state *s, uint64_t seed, uint32_t chain_id,
+                    int32_t l, double *pi, double *ispred, double *like) {
+  const int nobs = pb->dims.nobs, dim = pb->dims.D;
+  o_rng g = {seed, chain_id};
+  for (int i = 0; i < nobs; i++) {
+    double TT = 0.0, pii[TPPMX_MAXD], yrow[TPPMX_MAXD];
+    for (int k = 0; k < dim; k++) TT += s->JJ[i + nobs * k];
+    for (int k = 0; k < dim; k++) {
+      pii[k] = s->JJ[i + nobs * k] / TT;
+      yrow[k] = pb->data.y[i + nobs * k];
+      if (pi) pi[i + nobs * k] = pii[k];
+    }
+    double u0, u1, cw = 0.0;
+    o_rng_u2(&g, (uint32_t)l, TPPMX_SITE_ISPRED, 0, (uint32_t)i, 0, &u0, &u1);
+    int pick = dim - 1;
+    for (int k = 0; k < dim; k++) {
+      cw += pii[k];
+      if (u0 < cw) { pick = k; break; }
+    }
+    if (ispred)
+      for (int k = 0; k < dim; k++) ispred[i + nobs * k] = (k == pick) ? 1.0 : 0.0;
+    if (like) like[i] = o_dmultinom(yrow, 1, pii, dim, 0);
+  }
+  return 0;
+}

@@ -75,6 +75,8 @@ int oracle_update_iter(const oracle_problem *pb, tppmx_state *s, uint64_t seed, 
                        int32_t l, int32_t *eta_acc, int32_t *beta_acc);
 int oracle_iterate(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,
                    int32_t iter0, int32_t n_iter, int32_t *eta_acc, int32_t *beta_acc);
+int oracle_insample(const oracle_problem *pb, const tppmx_state *s, uint64_t seed, uint32_t chain_id,
+                    int32_t l, double *pi, double *ispred, double *like);
 double oracle_gammainc(double a, double x);
 double oracle_gammaincinv(double a, double p);
 double oracle_dmvnrm_log(const double *x, const double *mean, const double *sigma, int n);

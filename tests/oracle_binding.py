@@ -60,6 +60,7 @@ def lib():
         i32p = c_ip
         L.oracle_update_iter.argtypes = [P, S, u64, u32, C.c_int32, i32p, i32p]
         L.oracle_iterate.argtypes = [P, S, u64, u32, C.c_int32, C.c_int32, i32p, i32p]
+        L.oracle_insample.argtypes = [P, S, u64, u32, C.c_int32, c_dp, c_dp, c_dp]
         L.oracle_gammainc.restype = d
         L.oracle_gammainc.argtypes = [d, d]
         L.oracle_gammaincinv.restype = d
@@ -135,6 +136,18 @@ class Problem:
         f = lambda a: a.ctypes.data_as(c_ip) if a is not None else c_ip()
         rc = lib().oracle_iterate(C.byref(self.c), C.byref(cs), seed, chain_id, iter0, n_iter, f(ea), f(ba))
         assert rc == 0, rc
+
+    def insample(self, s: HostState, seed, chain_id, iter_):
+        """In-sample fit of a saved iteration (:1060-1075): pi, ispred (nobs x D), like (nobs)."""
+        d = self.dims
+        pi = np.zeros((d.nobs, d.D), order="F")
+        isp = np.zeros((d.nobs, d.D), order="F")
+        like = np.zeros(d.nobs)
+        cs = s.cstruct()
+        rc = lib().oracle_insample(C.byref(self.c), C.byref(cs), seed, chain_id, iter_, pi.ctypes.data_as(c_dp),
+                                   isp.ctypes.data_as(c_dp), like.ctypes.data_as(c_dp))
+        assert rc == 0, rc
+        return pi, isp, like
 
     def predict(self, s: HostState, seed, chain_id, iter_):
         d = self.dims

@@ -17,6 +17,7 @@
 #include "summary.cuh"
 #include "sweep_fast.cuh"
 #include "update.cuh"
+#include "dropin.cuh"
 
 using namespace tppmx;
 
@@ -1216,4 +1217,146 @@ extern "C" int tppmx_batch_summaries(tppmx_batch *b, const double *util_w, doubl
   if (utility) CK(ctx, cudaMemcpy(utility, du, sizeof(double) * d.n_datasets * d.npred * d.T, cudaMemcpyDeviceToHost));
   if (best_arm) CK(ctx, cudaMemcpy(best_arm, db, sizeof(int32_t) * d.n_datasets * d.npred, cudaMemcpyDeviceToHost));
   return TPPMX_OK;
+}
+
+// ---- drop-in for dm_ppmx_ct (reference src/dm_ppmx_ct.cpp:10-1472), one chain -----------------------
+extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppmx_ppmxct_out *o) {
+  if (!ctx || ctx->closed) return TPPMX_ERR_ARG;
+  if (!a || !o) return fail(ctx, TPPMX_ERR_ARG, "null argument");
+  if (a->iter < 1 || a->burn < 0 || a->thin < 1 || a->burn > a->iter) return fail(ctx, TPPMX_ERR_ARG, "iter/burn/thin");
+  if (!a->treatments || !a->y || !a->grid || !a->similparam || !a->hP0_mu0 || !a->mhtunepar || !a->n_a ||
+      !a->curr_cluster || !a->ncluster_curr || (a->Q > 0 && (!a->z || !a->initbeta)) || (a->ncon > 0 && !a->xcon) ||
+      (a->ncat > 0 && (!a->xcat || !a->catvec)))
+    return fail(ctx, TPPMX_ERR_ARG, "null input array");
+  const int nobs = a->nobs, T = a->A, D = a->D, Q = a->Q, P = a->ncon, ncat = a->ncat, npred = a->npred, G = a->G;
+  const int ntm = a->ntmax, nout = (a->iter - a->burn) / a->thin;
+  if (T < 1 || T > TPPMX_MAXT || D < 1 || D > TPPMX_MAXD || ntm < 1 || G < 1) return fail(ctx, TPPMX_ERR_ARG, "dims out of range");
+
+  tppmx_model M;
+  memset(&M, 0, sizeof(M));
+  M.PPMx = a->PPMx; M.cohesion = a->cohesion; M.similarity = a->similarity; M.consim = a->consim;
+  M.calibration = a->calibration; M.coardegree = a->coardegree; M.reuse = a->reuse; M.CC = a->CC;
+  M.upd_hier = a->upd_hier; M.hsp = a->hsp; M.noprog = a->noprog; M.nolik = 0; M.alpha = a->alpha;
+  for (int k = 0; k < 7; k++) M.similparam[k] = a->similparam[k];
+  for (int k = 0; k < D; k++) M.hP0_mu0[k] = a->hP0_mu0[k];
+  M.hP0_nu0 = a->hP0_nu0; M.hP0_s0 = a->hP0_s0; M.hP0_Lambda0 = a->hP0_Lambda0;
+  M.mhtune_eta = a->mhtunepar[0]; M.mhtune_beta = a->mhtunepar[1];
+
+  std::vector<int32_t> treat(nobs), catvec(ncat > 0 ? ncat : 1, 0), xcat((size_t)nobs * (ncat > 0 ? ncat : 1), 0),
+      xcatp((size_t)(npred > 0 ? npred : 1) * (ncat > 0 ? ncat : 1), 0);
+  int maxC = 0;
+  for (int i = 0; i < nobs; i++) treat[i] = (int32_t)a->treatments[i];
+  for (int p = 0; p < ncat; p++) {
+    catvec[p] = (int32_t)a->catvec[p];
+    if (catvec[p] > maxC) maxC = catvec[p];  // max_C = catvec.max() (:107)
+  }
+  for (size_t e = 0; e < (size_t)nobs * ncat; e++) xcat[e] = (int32_t)a->xcat[e];
+  for (size_t e = 0; e < (size_t)npred * ncat; e++) xcatp[e] = (int32_t)a->xcatp[e];
+
+  tppmx_dims dm;
+  memset(&dm, 0, sizeof(dm));
+  dm.nobs = nobs; dm.T = T; dm.D = D; dm.Q = Q; dm.P = P; dm.ncat = ncat; dm.maxC = maxC; dm.npred = npred;
+  dm.G = G; dm.ntmax = ntm; dm.kcap = 0;
+
+  std::vector<double> logV;
+  const double *logVp = a->logV_compact;
+  if (a->cohesion == 2 && a->Vwm) {  // the two rows of the dense cube that are read (:563, :680, :981)
+    logV.assign((size_t)T * 2 * ntm * G, -INFINITY);
+    for (int t = 0; t < T; t++)
+      for (int r = 0; r < 2; r++) {
+        const int row = (int)a->n_a[t] - 2 + r;
+        if (row < 0 || row >= a->Vwm_rows) continue;
+        for (int K = 1; K <= ntm && K <= a->Vwm_cols; K++)
+          for (int g = 0; g < G; g++)
+            logV[(((size_t)t * 2 + r) * ntm + (K - 1)) * G + g] =
+                log(a->Vwm[row + (size_t)a->Vwm_rows * ((K - 1) + (size_t)a->Vwm_cols * g)]);
+      }
+    logVp = logV.data();
+  }
+  if (a->cohesion == 2 && !logVp) return fail(ctx, TPPMX_ERR_ARG, "cohesion 2 needs Vwm or logV_compact");
+  tppmx_shared sh = {catvec.data(), a->grid, a->cohesion == 2 ? logVp : nullptr};
+  tppmx_dataset ds = {treat.data(), a->y, a->z, a->xcon, xcat.data(), a->zpred, a->xconp, xcatp.data()};
+
+  tppmx_batch *B = nullptr;
+  RC(tppmx_batch_create(ctx, &M, &dm, &sh, 1, &ds, 1, nullptr, nullptr, &B));
+  std::vector<int32_t> lab((size_t)T * ntm), ncl(T);
+  for (size_t e = 0; e < lab.size(); e++) lab[e] = (int32_t)a->curr_cluster[e];
+  for (int t = 0; t < T; t++) ncl[t] = (int32_t)a->ncluster_curr[t];
+  int rc = tppmx_batch_init(B, a->seed, lab.data(), ncl.data(), a->initbeta);
+
+  const DevBatch &d = B->d;
+  TraceBufs tr;
+  memset(&tr, 0, sizeof(tr));
+  tr.nout = nout > 0 ? nout : 1;
+  std::vector<void *> tofree;
+  auto dalloc = [&](double **p, size_t n) {
+    if (rc) return;
+    void *q = nullptr;
+    if (cudaMalloc(&q, sizeof(double) * (n ? n : 1)) != cudaSuccess) { rc = fail(ctx, TPPMX_ERR_NOMEM, "trace buffers"); return; }
+    cudaMemsetAsync(q, 0, sizeof(double) * (n ? n : 1), ctx->stream);
+    tofree.push_back(q);
+    *p = (double *)q;
+  };
+  const size_t no = (size_t)tr.nout, n1 = (size_t)npred * D * T;
+  dalloc(&tr.eta, no * T * D * ntm); dalloc(&tr.beta, no * Q * D); dalloc(&tr.sigma, no * T); dalloc(&tr.kappa, no * T);
+  dalloc(&tr.cl_lab, no * T * ntm); dalloc(&tr.pi, no * nobs * D); dalloc(&tr.pipred, no * n1);
+  dalloc(&tr.yispred, no * nobs * D); dalloc(&tr.ypred, no * n1); dalloc(&tr.clupred, no * npred * T);
+  dalloc(&tr.nclus, no * T); dalloc(&tr.lpml, no); dalloc(&tr.mnlike, nobs); dalloc(&tr.mnllike, nobs);
+  dalloc(&tr.sumtotclu, T);
+
+  int launches = 0, ll = 0;
+  for (int l = 0; l < a->iter && !rc; l++) {
+    rc = sweep_launch(B, a->seed, l, 1, false, &launches);
+    if (!rc) rc = update_launch(B, a->seed, l, &launches);
+    if (rc) break;
+    sumtotclu_kernel<<<1, 32, 0, ctx->stream>>>(d, tr);
+    if ((l > (a->burn - 1)) && ((l + 1) % a->thin == 0) && ll < nout) {  // :1060
+      if (npred > 0)
+        predict_kernel<<<dim3(1, T), predict_threads(d), 0, ctx->stream>>>(d, a->seed, l, B->pred_pi, B->pred_y, B->pred_c);
+      insample_save_kernel<<<1, 256, 0, ctx->stream>>>(d, tr, a->seed, l, ll, B->pred_pi, B->pred_y, B->pred_c);
+      ll++;
+    }
+  }
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: kernel failure");
+  if (!rc) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, std::string("dm_ppmx_ct: ") + cudaGetErrorString(e));
+  }
+  if (!rc) rc = check_status(B);
+  auto dl = [&](double *dst, const double *src, size_t n) {
+    if (!rc && dst && n && cudaMemcpy(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: download");
+  };
+  if (nout > 0) {
+    dl(o->eta, tr.eta, no * T * D * ntm); dl(o->beta, tr.beta, no * Q * D); dl(o->sigma_ngg, tr.sigma, no * T);
+    dl(o->kappa_ngg, tr.kappa, no * T); dl(o->cl_lab, tr.cl_lab, no * T * ntm); dl(o->pi, tr.pi, no * nobs * D);
+    dl(o->pipred, tr.pipred, no * n1); dl(o->yispred, tr.yispred, no * nobs * D); dl(o->ypred, tr.ypred, no * n1);
+    dl(o->clupred, tr.clupred, no * npred * T); dl(o->nclus, tr.nclus, no * T); dl(o->lpml, tr.lpml, no);
+  }
+  if (!rc) {
+    std::vector<double> mn(nobs), mnl(nobs), stc(T);
+    dl(mn.data(), tr.mnlike, nobs); dl(mnl.data(), tr.mnllike, nobs); dl(stc.data(), tr.sumtotclu, T);
+    if (!rc && o->WAIC) {  // :1445-1450
+      double el = 0.0;
+      for (int i = 0; i < nobs; i++) el += (2 * mnl[i] - log(mn[i]));
+      *o->WAIC = -2 * el;
+    }
+    std::vector<int32_t> ea((size_t)T * ntm), ba((size_t)(Q > 0 ? Q : 1) * D);
+    if (!rc) rc = tppmx_batch_get_acceptance(B, 0, ea.data(), ba.data());
+    if (!rc && o->eta_acc)
+      for (int t = 0; t < T; t++)
+        for (int j = 0; j < ntm; j++) o->eta_acc[t + (size_t)T * j] = (double)ea[t + (size_t)T * j] / stc[t];  // :1432-1434
+    if (!rc && o->beta_acc)
+      for (int e = 0; e < Q * D; e++) o->beta_acc[e] = (double)ba[e];
+    if (!rc && o->num_treat)
+      for (int t = 0; t < T; t++) o->num_treat[t] = a->n_a[t];
+    tppmx_state st;
+    memset(&st, 0, sizeof(st));
+    st.Theta = o->theta_prior;
+    st.Sigma = o->sigma_prior;
+    if (!rc) rc = tppmx_batch_get_state(B, 0, &st);
+  }
+  for (void *q : tofree) cudaFree(q);
+  tppmx_batch_destroy(B);
+  return rc;
 }

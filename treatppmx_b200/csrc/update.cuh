@@ -64,9 +64,40 @@ __device__ __forceinline__ double d_dmvn_log(const double *x, int xstride, const
     for (int k = 0; k < r; k++) s -= L[r + n * k] * z[k];
     z[r] = s / L[r + n * r];
     zz += z[r] * z[r];
-    rootisum += log(1.0 / L[r + n * r]);
+    rootisum += fast_log(1.0 / L[r + n * r]);
   }
   return -(double)n / 2.0 * 1.8378770664093453 - 0.5 * zz + rootisum;
+}
+
+// Out-of-line copies of the heavy helpers: the kernel has ~15 call sites of Philox / gamma /
+// lgamma; inlined, the code grows to ~270 KB and the instruction cache, not the math, bounds it
+// (profiles/r1_update_kernel_*: stall_no_instruction 3.8 per issue).
+__device__ __noinline__ double upd_lgamma(double x) { return lgamma_pos(x); }
+__device__ __noinline__ double upd_gamma(Rng g, uint32_t iter, uint32_t site, uint32_t arm, uint32_t index, double a) {
+  return rng_gamma(g, iter, site, arm, index, a);
+}
+__device__ __noinline__ double2 upd_u2(Rng g, uint32_t iter, uint32_t site, uint32_t arm, uint32_t index, uint32_t sub) {
+  double u0, u1;
+  rng_u2(g, iter, site, arm, index, sub, u0, u1);
+  return make_double2(u0, u1);
+}
+__device__ __noinline__ double2 upd_n2(Rng g, uint32_t iter, uint32_t site, uint32_t arm, uint32_t index, uint32_t sub) {
+  double n0, n1;
+  rng_n2(g, iter, site, arm, index, sub, n0, n1);
+  return make_double2(n0, n1);
+}
+__device__ __noinline__ double upd_gammainc(double a, double x) { return tppmx_gammainc(a, x); }
+__device__ __noinline__ double upd_gammaincinv(double a, double p) { return tppmx_gammaincinv(a, p); }
+__device__ __noinline__ double upd_log(double x) { return fast_log(x); }
+__device__ __noinline__ double upd_exp(double x) { return fast_exp(x); }
+// D standard normals (block b gives normals 2b, 2b+1), as rng_normals
+__device__ __forceinline__ void upd_normals(const Rng &g, uint32_t iter, uint32_t site, uint32_t arm, uint32_t index,
+                                            int D, double *out) {
+  for (int bq = 0; 2 * bq < D; bq++) {
+    const double2 n = upd_n2(g, iter, site, arm, index, (uint32_t)bq);
+    out[2 * bq] = n.x;
+    if (2 * bq + 1 < D) out[2 * bq + 1] = n.y;
+  }
 }
 
 // named barriers: 1 = the worker warps among themselves, 2 = workers -> serial warp hand-off
@@ -141,7 +172,7 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
     const int t = e / ks, j = e - t * ks;
     if (j < nclu[t]) {
       double nrm[DM];
-      rng_normals(rng, l, TPPMX_SITE_ETA_PROP, t, (uint32_t)j, D, nrm, 1);
+      upd_normals(rng, l, TPPMX_SITE_ETA_PROP, t, (uint32_t)j, D, nrm);
       for (int k = 0; k < D; k++) {
         const double ev = eta[((size_t)t * D + k) * ks + j];
         eold[(((size_t)t * 2 + 0) * D + k) * ks + j] = ev;
@@ -156,11 +187,11 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       const int i = arm_pat[e], j = labels[e] - 1;
       double c = 0.0, p = 0.0;
       for (int k = 0; k < D; k++) {
-        const double lgv = lg[(size_t)i * D + k], lj = fast_log(JJ[(size_t)i * D + k]);
+        const double lgv = lg[(size_t)i * D + k], lj = upd_log(JJ[(size_t)i * D + k]);
         const double e0 = eold[(((size_t)t * 2 + 0) * D + k) * ks + j], e1 = eold[(((size_t)t * 2 + 1) * D + k) * ks + j];
-        const double g0 = fast_exp(lgv), g1 = fast_exp(__dadd_rn(__dsub_rn(lgv, e0), e1));  // :651
-        c += lgamma_pos(g0) + g0 * lj;
-        p += lgamma_pos(g1) + g1 * lj;
+        const double g0 = upd_exp(lgv), g1 = upd_exp(__dadd_rn(__dsub_rn(lgv, e0), e1));  // :651
+        c += upd_lgamma(g0) + g0 * lj;
+        p += upd_lgamma(g1) + g1 * lj;
       }
       cur[e] = c;
       prop[e] = p;
@@ -181,8 +212,8 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       log_den += d_dmvn_log<DM>(eold + (((size_t)t * 2 + 0) * D) * ks + j, ks, Theta + t * D, L, D);
       log_den += d_dmvn_log<DM>(eold + (((size_t)t * 2 + 1) * D) * ks + j, ks, Theta + t * D, L, D);  // quirk 9 (:671)
       double u0, u1;
-      rng_u2(rng, l, TPPMX_SITE_ETA_PROP, t, (uint32_t)j, 0x100u, u0, u1);
-      const int ok = log(u0) < log_num - log_den;
+      { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_ETA_PROP, t, (uint32_t)j, 0x100u); u0 = r2_.x; u1 = r2_.y; }
+      const int ok = upd_log(u0) < log_num - log_den;
       acc[e] = ok;
       if (ok) {
         b.eta_flag[(size_t)chain * T * ks + e] += 1;
@@ -242,10 +273,10 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
         d_chol_lower<DM>(S, D, L);
         for (int i = 0; i < D * D; i++) A[i] = 0.0;
         for (int k = 0; k < D; k++) {
-          A[k + D * k] = sqrt(2.0 * rng_gamma(rng, l, TPPMX_SITE_HIER_W, t, (uint32_t)k, 0.5 * (fplp - (double)k)));
+          A[k + D * k] = sqrt(2.0 * upd_gamma(rng, l, TPPMX_SITE_HIER_W, t, (uint32_t)k, 0.5 * (fplp - (double)k)));
           for (int r = 0; r < k; r++) {
             double n0, n1;
-            rng_n2(rng, l, TPPMX_SITE_HIER_W, t, (uint32_t)(1000 + k * D + r), 0, n0, n1);
+            { const double2 r2_ = upd_n2(rng, l, TPPMX_SITE_HIER_W, t, (uint32_t)(1000 + k * D + r), 0); n0 = r2_.x; n1 = r2_.y; }
             A[k + D * r] = n0;
           }
         }
@@ -266,7 +297,7 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
         for (int k = 0; k < D * D; k++) tmp[k] = Lam[k] * (dn + nu0);
         d_inv_spd<DM>(tmp, D, sptp);
         d_chol_lower<DM>(sptp, D, L);
-        rng_normals(rng, l, TPPMX_SITE_HIER_THETA, t, 0, D, zn, 1);
+        upd_normals(rng, l, TPPMX_SITE_HIER_THETA, t, 0, D, zn);
         for (int k = 0; k < D; k++) {
           double a = fptp[k];
           for (int r = 0; r <= k; r++) a += L[k + D * r] * zn[r];
@@ -285,15 +316,15 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       double tau = b.tau[chain];
       for (int k = 0; k < len; k++) {
         double u0, u1;
-        rng_u2(rng, l, TPPMX_SITE_HS_LAMBDA, 0, (uint32_t)k, 0, u0, u1);
+        { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_HS_LAMBDA, 0, (uint32_t)k, 0); u0 = r2_.x; u1 = r2_.y; }
         double et = 1.0 / (lambda[k] * lambda[k]);
         const double upsi = u0 * (1.0 / (1.0 + et));
         const double tempps = (beta[k] * beta[k]) / (2.0 * tau * tau);
         const double ub = (1.0 - upsi) / upsi;
-        double Fub = 1.0 - exp(-tempps * ub);
+        double Fub = 1.0 - upd_exp(-tempps * ub);
         if (Fub < 1e-4) Fub = 1e-4;
         const double up = u1 * Fub;
-        et = -log(1.0 - up) / tempps;
+        et = -upd_log(1.0 - up) / tempps;
         lambda[k] = 1.0 / sqrt(et);
       }
       double tempt = 0.0, u0, u1;
@@ -303,14 +334,14 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       }
       tempt = tempt / 2.0;
       double et = 1.0 / (tau * tau);
-      rng_u2(rng, l, TPPMX_SITE_HS_TAU, 0, 0, 0, u0, u1);
+      { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_HS_TAU, 0, 0, 0); u0 = r2_.x; u1 = r2_.y; }
       const double utau = u0 * (1.0 / (1.0 + et));
       const double ubt = (1.0 - utau) / utau;
       const double shape = ((double)len + 1.0) / 2.0;
-      double Fubt = tppmx_gammainc(shape, ubt * tempt);
+      double Fubt = upd_gammainc(shape, ubt * tempt);
       if (Fubt < 1e-4) Fubt = 1e-4;
       const double ut = u1 * Fubt;
-      et = tppmx_gammaincinv(shape, ut) / tempt;
+      et = upd_gammaincinv(shape, ut) / tempt;
       if (et < .0001) et = .0001;
       tau = 1.0 / sqrt(et);
       if (tau < .0001) tau = .0001;
@@ -331,8 +362,8 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       const double sg = b.grid[2 * g];
       const int K = nclu[t];
       double v = 0.0;
-      const double l1 = lgamma_pos(1.0 - sg);
-      for (int j = 0; j < K; j++) v += lgamma_pos((double)njv[t * ks + j] - sg) - l1;
+      const double l1 = upd_lgamma(1.0 - sg);
+      for (int j = 0; j < K; j++) v += upd_lgamma((double)njv[t * ks + j] - sg) - l1;
       v += b.logV[(((size_t)t * 2 + 1) * ntm + (K - 1)) * G + g];
       os[e] = v;
     }
@@ -342,12 +373,12 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       for (int g = 1; g < G; g++) mx = fmax(mx, os[t * G + g]);
       double den = 0.0;
       for (int g = 0; g < G; g++) {
-        const double e = exp(os[t * G + g] - mx);
+        const double e = upd_exp(os[t * G + g] - mx);
         os[t * G + g] = e;
         den += e;
       }
       double u0, u1, cw = 0.0;
-      rng_u2(rng, l, TPPMX_SITE_SIGKAP, t, 0, 0, u0, u1);
+      { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_SIGKAP, t, 0, 0); u0 = r2_.x; u1 = r2_.y; }
       int pk = G - 1;
       for (int g = 0; g < G; g++) {
         cw += os[t * G + g] / den;
@@ -372,9 +403,9 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
     for (int kk = 0; kk < D; kk++) {
       double sd = 0.0, dummy = 0.0;
       for (int i = tid; i < nobs; i += nw) {
-        const double lj = fast_log(JJ[(size_t)i * D + kk]);
-        const double g0 = fast_exp(lg[(size_t)i * D + kk]);
-        const double c = g0 * lj - lgamma_pos(g0);
+        const double lj = upd_log(JJ[(size_t)i * D + kk]);
+        const double g0 = upd_exp(lg[(size_t)i * D + kk]);
+        const double c = g0 * lj - upd_lgamma(g0);
         ljs[i] = lj;
         cu[i] = c;
         sd += c;
@@ -384,15 +415,15 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
         const int h = kk + q * D;
         const double bh = beta[h];
         double n0, n1;
-        rng_n2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)(kk * Q + q), 0, n0, n1);
+        { const double2 r2_ = upd_n2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)(kk * Q + q), 0); n0 = r2_.x; n1 = r2_.y; }
         const double beta_p = bh + mh_beta * n0;
         double sn = 0.0;
         dummy = 0.0;
         for (int i = tid; i < nobs; i += nw) {
           const double zq = z[(size_t)i * Q + q];
           const double lgp = __dadd_rn(__dsub_rn(lg[(size_t)i * D + kk], __dmul_rn(bh, zq)), __dmul_rn(beta_p, zq));  // :764
-          const double g1 = fast_exp(lgp);
-          const double c = g1 * ljs[i] - lgamma_pos(g1);
+          const double g1 = upd_exp(lgp);
+          const double c = g1 * ljs[i] - upd_lgamma(g1);
           pr[i] = c;
           sn += c;
         }
@@ -400,8 +431,8 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
         const double sb = sigma_beta[h];
         const double log_den = sd + dnorm_log(bh, 0.0, sb), log_num = sn + dnorm_log(beta_p, 0.0, sb);
         double u0, u1;
-        rng_u2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)(kk * Q + q), 1, u0, u1);
-        if (log(u0) < log_num - log_den) {  // same inputs in every worker thread: uniform branch
+        { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)(kk * Q + q), 1); u0 = r2_.x; u1 = r2_.y; }
+        if (upd_log(u0) < log_num - log_den) {  // same inputs in every worker thread: uniform branch
           for (int i = tid; i < nobs; i += nw) {
             const double zq = z[(size_t)i * Q + q];
             lg[(size_t)i * D + kk] = __dadd_rn(__dsub_rn(lg[(size_t)i * D + kk], __dmul_rn(bh, zq)), __dmul_rn(beta_p, zq));
@@ -423,8 +454,8 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
   // ================= JJ, ss gamma draws, src/dm_ppmx_ct.cpp:1042-1055 =================
   for (int e = tid; e < nobs * D; e += nw) {
     const int i = e / D;
-    const double shape = y[e] + fast_exp(lg[e]);
-    double v = rng_gamma(rng, l, TPPMX_SITE_JJ, 0, (uint32_t)e, shape) * (1.0 / (ss[i] + 1.0));
+    const double shape = y[e] + upd_exp(lg[e]);
+    double v = upd_gamma(rng, l, TPPMX_SITE_JJ, 0, (uint32_t)e, shape) * (1.0 / (ss[i] + 1.0));
     if (v < 1e-100) v = 1e-100;
     JJ[e] = v;
   }
@@ -432,7 +463,7 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
   for (int i = tid; i < nobs; i += nw) {
     double TT = 0.0;
     for (int k = 0; k < D; k++) TT += JJ[(size_t)i * D + k];
-    ss[i] = rng_gamma(rng, l, TPPMX_SITE_SS, 0, (uint32_t)i, 1.0) * (1.0 / TT);
+    ss[i] = upd_gamma(rng, l, TPPMX_SITE_SS, 0, (uint32_t)i, 1.0) * (1.0 / TT);
   }
   (void)P;
 }
