@@ -39,6 +39,59 @@ __device__ inline PredW pred_weight(const DevBatch &b, const SimConst &s, const 
   return r;
 }
 
+// :1366-1382 given the drawn cluster: eta_pred (the cluster's eta*, or N(Theta, Sigma) for an
+// auxiliary pick), pi = softmax(eta_pred + beta' zpred) without max-shift as the reference,
+// one multinomial draw, outputs in the reference's layouts.
+__device__ inline void pred_emit(const DevBatch &b, const Rng &rng, const ArmView &A, int iter, int tt, int pp, int ds,
+                                 int newci, int K, const double *beta, const double *Theta, const double *Sigma,
+                                 size_t obase, int chain, double *pipred, double *ypred, int *predclass) {
+  const int D = b.D, npred = b.npred;
+  double eta_pred[TPPMX_MAXD];
+  if (newci <= K) {  // :1366-1370
+    for (int k = 0; k < D; k++) eta_pred[k] = A.eta[(size_t)k * A.ks + newci - 1];
+  } else {
+    double zn[TPPMX_MAXD], L[TPPMX_MAXD * TPPMX_MAXD];
+    rng_normals(rng, iter, TPPMX_SITE_PRED_ETA, tt, (uint32_t)pp, D, zn, 1);
+    for (int a = 0; a < D; a++)
+      for (int c = 0; c <= a; c++) {
+        double sum = Sigma[a + D * c];
+        for (int k = 0; k < c; k++) sum -= L[a + D * k] * L[c + D * k];
+        L[a + D * c] = (a == c) ? sqrt(sum) : sum / L[c + D * c];
+      }
+    for (int k = 0; k < D; k++) {
+      double acc = Theta[k];
+      for (int r = 0; r <= k; r++) acc += L[k + D * r] * zn[r];
+      eta_pred[k] = acc;
+    }
+  }
+  // :1373-1379 softmax(eta_pred + beta' zpred) without max-shift, as the reference
+  const double *zp = b.zpred + ((size_t)ds * npred + pp) * b.Q;
+  double pi_row[TPPMX_MAXD], sumrow = 0.0;
+  for (int k = 0; k < D; k++) {
+    double lg = eta_pred[k];
+    for (int q = 0; q < b.Q; q++) lg += beta[k + q * D] * zp[q];
+    pi_row[k] = exp(lg);
+    sumrow += pi_row[k];
+  }
+  for (int k = 0; k < D; k++) pi_row[k] = pi_row[k] / sumrow;
+  double uy, uy1, cw = 0.0;  // :1381 rmultinom(1, pi)
+  rng_u2(rng, iter, TPPMX_SITE_PRED_Y, tt, (uint32_t)pp, 0, uy, uy1);
+  int pick = D - 1;
+  for (int k = 0; k < D; k++) {
+    cw += pi_row[k];
+    if (uy < cw) {
+      pick = k;
+      break;
+    }
+  }
+  for (int k = 0; k < D; k++) {
+    const size_t o = obase + pp + (size_t)npred * (k + (size_t)D * tt);
+    if (pipred) pipred[o] = pi_row[k];
+    if (ypred) ypred[o] = (k == pick) ? 1.0 : 0.0;
+  }
+  if (predclass) predclass[(size_t)chain * npred * b.T + pp + (size_t)npred * tt] = newci;
+}
+
 // grid = (chains, T); threads stride over new patients
 __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed, int iter,
                                                       double *pipred, double *ypred,
@@ -112,50 +165,110 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
       }
     }
 
-    double eta_pred[TPPMX_MAXD];
-    if (newci <= K) {  // :1366-1370
-      for (int k = 0; k < D; k++) eta_pred[k] = A.eta[(size_t)k * A.ks + newci - 1];
-    } else {
-      double zn[TPPMX_MAXD], L[TPPMX_MAXD * TPPMX_MAXD];
-      rng_normals(rng, iter, TPPMX_SITE_PRED_ETA, tt, (uint32_t)pp, D, zn, 1);
-      for (int a = 0; a < D; a++)
-        for (int c = 0; c <= a; c++) {
-          double sum = Sigma[a + D * c];
-          for (int k = 0; k < c; k++) sum -= L[a + D * k] * L[c + D * k];
-          L[a + D * c] = (a == c) ? sqrt(sum) : sum / L[c + D * c];
+    pred_emit(b, rng, A, iter, tt, pp, ds, newci, K, beta, Theta, Sigma, obase, chain, pipred, ypred, predclass);
+  }
+}
+
+// ---- fast variant for the default switches (PPMx=1, NN auxiliary similarity, calibration 0|2,
+// ncat=0), the same closed form as sweep_fast.cuh: for an occupied cluster j and a new patient
+//   w_j = C0_j + C1_j * b_j + C2_j * qx,   b_j = sum_p t_jp x_p,  qx = sum_p x_p^2,
+// with t_jp = sumx_jp / v2 + m0 / s20 and the three coefficients functions of (n_j, sum_p t_jp^2)
+// only.  A block stages t [P][K] and the coefficients in shared memory once; a thread then needs
+// P fused multiply-adds per cluster and no transcendental before the softmax.
+// dynamic smem: ((P + 3) * KP + P * nth + (KP + 1) * nth) doubles, KP = clusters staged (>= K).
+__global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t seed, int iter, int KP,
+                                                           double *pipred, double *ypred, int *predclass) {
+  extern __shared__ double psm[];
+  const int chain = blockIdx.x, tt = blockIdx.y, tid = threadIdx.x, nth = blockDim.x;
+  const int ds = b.chain_ds[chain];
+  const SimConst s = make_simconst(b);
+  const Rng rng = make_rng(seed, b.chain_id[chain]);
+  const ArmView A = arm_view_global(b, chain, tt, ds);
+  const int K = A.K, CC = b.CC, D = b.D, P = b.P, npred = b.npred;
+  double *ts = psm;                  // [P][KP]
+  double *c0s = ts + (size_t)P * KP; // [KP] x 3
+  double *c1s = c0s + KP, *c2s = c1s + KP;
+  double *xs = c2s + KP;             // [P][nth]
+  double *ws = xs + (size_t)P * nth; // [KP + 1][nth]
+  const double sigma = b.sigma[(size_t)chain * b.T + tt];
+  const int idxs = b.idxs[chain];
+  const double scale = (s.calibration == 2) ? s.calscale : 1.0;
+  double dV = 0.0;
+  if (s.cohesion == 2 && K >= 1) {
+    const size_t base = ((size_t)tt * 2) * b.ntmax;
+    dV = b.logV[(base + b.ntmax + (K - 1)) * b.G + idxs] - b.logV[(base + (K - 1)) * b.G + idxs];
+  }
+  const double dP = (double)P;
+  for (int j = tid; j < K; j += nth) {  // per-cluster coefficients
+    const int n = A.nj[j];
+    double a = 0.0;
+    for (int p = 0; p < P; p++) {
+      const double t = fma(A.sumx[(size_t)p * A.ks + j], s.iv2, s.c0);
+      ts[(size_t)p * KP + j] = t;
+      a = fma(t, t, a);
+    }
+    const NNRow r0 = b.nn_tab[n], r1 = b.nn_tab[n + 1];
+    const double coh = (s.cohesion == 1) ? log((double)n) : dV + log((double)n - sigma);
+    c0s[j] = coh + scale * (dP * (r1.A0 - r0.A0) + (r1.H - r0.H) * a);
+    c1s[j] = scale * 2.0 * s.iv2 * r1.H;
+    c2s[j] = scale * (r1.H * s.iv2 * s.iv2 - s.hiv2);
+  }
+  // auxiliary clusters: t = c0 for every p, n = 0
+  const NNRow q1 = b.nn_tab[1];
+  const double a_aux = dP * s.c0 * s.c0;
+  const double coh_aux = (s.cohesion == 1) ? log(b.model.alpha) - log((double)CC) : dV;
+  const double *beta = b.beta + (size_t)chain * b.Q * D;
+  const double *Theta = b.Theta + ((size_t)chain * b.T + tt) * D;
+  const double *Sigma = b.Sigma + ((size_t)chain * b.T + tt) * D * D;
+  const size_t obase = (size_t)chain * npred * D * b.T;
+  __syncthreads();
+
+  for (int pp0 = 0; pp0 < npred; pp0 += nth) {
+    const int pp = pp0 + tid;
+    const bool on = pp < npred;
+    double qx = 0.0, sx = 0.0;
+    if (on) {
+      const double *x = b.xp + ((size_t)ds * npred + pp) * P;
+      for (int p = 0; p < P; p++) {
+        const double xv = x[p];
+        xs[(size_t)p * nth + tid] = xv;
+        qx = fma(xv, xv, qx);
+        sx += xv;
+      }
+    }
+    if (on) {
+      double wmax = -INFINITY;
+      for (int j = 0; j < K; j++) {
+        double bj = 0.0;
+        for (int p = 0; p < P; p++) bj = fma(ts[(size_t)p * KP + j], xs[(size_t)p * nth + tid], bj);
+        const double w = c0s[j] + c1s[j] * bj + c2s[j] * qx;
+        ws[(size_t)j * nth + tid] = w;
+        wmax = fmax(wmax, w);
+      }
+      const double tY = a_aux + s.iv2 * (2.0 * s.c0 * sx + s.iv2 * qx);
+      const double w_aux = coh_aux + scale * (dP * q1.A0 - s.hiv2 * qx + q1.H * tY);
+      wmax = fmax(wmax, w_aux);
+      double den = 0.0;
+      for (int j = 0; j < K; j++) {
+        const double e = exp(ws[(size_t)j * nth + tid] - wmax);
+        ws[(size_t)j * nth + tid] = e;
+        den += e;
+      }
+      const double e_aux = exp(w_aux - wmax);
+      for (int m = 0; m < CC; m++) den += e_aux;
+      double uu, u1;
+      rng_u2(rng, iter, TPPMX_SITE_PRED_U, tt, (uint32_t)pp, 0, uu, u1);
+      int newci = K + CC;  // quirk 7: see predict_kernel
+      double cw = 0.0;
+      for (int j = 0; j < K + CC; j++) {
+        cw += ((j < K) ? ws[(size_t)j * nth + tid] : e_aux) / den;
+        if (uu < cw) {
+          newci = j + 1;
+          break;
         }
-      for (int k = 0; k < D; k++) {
-        double acc = Theta[k];
-        for (int r = 0; r <= k; r++) acc += L[k + D * r] * zn[r];
-        eta_pred[k] = acc;
       }
+      pred_emit(b, rng, A, iter, tt, pp, ds, newci, K, beta, Theta, Sigma, obase, chain, pipred, ypred, predclass);
     }
-    // :1373-1379 softmax(eta_pred + beta' zpred) without max-shift, as the reference
-    const double *zp = b.zpred + ((size_t)ds * npred + pp) * b.Q;
-    double pi_row[TPPMX_MAXD], sumrow = 0.0;
-    for (int k = 0; k < D; k++) {
-      double lg = eta_pred[k];
-      for (int q = 0; q < b.Q; q++) lg += beta[k + q * D] * zp[q];
-      pi_row[k] = exp(lg);
-      sumrow += pi_row[k];
-    }
-    for (int k = 0; k < D; k++) pi_row[k] = pi_row[k] / sumrow;
-    double uy, uy1, cw = 0.0;  // :1381 rmultinom(1, pi)
-    rng_u2(rng, iter, TPPMX_SITE_PRED_Y, tt, (uint32_t)pp, 0, uy, uy1);
-    int pick = D - 1;
-    for (int k = 0; k < D; k++) {
-      cw += pi_row[k];
-      if (uy < cw) {
-        pick = k;
-        break;
-      }
-    }
-    for (int k = 0; k < D; k++) {
-      const size_t o = obase + pp + (size_t)npred * (k + (size_t)D * tt);
-      if (pipred) pipred[o] = pi_row[k];
-      if (ypred) ypred[o] = (k == pick) ? 1.0 : 0.0;
-    }
-    if (predclass) predclass[(size_t)chain * npred * b.T + pp + (size_t)npred * tt] = newci;
   }
 }
 

@@ -180,6 +180,7 @@ static int dev_upload(tppmx_batch *b, const T **p, const std::vector<T> &h) {
   return TPPMX_OK;
 }
 static bool fast_eligible(const tppmx_batch *b, int lpu);
+static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc);
 // one thread per new patient of an (chain, arm) block: no more threads than patients
 static inline int predict_threads(const DevBatch &d) {
   const int t = ((d.npred + 31) / 32) * 32;
@@ -1110,7 +1111,7 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
   double *dpi = pipred ? b->pred_pi : nullptr, *dy = ypred ? b->pred_y : nullptr;
   int *dc = predclass ? b->pred_c : nullptr;
   CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
-  predict_kernel<<<dim3(d.n_chains, d.T), predict_threads(d), 0, ctx->stream>>>(d, seed, iter, dpi, dy, dc);
+  RC(predict_launch(b, d.n_chains, seed, iter, dpi, dy, dc));
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess && pipred) e = cudaMemcpy(pipred, dpi, n1 * sizeof(double), cudaMemcpyDeviceToHost);
@@ -1121,6 +1122,34 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
   cudaEventElapsedTime(&ms, b->ev0, b->ev1);
   b->last_ms = ms;
   b->last_launches = 1;
+  return TPPMX_OK;
+}
+
+// Predictive step: the closed-form kernel for the default switches (same eligibility as the fast
+// sweep, any reuse), the generic kernel otherwise or when the clusters do not fit the staged
+// capacity.  The partition size is not known on the host, so the staged capacity is kcap capped
+// at 64; chains with more clusters are rare and handled by the block itself falling back is not
+// possible mid-kernel, hence the cap decides the kernel for the whole launch.
+static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc) {
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  const tppmx_model &m = d.model;
+  const int nth = predict_threads(d);
+  const bool eligible = b->opt_impl != 1 && m.PPMx == 1 && m.consim == 1 && m.similarity == 1 &&
+                        (m.calibration == 0 || m.calibration == 2) && d.ncat == 0 && d.P >= 1 && d.kcap <= 128;
+  if (eligible) {
+    const int KP = d.kcap;
+    const size_t smem = sizeof(double) * ((size_t)(d.P + 3) * KP + (size_t)d.P * nth + (size_t)(KP + 1) * nth);
+    if (smem <= 200 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(predict_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("predict_fast_kernel: ") + cudaGetErrorString(e));
+      predict_fast_kernel<<<dim3(n_chains_launch, d.T), nth, smem, ctx->stream>>>(d, seed, iter, KP, dpi, dy, dc);
+      CK(ctx, cudaGetLastError());
+      return TPPMX_OK;
+    }
+  }
+  predict_kernel<<<dim3(n_chains_launch, d.T), nth, 0, ctx->stream>>>(d, seed, iter, dpi, dy, dc);
+  CK(ctx, cudaGetLastError());
   return TPPMX_OK;
 }
 
@@ -1147,7 +1176,7 @@ static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do
     (*launches)++;
   }
   if (do_pred) {
-    predict_kernel<<<dim3(d.n_chains, d.T), predict_threads(d), 0, ctx->stream>>>(d, seed, iter, b->pred_pi, nullptr, nullptr);
+    RC(predict_launch(b, d.n_chains, seed, iter, b->pred_pi, nullptr, nullptr));
     pi_accumulate_kernel<<<d.n_chains, 256, 0, ctx->stream>>>(d, b->pred_pi, b->pi_sum);
     (*launches) += 2;
   }
@@ -1312,7 +1341,7 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
     sumtotclu_kernel<<<1, 32, 0, ctx->stream>>>(d, tr);
     if ((l > (a->burn - 1)) && ((l + 1) % a->thin == 0) && ll < nout) {  // :1060
       if (npred > 0)
-        predict_kernel<<<dim3(1, T), predict_threads(d), 0, ctx->stream>>>(d, a->seed, l, B->pred_pi, B->pred_y, B->pred_c);
+        rc = predict_launch(B, 1, a->seed, l, B->pred_pi, B->pred_y, B->pred_c);
       insample_save_kernel<<<1, 256, 0, ctx->stream>>>(d, tr, a->seed, l, ll, B->pred_pi, B->pred_y, B->pred_c);
       ll++;
     }
