@@ -981,7 +981,9 @@ static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launc
     update_kernel<3><<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
   else
     update_kernel<0><<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
-  (*launches)++;
+  const size_t npat = (size_t)d.n_chains * d.nobs;
+  jjss_kernel<<<(unsigned)((npat + 127) / 128), 128, 0, ctx->stream>>>(d, seed, iter);
+  (*launches) += 2;
   CK(ctx, cudaGetLastError());
   return TPPMX_OK;
 }

@@ -25,14 +25,19 @@ struct UpdArgs {
   int *acc;      // [nc][T][kcap]        accept flags of this iteration
 };
 
-// lower Cholesky factor, column-major n x n (n <= DM; with a compile-time n everything unrolls
-// into registers)
+// lower Cholesky factor, column-major n x n (n <= DM).  The loops are deliberately NOT unrolled:
+// this code runs once per chain and iteration on one lane, so its cost is instruction fetch,
+// not arithmetic (profiles/r1_update_kernel_*: stall_no_instruction dominates).
 template <int DM>
 __device__ __forceinline__ void d_chol_lower(const double *A, int n, double *L) {
+  #pragma unroll 1
   for (int i = 0; i < n * n; i++) L[i] = 0.0;
+  #pragma unroll 1
   for (int i = 0; i < n; i++)
+    #pragma unroll 1
     for (int j = 0; j <= i; j++) {
       double sum = A[i + n * j];
+      #pragma unroll 1
       for (int k = 0; k < j; k++) sum -= L[i + n * k] * L[j + n * k];
       L[i + n * j] = (i == j) ? sqrt(sum) : sum / L[j + n * j];
     }
@@ -41,16 +46,23 @@ template <int DM>
 __device__ __forceinline__ void d_inv_spd(const double *A, int n, double *Ainv) {
   double L[DM * DM], Li[DM * DM];
   d_chol_lower<DM>(A, n, L);
+  #pragma unroll 1
   for (int i = 0; i < n * n; i++) Li[i] = 0.0;
+  #pragma unroll 1
   for (int c = 0; c < n; c++)
+    #pragma unroll 1
     for (int r = 0; r < n; r++) {
       double s = (r == c) ? 1.0 : 0.0;
+      #pragma unroll 1
       for (int k = 0; k < r; k++) s -= L[r + n * k] * Li[k + n * c];
       Li[r + n * c] = s / L[r + n * r];
     }
+  #pragma unroll 1
   for (int r = 0; r < n; r++)
+    #pragma unroll 1
     for (int c = 0; c < n; c++) {
       double s = 0.0;
+      #pragma unroll 1
       for (int k = 0; k < n; k++) s += Li[k + n * r] * Li[k + n * c];
       Ainv[r + n * c] = s;
     }
@@ -59,8 +71,10 @@ __device__ __forceinline__ void d_inv_spd(const double *A, int n, double *Ainv) 
 template <int DM>
 __device__ __forceinline__ double d_dmvn_log(const double *x, int xstride, const double *mean, const double *L, int n) {
   double z[DM], rootisum = 0.0, zz = 0.0;
+  #pragma unroll 1
   for (int r = 0; r < n; r++) {
     double s = x[(size_t)r * xstride] - mean[r];
+    #pragma unroll 1
     for (int k = 0; k < r; k++) s -= L[r + n * k] * z[k];
     z[r] = s / L[r + n * r];
     zz += z[r] * z[r];
@@ -244,6 +258,7 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
     const int lane = tid - nw;
     // ================= (Theta, Sigma) hierarchy, src/dm_ppmx_ct.cpp:880-902 =================
     if (b.model.upd_hier == 1) {
+      #pragma unroll 1
       for (int t = lane; t < T; t += 32) {
         const int nt = arm_n[t];
         const double dn = (double)nt, nu0 = b.model.hP0_nu0;
@@ -251,59 +266,80 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
         // eta_i = eta*[label_i] (:885): mean and covariance over patients are sums over the K
         // clusters weighted by their sizes (same value, K instead of n_t terms)
         const int K = nclu[t];
+        #pragma unroll 1
         for (int k = 0; k < D; k++) {
           double a = 0.0;
+          #pragma unroll 1
           for (int j = 0; j < K; j++) a += (double)njv[t * ks + j] * eta[((size_t)t * D + k) * ks + j];
           em[k] = a / dn;
         }
+        #pragma unroll 1
         for (int k = 0; k < D; k++)
+          #pragma unroll 1
           for (int r = 0; r < D; r++) {
             double a = 0.0;
+            #pragma unroll 1
             for (int j = 0; j < K; j++)
               a += (double)njv[t * ks + j] * ((eta[((size_t)t * D + k) * ks + j] - em[k]) * (eta[((size_t)t * D + r) * ks + j] - em[r]));
             ecov[k + D * r] = a / dn;
           }
         const double fplp = b.model.hP0_s0 + (dn * .5);
+        #pragma unroll 1
         for (int k = 0; k < D; k++)
+          #pragma unroll 1
           for (int r = 0; r < D; r++)
             S[k + D * r] = ((k == r) ? b.model.hP0_Lambda0 : 0.0) +
                            (dn * .5) * (ecov[k + D * r] + (nu0 / (nu0 + dn)) * ((em[k] - b.model.hP0_mu0[k]) * (em[r] - b.model.hP0_mu0[r])));
         // Lambda ~ Wishart(S, fplp): Bartlett
         double L[DM * DM], A[DM * DM], LA[DM * DM], Lam[DM * DM];
         d_chol_lower<DM>(S, D, L);
+        #pragma unroll 1
         for (int i = 0; i < D * D; i++) A[i] = 0.0;
+        #pragma unroll 1
         for (int k = 0; k < D; k++) {
           A[k + D * k] = sqrt(2.0 * upd_gamma(rng, l, TPPMX_SITE_HIER_W, t, (uint32_t)k, 0.5 * (fplp - (double)k)));
+          #pragma unroll 1
           for (int r = 0; r < k; r++) {
             double n0, n1;
             { const double2 r2_ = upd_n2(rng, l, TPPMX_SITE_HIER_W, t, (uint32_t)(1000 + k * D + r), 0); n0 = r2_.x; n1 = r2_.y; }
             A[k + D * r] = n0;
           }
         }
+        #pragma unroll 1
         for (int k = 0; k < D; k++)
+          #pragma unroll 1
           for (int r = 0; r < D; r++) {
             double a = 0.0;
+            #pragma unroll 1
             for (int i = 0; i < D; i++) a += L[k + D * i] * A[i + D * r];
             LA[k + D * r] = a;
           }
+        #pragma unroll 1
         for (int k = 0; k < D; k++)
+          #pragma unroll 1
           for (int r = 0; r < D; r++) {
             double a = 0.0;
+            #pragma unroll 1
             for (int i = 0; i < D; i++) a += LA[k + D * i] * LA[r + D * i];
             Lam[k + D * r] = a;
           }
         double fptp[DM], tmp[DM * DM], sptp[DM * DM], zn[DM];
+        #pragma unroll 1
         for (int k = 0; k < D; k++) fptp[k] = (b.model.hP0_mu0[k] * nu0 + dn * em[k]) / (nu0 + dn);
+        #pragma unroll 1
         for (int k = 0; k < D * D; k++) tmp[k] = Lam[k] * (dn + nu0);
         d_inv_spd<DM>(tmp, D, sptp);
         d_chol_lower<DM>(sptp, D, L);
         upd_normals(rng, l, TPPMX_SITE_HIER_THETA, t, 0, D, zn);
+        #pragma unroll 1
         for (int k = 0; k < D; k++) {
           double a = fptp[k];
+          #pragma unroll 1
           for (int r = 0; r <= k; r++) a += L[k + D * r] * zn[r];
           Theta[t * D + k] = a;
         }
         d_inv_spd<DM>(Lam, D, tmp);
+        #pragma unroll 1
         for (int k = 0; k < D * D; k++) Sigma[t * D * D + k] = tmp[k];
       }
     }
@@ -314,6 +350,7 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       const int len = Q * D;
       double *lambda = b.lambda + (size_t)chain * len;
       double tau = b.tau[chain];
+      #pragma unroll 1
       for (int k = 0; k < len; k++) {
         double u0, u1;
         { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_HS_LAMBDA, 0, (uint32_t)k, 0); u0 = r2_.x; u1 = r2_.y; }
@@ -328,6 +365,7 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
         lambda[k] = 1.0 / sqrt(et);
       }
       double tempt = 0.0, u0, u1;
+      #pragma unroll 1
       for (int k = 0; k < len; k++) {
         const double r = beta[k] / lambda[k];
         tempt += r * r;
@@ -346,6 +384,7 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       tau = 1.0 / sqrt(et);
       if (tau < .0001) tau = .0001;
       b.tau[chain] = tau;
+      #pragma unroll 1
       for (int k = 0; k < len; k++) sigma_beta[k] = lambda[k] * tau;
     }
     return;
@@ -451,21 +490,35 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
   __threadfence_block();
   bar_arrive2(nth);  // beta is final: the serial warp may run the horseshoe
 
-  // ================= JJ, ss gamma draws, src/dm_ppmx_ct.cpp:1042-1055 =================
-  for (int e = tid; e < nobs * D; e += nw) {
-    const int i = e / D;
-    const double shape = y[e] + upd_exp(lg[e]);
-    double v = upd_gamma(rng, l, TPPMX_SITE_JJ, 0, (uint32_t)e, shape) * (1.0 / (ss[i] + 1.0));
-    if (v < 1e-100) v = 1e-100;
-    JJ[e] = v;
-  }
-  bar_workers(nw);
-  for (int i = tid; i < nobs; i += nw) {
-    double TT = 0.0;
-    for (int k = 0; k < D; k++) TT += JJ[(size_t)i * D + k];
-    ss[i] = upd_gamma(rng, l, TPPMX_SITE_SS, 0, (uint32_t)i, 1.0) * (1.0 / TT);
-  }
   (void)P;
+  (void)y;
+  (void)ss;
+}
+
+// ================= JJ, ss gamma draws, src/dm_ppmx_ct.cpp:1042-1055 =================
+// One thread per (chain, patient), flattened over the whole batch: the draws of a patient only
+// read its own loggamma row and ss, so nothing ties them to the chain's CTA — a separate small
+// kernel keeps the update kernel's instruction footprint down and fills the machine.
+__global__ void __launch_bounds__(128) jjss_kernel(DevBatch b, uint64_t seed, int l) {
+  const size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= (size_t)b.n_chains * b.nobs) return;
+  const int chain = (int)(gi / b.nobs), i = (int)(gi - (size_t)chain * b.nobs);
+  const int ds = b.chain_ds[chain], D = b.D;
+  const Rng rng = make_rng(seed, b.chain_id[chain]);
+  const double *lg = b.lg + ((size_t)chain * b.nobs + i) * D;
+  const double *y = b.y + ((size_t)ds * b.nobs + i) * D;
+  double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
+  double *ss = b.ss + (size_t)chain * b.nobs + i;
+  const double sc = 1.0 / (*ss + 1.0);
+  double TT = 0.0;
+  for (int k = 0; k < D; k++) {
+    const double shape = y[k] + fast_exp(lg[k]);
+    double v = rng_gamma(rng, l, TPPMX_SITE_JJ, 0, (uint32_t)(i * D + k), shape) * sc;
+    if (v < 1e-100) v = 1e-100;
+    JJ[k] = v;
+    TT += v;
+  }
+  *ss = rng_gamma(rng, l, TPPMX_SITE_SS, 0, (uint32_t)i, 1.0) * (1.0 / TT);
 }
 
 }  // namespace tppmx
