@@ -130,10 +130,14 @@ class HostDataset:
         self.xcatp = np.ascontiguousarray(self.xcatp, dtype=np.int32)
 
     def cstruct(self) -> Dataset:
-        d = Dataset()
-        d.treat, d.y, d.z = _ip(self.treat), _dp(self.y), _dp(self.z)
-        d.xcon, d.xcat = _dp(self.xcon), _ip(self.xcat)
-        d.zpred, d.xconp, d.xcatp = _dp(self.zpred), _dp(self.xconp), _ip(self.xcatp)
+        """The C view of this dataset (eight pointers into the arrays above); built once."""
+        d = self.__dict__.get("_cs")
+        if d is None:
+            d = Dataset()
+            d.treat, d.y, d.z = _ip(self.treat), _dp(self.y), _dp(self.z)
+            d.xcon, d.xcat = _dp(self.xcon), _ip(self.xcat)
+            d.zpred, d.xconp, d.xcatp = _dp(self.zpred), _dp(self.xconp), _ip(self.xcatp)
+            self.__dict__["_cs"] = d
         return d
 
 

@@ -1,7 +1,7 @@
 // layout.h — device-side data layout of a batch of chains (private to the library).
 //
 // HBM layout (all arrays chain-major, one contiguous slab per field):
-//   datasets : x, x2 [nd][nobs][P]   z [nd][nobs][Q]   y [nd][nobs][D]   (patient-major rows,
+//   datasets : x [nd][nobs][P]   z [nd][nobs][Q]   y [nd][nobs][D]   (patient-major rows,
 //              read-only, shared by every chain of the dataset -> L2 resident)
 //              arm_pat [nd][T][ntmax] patient index of the it-th patient of arm t
 //   chains   : cluster sufficient statistics in structure-of-arrays form
@@ -35,12 +35,12 @@ struct DevBatch {
   const int *arm_n;     // [nd][T]
   const int *arm_pat;   // [nd][T][ntmax]
   const int *treat;     // [nd][nobs]
-  const double *x, *x2; // [nd][nobs][P]
+  const double *x;       // [nd][nobs][P]  (x^2 is formed on the device with a separately rounded multiply)
   const int *xcat;      // [nd][nobs][ncat]
   const double *z;      // [nd][nobs][Q]
   const double *y;      // [nd][nobs][D]
   const double *zpred;  // [nd][npred][Q]
-  const double *xp, *xp2;  // [nd][npred][P]
+  const double *xp;      // [nd][npred][P]
   const int *xcatp;     // [nd][npred][ncat]
   // chains (n_chains + 1 slots; the last one is the scratch slot of tppmx_score_patient)
   const int *chain_ds;

@@ -18,7 +18,7 @@ struct PredW {  // weight of cluster j for one new patient, plus the raw similar
 };
 
 __device__ inline PredW pred_weight(const DevBatch &b, const SimConst &s, const ArmView &A, int j,
-                                    const double *x, const double *x2, const int *xc_train,
+                                    const double *x, const int *xc_train,
                                     const int *xc_new, double sigma, double dV,
                                     double log_alpha_cc) {
   const bool occ = j < A.K;
@@ -26,7 +26,7 @@ __device__ inline PredW pred_weight(const DevBatch &b, const SimConst &s, const 
   double lgN, lgY;
   // quirk (:1157): an occupied cluster's "with" count uses the TRAINING xcat row indexed by the
   // prediction index; auxiliary clusters use xcatp (:1238).
-  sim_terms(b, s, A.sumx + j, A.sumx2 + j, A.njc + j, A.ks, n, occ, x, x2, occ ? xc_train : xc_new,
+  sim_terms(b, s, A.sumx + j, A.sumx2 + j, A.njc + j, A.ks, n, occ, x, occ ? xc_train : xc_new,
             lgN, lgY);
   PredW r;
   r.gN = occ ? lgN : lgY;
@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
 
   for (int pp = threadIdx.x; pp < npred; pp += blockDim.x) {
     const double *x = b.xp + ((size_t)ds * npred + pp) * b.P;
-    const double *x2 = b.xp2 + ((size_t)ds * npred + pp) * b.P;
     const int *xc_new = b.xcatp + ((size_t)ds * npred + pp) * nc1;
     // quirk 6: training row `pp` (requires pp < nobs when ncat > 0; checked on the host)
     const int *xc_train = b.xcat + ((size_t)ds * b.nobs + (pp < b.nobs ? pp : 0)) * nc1;
@@ -127,7 +126,7 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
     double mN = -INFINITY, sN = 0.0, mY = -INFINITY, sY = 0.0;
     if (cal1) {  // :1282-1307 log-softmax normalisers of gtilN (all) and gtilY (occupied)
       for (int j = 0; j < ntot; j++) {
-        const PredW r = pred_weight(b, s, A, j, x, x2, xc_train, xc_new, sigma, dV, log_alpha_cc);
+        const PredW r = pred_weight(b, s, A, j, x, xc_train, xc_new, sigma, dV, log_alpha_cc);
         double m2 = fmax(mN, r.gN);
         sN = sN * exp(mN - m2) + exp(r.gN - m2);
         mN = m2;
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
     }
     const double lsN = log(sN), lsY = log(sY);
     auto weight_of = [&](int j) {
-      const PredW r = pred_weight(b, s, A, j, x, x2, xc_train, xc_new, sigma, dV, log_alpha_cc);
+      const PredW r = pred_weight(b, s, A, j, x, xc_train, xc_new, sigma, dV, log_alpha_cc);
       if (!cal1) return r.w;
       const double lgtilNk = (r.gN - mN) - lsN;
       return (j < K) ? r.w + ((r.gY - mY) - lsY) - lgtilNk : r.w + lgtilNk;

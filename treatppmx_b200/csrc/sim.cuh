@@ -106,11 +106,11 @@ __device__ inline double gsim_cat(const SimConst &s, const int *cnt, int cstride
 
 // Similarity of one cluster with and without the candidate patient (src/dm_ppmx_ct.cpp:466-553
 // for an occupied cluster, :616-672 for an auxiliary one, which is the "with" term of an empty
-// cluster).  sumx/sumx2 point at column j of the [P][ks] SoA arrays; x/x2/xc are the patient's
+// cluster).  sumx/sumx2 point at column j of the [P][ks] SoA arrays; x/xc are the patient's
 // covariates; xc_add is the categorical row added in the "with" term.
 __device__ inline void sim_terms(const DevBatch &b, const SimConst &s, const double *sumx,
                                  const double *sumx2, const int *njc, int ks, int n, bool occ,
-                                 const double *__restrict__ x, const double *__restrict__ x2,
+                                 const double *__restrict__ x,
                                  const int *__restrict__ xc_add, double &lgN, double &lgY) {
   lgN = 0.0;
   lgY = 0.0;
@@ -122,7 +122,7 @@ __device__ inline void sim_terms(const DevBatch &b, const SimConst &s, const dou
     for (int p = 0; p < P; p++) {
       const double S = occ ? sumx[(size_t)p * ks] : 0.0;
       const double SS = occ ? sumx2[(size_t)p * ks] : 0.0;
-      const double xp = __ldg(x + p), x2p = __ldg(x2 + p);
+      const double xp = __ldg(x + p), x2p = __dmul_rn(xp, xp);
       const double t = fma(S, s.iv2, s.c0);
       const double S2 = S + xp, SS2 = SS + x2p;
       const double t2 = fma(S2, s.iv2, s.c0);
@@ -149,7 +149,7 @@ __device__ inline void sim_terms(const DevBatch &b, const SimConst &s, const dou
     for (int p = 0; p < P; p++) {
       const double S = occ ? sumx[(size_t)p * ks] : 0.0;
       const double SS = occ ? sumx2[(size_t)p * ks] : 0.0;
-      const double xp = __ldg(x + p), x2p = __ldg(x2 + p);
+      const double xp = __ldg(x + p), x2p = __dmul_rn(xp, xp);
       if (occ) lgN += gsim_nnig(s, S, SS, n, s.DD);
       lgY += gsim_nnig(s, S + xp, SS + x2p, n + 1, s.DD);
     }

@@ -30,7 +30,7 @@ struct ArmView {
 };
 
 struct PatientIn {  // read-only inputs of the patient being reallocated
-  const double *x, *x2;  // [P]
+  const double *x;       // [P]
   const int *xc;         // [ncat]
   const double *zb;      // [D]
   const double *ljj;     // [D]
@@ -70,7 +70,7 @@ __device__ inline void remove_patient(const DevBatch &b, const SimConst &s, ArmV
     if (s.PPMx) {
       for (int p = lane; p < s.P; p += 32) {
         A.sumx[(size_t)p * ks + zi] = __dsub_rn(A.sumx[(size_t)p * ks + zi], pt.x[p]);
-        A.sumx2[(size_t)p * ks + zi] = __dsub_rn(A.sumx2[(size_t)p * ks + zi], pt.x2[p]);
+        A.sumx2[(size_t)p * ks + zi] = __dsub_rn(A.sumx2[(size_t)p * ks + zi], __dmul_rn(pt.x[p], pt.x[p]));
       }
       for (int p = lane; p < s.ncat; p += 32) A.njc[((size_t)p * b.maxC + pt.xc[p]) * ks + zi] -= 1;
     }
@@ -114,7 +114,7 @@ __device__ inline void remove_patient(const DevBatch &b, const SimConst &s, ArmV
     if (s.PPMx) {
       for (int p = lane; p < s.P; p += 32) {
         A.sumx[(size_t)p * ks + K - 1] = __dsub_rn(A.sumx[(size_t)p * ks + K - 1], pt.x[p]);
-        A.sumx2[(size_t)p * ks + K - 1] = __dsub_rn(A.sumx2[(size_t)p * ks + K - 1], pt.x2[p]);
+        A.sumx2[(size_t)p * ks + K - 1] = __dsub_rn(A.sumx2[(size_t)p * ks + K - 1], __dmul_rn(pt.x[p], pt.x[p]));
       }
       for (int p = lane; p < s.ncat; p += 32) A.njc[((size_t)p * b.maxC + pt.xc[p]) * ks + K - 1] -= 1;
     }
@@ -151,7 +151,7 @@ __device__ inline ScoreOut score_clusters(const DevBatch &b, const SimConst &s, 
     double w = -INFINITY, lgN = 0.0, lgY = 0.0;
     if (act) {
       const int n = occ ? A.nj[j] : 0;
-      sim_terms(b, s, A.sumx + j, A.sumx2 + j, A.njc + j, ks, n, occ, pt.x, pt.x2,
+      sim_terms(b, s, A.sumx + j, A.sumx2 + j, A.njc + j, ks, n, occ, pt.x,
                 occ ? xc_occ : pt.xc, lgN, lgY);
       w = cohesion_term(s, occ, n, sigma, dV, log_alpha_cc);
       if (!cal1) {
@@ -312,7 +312,7 @@ __device__ inline bool realloc_step(const DevBatch &b, const SimConst &s, ArmVie
   if (s.PPMx) {  // :847-856
     for (int p = lane; p < s.P; p += 32) {
       A.sumx[(size_t)p * ks + lab - 1] = __dadd_rn(A.sumx[(size_t)p * ks + lab - 1], pt.x[p]);
-      A.sumx2[(size_t)p * ks + lab - 1] = __dadd_rn(A.sumx2[(size_t)p * ks + lab - 1], pt.x2[p]);
+      A.sumx2[(size_t)p * ks + lab - 1] = __dadd_rn(A.sumx2[(size_t)p * ks + lab - 1], __dmul_rn(pt.x[p], pt.x[p]));
     }
     for (int p = lane; p < s.ncat; p += 32) A.njc[((size_t)p * b.maxC + pt.xc[p]) * ks + lab - 1] += 1;
   }
@@ -323,7 +323,6 @@ __device__ inline bool realloc_step(const DevBatch &b, const SimConst &s, ArmVie
 __device__ __forceinline__ PatientIn patient_in(const DevBatch &b, int chain, int ds, int i) {
   PatientIn pt;
   pt.x = b.x + ((size_t)ds * b.nobs + i) * b.P;
-  pt.x2 = b.x2 + ((size_t)ds * b.nobs + i) * b.P;
   pt.xc = b.xcat + ((size_t)ds * b.nobs + i) * (b.ncat > 0 ? b.ncat : 1);
   pt.zb = b.zb + ((size_t)chain * b.nobs + i) * b.D;
   pt.ljj = b.ljj + ((size_t)chain * b.nobs + i) * b.D;

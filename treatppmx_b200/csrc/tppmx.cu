@@ -179,6 +179,25 @@ static int dev_upload(tppmx_batch *b, const T **p, const std::vector<T> &h) {
   b->up_used += bytes;
   return TPPMX_OK;
 }
+// upload region, written in place: returns the host pointer inside the pinned mirror (nullptr in
+// the sizing pass) and sets the device pointer
+template <class T>
+static T *dev_stage(tppmx_batch *b, const T **p, size_t n, int *rc) {
+  const size_t bytes = al256((n ? n : 1) * sizeof(T));
+  if (b->dry) {
+    b->up_need += bytes;
+    *p = nullptr;
+    return nullptr;
+  }
+  if (b->up_used + bytes > b->up_need) {
+    *rc = TPPMX_ERR_NOMEM;
+    return nullptr;
+  }
+  T *h = (T *)(b->ar.hbase + b->up_used);
+  *p = (const T *)(b->ar.dbase + b->up_used);
+  b->up_used += bytes;
+  return h;
+}
 static bool fast_eligible(const tppmx_batch *b, int lpu);
 static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc);
 // one thread per new patient of an (chain, arm) block: no more threads than patients
@@ -291,71 +310,68 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
     std::vector<NNRow> tab = build_nn_tab(*model, d.ntmax);
     TRY(dev_upload(b, &d.nn_tab, tab));
 
-    // datasets
-    std::vector<int> arm_n((size_t)n_datasets * T, 0), arm_pat((size_t)n_datasets * T * d.ntmax, 0);
-    std::vector<int> treat((size_t)n_datasets * nobs), xcat((size_t)n_datasets * nobs * nc1, 0);
-    std::vector<double> x((size_t)n_datasets * nobs * P), x2(x.size()), z((size_t)n_datasets * nobs * Q);
-    std::vector<double> y((size_t)n_datasets * nobs * D);
-    std::vector<double> zp((size_t)n_datasets * npred * Q), xp((size_t)n_datasets * npred * P), xp2(xp.size());
-    std::vector<int> xcp((size_t)n_datasets * npred * nc1, 0);
-    for (int ds = 0; ds < n_datasets && !b->dry; ds++) {
-      const tppmx_dataset &s = datasets[ds];
-      if (!s.treat || !s.y || (Q > 0 && !s.z) || (P > 0 && !s.xcon) || (ncat > 0 && !s.xcat)) {
-        rc = fail(ctx, TPPMX_ERR_ARG, "dataset has null arrays");
-        goto bad;
-      }
-      for (int i = 0; i < nobs; i++) {
-        const int t = s.treat[i];
-        if (t < 0 || t >= T) { rc = fail(ctx, TPPMX_ERR_ARG, "treat out of range"); goto bad; }
-        int &na = arm_n[(size_t)ds * T + t];
-        if (na >= d.ntmax) { rc = fail(ctx, TPPMX_ERR_ARG, "an arm has more than ntmax patients"); goto bad; }
-        arm_pat[((size_t)ds * T + t) * d.ntmax + na] = i;
-        na++;
-        treat[(size_t)ds * nobs + i] = t;
-        for (int p = 0; p < P; p++) {
-          const double v = s.xcon[(size_t)i * P + p];
-          x[((size_t)ds * nobs + i) * P + p] = v;
-          x2[((size_t)ds * nobs + i) * P + p] = v * v;
-        }
-        for (int p = 0; p < ncat; p++) {
-          const int cv = s.xcat[(size_t)i * ncat + p];
-          if (cv < 0 || cv >= d.maxC) { rc = fail(ctx, TPPMX_ERR_ARG, "xcat out of range"); goto bad; }
-          xcat[((size_t)ds * nobs + i) * nc1 + p] = cv;
-        }
-        for (int q = 0; q < Q; q++) z[((size_t)ds * nobs + i) * Q + q] = s.z[i + (size_t)nobs * q];
-        for (int k = 0; k < D; k++) y[((size_t)ds * nobs + i) * D + k] = s.y[i + (size_t)nobs * k];
-      }
-      if (npred > 0 && ((Q > 0 && !s.zpred) || (P > 0 && !s.xconp) || (ncat > 0 && !s.xcatp))) {
-        rc = fail(ctx, TPPMX_ERR_ARG, "npred>0 but prediction arrays are null");
-        goto bad;
-      }
-      for (int pp = 0; pp < npred; pp++) {
-        for (int q = 0; q < Q; q++) zp[((size_t)ds * npred + pp) * Q + q] = s.zpred[pp + (size_t)npred * q];
-        for (int p = 0; p < P; p++) {
-          const double v = s.xconp[(size_t)pp * P + p];
-          xp[((size_t)ds * npred + pp) * P + p] = v;
-          xp2[((size_t)ds * npred + pp) * P + p] = v * v;
-        }
-        for (int p = 0; p < ncat; p++) {
-          const int cv = s.xcatp[(size_t)pp * ncat + p];
-          if (cv < 0 || cv >= d.maxC) { rc = fail(ctx, TPPMX_ERR_ARG, "xcatp out of range"); goto bad; }
-          xcp[((size_t)ds * npred + pp) * nc1 + p] = cv;
+    // datasets: packed straight into the pinned mirror (patient-major rows); the covariate rows
+    // xcon / xconp already have that layout and are block-copied
+    {
+      int src = TPPMX_OK;
+      int *h_arm_n = dev_stage(b, &d.arm_n, (size_t)n_datasets * T, &src);
+      int *h_arm_pat = dev_stage(b, &d.arm_pat, (size_t)n_datasets * T * d.ntmax, &src);
+      int *h_treat = dev_stage(b, &d.treat, (size_t)n_datasets * nobs, &src);
+      double *h_x = dev_stage(b, &d.x, (size_t)n_datasets * nobs * P, &src);
+      int *h_xcat = dev_stage(b, &d.xcat, (size_t)n_datasets * nobs * nc1, &src);
+      double *h_z = dev_stage(b, &d.z, (size_t)n_datasets * nobs * Q, &src);
+      double *h_y = dev_stage(b, &d.y, (size_t)n_datasets * nobs * D, &src);
+      double *h_zp = dev_stage(b, &d.zpred, (size_t)n_datasets * npred * Q, &src);
+      double *h_xp = dev_stage(b, &d.xp, (size_t)n_datasets * npred * P, &src);
+      int *h_xcp = dev_stage(b, &d.xcatp, (size_t)n_datasets * npred * nc1, &src);
+      if (src) { rc = src; goto bad; }
+      if (!b->dry) {
+        memset(h_arm_n, 0, sizeof(int) * (size_t)n_datasets * T);
+        memset(h_arm_pat, 0, sizeof(int) * (size_t)n_datasets * T * d.ntmax);
+        if (ncat == 0) {
+          memset(h_xcat, 0, sizeof(int) * (size_t)n_datasets * nobs * nc1);
+          memset(h_xcp, 0, sizeof(int) * (size_t)n_datasets * (npred > 0 ? npred : 0) * nc1);
         }
       }
+      for (int ds = 0; ds < n_datasets && !b->dry; ds++) {
+        const tppmx_dataset &s = datasets[ds];
+        if (!s.treat || !s.y || (Q > 0 && !s.z) || (P > 0 && !s.xcon) || (ncat > 0 && !s.xcat)) {
+          rc = fail(ctx, TPPMX_ERR_ARG, "dataset has null arrays");
+          goto bad;
+        }
+        if (P > 0) memcpy(h_x + (size_t)ds * nobs * P, s.xcon, sizeof(double) * (size_t)nobs * P);
+        int *an = h_arm_n + (size_t)ds * T;
+        for (int i = 0; i < nobs; i++) {
+          const int t = s.treat[i];
+          if (t < 0 || t >= T) { rc = fail(ctx, TPPMX_ERR_ARG, "treat out of range"); goto bad; }
+          if (an[t] >= d.ntmax) { rc = fail(ctx, TPPMX_ERR_ARG, "an arm has more than ntmax patients"); goto bad; }
+          h_arm_pat[((size_t)ds * T + t) * d.ntmax + an[t]] = i;
+          an[t]++;
+          h_treat[(size_t)ds * nobs + i] = t;
+          for (int p = 0; p < ncat; p++) {
+            const int cv = s.xcat[(size_t)i * ncat + p];
+            if (cv < 0 || cv >= d.maxC) { rc = fail(ctx, TPPMX_ERR_ARG, "xcat out of range"); goto bad; }
+            h_xcat[((size_t)ds * nobs + i) * nc1 + p] = cv;
+          }
+          for (int q = 0; q < Q; q++) h_z[((size_t)ds * nobs + i) * Q + q] = s.z[i + (size_t)nobs * q];
+          for (int k = 0; k < D; k++) h_y[((size_t)ds * nobs + i) * D + k] = s.y[i + (size_t)nobs * k];
+        }
+        if (npred > 0 && ((Q > 0 && !s.zpred) || (P > 0 && !s.xconp) || (ncat > 0 && !s.xcatp))) {
+          rc = fail(ctx, TPPMX_ERR_ARG, "npred>0 but prediction arrays are null");
+          goto bad;
+        }
+        if (npred > 0 && P > 0) memcpy(h_xp + (size_t)ds * npred * P, s.xconp, sizeof(double) * (size_t)npred * P);
+        for (int pp = 0; pp < npred; pp++) {
+          for (int q = 0; q < Q; q++) h_zp[((size_t)ds * npred + pp) * Q + q] = s.zpred[pp + (size_t)npred * q];
+          for (int p = 0; p < ncat; p++) {
+            const int cv = s.xcatp[(size_t)pp * ncat + p];
+            if (cv < 0 || cv >= d.maxC) { rc = fail(ctx, TPPMX_ERR_ARG, "xcatp out of range"); goto bad; }
+            h_xcp[((size_t)ds * npred + pp) * nc1 + p] = cv;
+          }
+        }
+      }
+      if (!b->dry) b->arm_n.assign(h_arm_n, h_arm_n + (size_t)n_datasets * T);
     }
-    b->arm_n = arm_n;
-    TRY(dev_upload(b, &d.arm_n, arm_n));
-    TRY(dev_upload(b, &d.arm_pat, arm_pat));
-    TRY(dev_upload(b, &d.treat, treat));
-    TRY(dev_upload(b, &d.x, x));
-    TRY(dev_upload(b, &d.x2, x2));
-    TRY(dev_upload(b, &d.xcat, xcat));
-    TRY(dev_upload(b, &d.z, z));
-    TRY(dev_upload(b, &d.y, y));
-    TRY(dev_upload(b, &d.zpred, zp));
-    TRY(dev_upload(b, &d.xp, xp));
-    TRY(dev_upload(b, &d.xp2, xp2));
-    TRY(dev_upload(b, &d.xcatp, xcp));
 
     // chains
     const size_t ns = (size_t)n_chains + 1;
@@ -541,7 +557,10 @@ __global__ void init_kernel(DevBatch b, uint64_t seed, const int *init_labels, c
         if (labels[t * b.ntmax + it] == j + 1) {
           const int i = b.arm_pat[((size_t)ds * T + t) * b.ntmax + it];
           s1 = __dadd_rn(s1, b.x[((size_t)ds * nobs + i) * P + p]);
-          s2 = __dadd_rn(s2, b.x2[((size_t)ds * nobs + i) * P + p]);
+          {
+            const double xv = b.x[((size_t)ds * nobs + i) * P + p];
+            s2 = __dadd_rn(s2, __dmul_rn(xv, xv));
+          }
         }
     }
     b.sumx[(size_t)chain * st_sumx(b) + e] = s1;
