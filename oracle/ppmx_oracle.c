@@ -220,6 +220,16 @@ static double o_logV(const o_ctx *c, int t, int r, int K, int g) {
   return c->pb->shared.logV[(((size_t)t * 2 + r) * c->ntmax + (K - 1)) * c->G + g];
 }
 
+/* log V(n_t, K) - log V(n_t - 1, K) at grid index g (:563, :680).  K = 0 can only happen while
+ * the single patient of a one-patient arm is out of its cluster; the reference would index
+ * Vwm(., -1, .) there (an Armadillo bounds error), so the case is undefined upstream.  The term is
+ * common to all candidate clusters and cancels in the normalisation: it is taken as 0, as on the
+ * device. */
+static double o_dV(const o_ctx *c, int t, int K, int g) {
+  if (K < 1) return 0.0;
+  return o_logV(c, t, 1, K, g) - o_logV(c, t, 0, K, g);
+}
+
 /* the DM-augmented likelihood piece, :570-576 */
 static double o_lik(const o_ctx *c, double w, const double *eta_col, int i) {
   if (c->pb->model.nolik) return w; /* prior_ppmx_core: no likelihood term */
@@ -351,7 +361,7 @@ static void o_realloc_patient(o_ctx *c, int tt, int it, int i, int l, int score_
     /* cohesion (:559-565 == :581-587) */
     if (cohesion == 1) weight[j] = log((double)NJ(tt, j));
     if (cohesion == 2) {
-      weight[j] = o_logV(c, tt, 1, nclu_curr[tt], idxs) - o_logV(c, tt, 0, nclu_curr[tt], idxs);
+      weight[j] = o_dV(c, tt, nclu_curr[tt], idxs);
       weight[j] += lgamma(NJ(tt, j) + 1 - c->s->sigma[tt]) - lgamma(NJ(tt, j) - c->s->sigma[tt]);
     }
     if ((PPMx == 0) | ((calibration != 2) & (PPMx == 1))) {
@@ -391,7 +401,7 @@ static void o_realloc_patient(o_ctx *c, int tt, int it, int i, int l, int score_
     }
     if (cohesion == 1) weight[j] = log(m->alpha) - log((double)CC);
     if (cohesion == 2)
-      weight[j] = o_logV(c, tt, 1, nclu_curr[tt], idxs) - o_logV(c, tt, 0, nclu_curr[tt], idxs);
+      weight[j] = o_dV(c, tt, nclu_curr[tt], idxs);
     if ((PPMx == 0) | ((calibration != 2) & (PPMx == 1))) weight[j] += lgcondraw + lgcatdraw;
     if ((calibration == 2) & (PPMx == 1)) {
       if (coardegree == 1) weight[j] += (1 / ((double)ncon + (double)ncat)) * (lgcondraw + lgcatdraw);
@@ -423,7 +433,7 @@ static void o_realloc_patient(o_ctx *c, int tt, int it, int i, int l, int score_
       lgtilYk = lgtilY[j] - log(sgY);
       if (cohesion == 1) weight[j] = log((double)NJ(tt, j));
       if (cohesion == 2) {
-        weight[j] = o_logV(c, tt, 1, nclu_curr[tt], idxs) - o_logV(c, tt, 0, nclu_curr[tt], idxs);
+        weight[j] = o_dV(c, tt, nclu_curr[tt], idxs);
         weight[j] += lgamma(NJ(tt, j) + 1 - c->s->sigma[tt]) - lgamma(NJ(tt, j) - c->s->sigma[tt]);
       }
       weight[j] += lgtilYk - lgtilNk;
@@ -434,7 +444,7 @@ static void o_realloc_patient(o_ctx *c, int tt, int it, int i, int l, int score_
       lgtilNk = lgtilN[j] - log(sgN);
       if (cohesion == 1) weight[j] = log(m->alpha) - log((double)CC);
       if (cohesion == 2)
-        weight[j] = o_logV(c, tt, 1, nclu_curr[tt], idxs) - o_logV(c, tt, 0, nclu_curr[tt], idxs);
+        weight[j] = o_dV(c, tt, nclu_curr[tt], idxs);
       weight[j] += lgtilNk;
       weight[j] = o_lik(c, weight[j], &ETAE(0, jj, tt), i);
     }
@@ -769,7 +779,7 @@ int oracle_predict(const oracle_problem *pb, const tppmx_state *s_in, uint64_t s
         }
         if (cohesion == 1) weight[j] = log((double)NJ(tt, j));
         if (cohesion == 2) {
-          weight[j] = o_logV(c, tt, 1, nclu_curr[tt], idxs) - o_logV(c, tt, 0, nclu_curr[tt], idxs);
+          weight[j] = o_dV(c, tt, nclu_curr[tt], idxs);
           weight[j] += lgamma(NJ(tt, j) + 1 - s_in->sigma[tt]) - lgamma(NJ(tt, j) - s_in->sigma[tt]);
         }
         if ((PPMx == 0) | ((calibration != 2) & (PPMx == 1))) weight[j] += lgcatY - lgcatN + lgconY - lgconN;
@@ -798,7 +808,7 @@ int oracle_predict(const oracle_problem *pb, const tppmx_state *s_in, uint64_t s
         }
         if (cohesion == 1) weight[j] = log(m->alpha) - log((double)CC);
         if (cohesion == 2)
-          weight[j] = o_logV(c, tt, 1, nclu_curr[tt], idxs) - o_logV(c, tt, 0, nclu_curr[tt], idxs);
+          weight[j] = o_dV(c, tt, nclu_curr[tt], idxs);
         if ((PPMx == 0) | ((calibration != 2) & (PPMx == 1))) weight[j] += lgcondraw + lgcatdraw;
         if ((calibration == 2) & (PPMx == 1)) {
           if (coardegree == 1) weight[j] += (1 / ((double)ncon + (double)ncat)) * (lgcondraw + lgcatdraw);
@@ -825,7 +835,7 @@ int oracle_predict(const oracle_problem *pb, const tppmx_state *s_in, uint64_t s
           double lgtilNk = lgtilN[j] - log(sgN), lgtilYk = lgtilY[j] - log(sgY);
           if (cohesion == 1) weight[j] = log((double)NJ(tt, j));
           if (cohesion == 2) {
-            weight[j] = o_logV(c, tt, 1, nclu_curr[tt], idxs) - o_logV(c, tt, 0, nclu_curr[tt], idxs);
+            weight[j] = o_dV(c, tt, nclu_curr[tt], idxs);
             weight[j] += lgamma(NJ(tt, j) + 1 - s_in->sigma[tt]) - lgamma(NJ(tt, j) - s_in->sigma[tt]);
           }
           weight[j] += lgtilYk - lgtilNk;
@@ -834,7 +844,7 @@ int oracle_predict(const oracle_problem *pb, const tppmx_state *s_in, uint64_t s
           double lgtilNk = lgtilN[j] - log(sgN);
           if (cohesion == 1) weight[j] = log(m->alpha) - log((double)CC);
           if (cohesion == 2)
-            weight[j] = o_logV(c, tt, 1, nclu_curr[tt], idxs) - o_logV(c, tt, 0, nclu_curr[tt], idxs);
+            weight[j] = o_dV(c, tt, nclu_curr[tt], idxs);
           weight[j] += lgtilNk;
         }
       }
