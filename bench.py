@@ -448,7 +448,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s_max * 1e3},
             "gpu_launches": launches,
             "sweep_kernel": {"impl": batch.last_sweep_info()[0], "handovers_last_step": batch.last_sweep_info()[1],
-                             "lanes_per_unit": args.lpu or 16},
+                             "lanes_per_unit": args.lpu or "auto (16; 32 for long arms)"},
             "wall_s_timed_region": t_wall,
             "clocks": clocks,
             "by_rank": by_rank,

@@ -48,28 +48,36 @@ struct FastArgs {
   int *bail_count; // [1]
   int KS, ntp, ncol, n_units;
   int unit_bytes, tab_bytes;
+  // big arms (BASELINE config 4: n_t in the thousands): everything indexed by patient position or
+  // by cluster size would not fit in shared memory, so it lives in global memory (L2-resident):
+  int big;          // 1: the three tables over n and labels / patient order / cohesion table are global
+  double *tabg;     // [3][ntmax + 2]  dA, HN, HY (filled once at batch creation)
+  double *logng;    // [units][ntp + 1]
+  int *patpad;      // [units][ntp + 1] patient order of the unit, zero-padded
 };
 
 __host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }
 // bytes of shared memory of one unit
-__host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D) {
-  size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (ntp + 1) + 2 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
-  size_t in = (size_t)KS + 2 * (KS + CC) + 2 * (ntp + 1) + 1;
+__host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D, int big) {
+  size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (big ? 0 : (ntp + 1)) + 2 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
+  size_t in = (size_t)KS + 2 * (KS + CC) + (big ? 0 : 2 * (ntp + 1)) + 1;
   return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t fast_tab_bytes(int ntmax) { return (((size_t)3 * (ntmax + 2) * 8) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t fast_tab_bytes(int ntmax, int big) {
+  return big ? 16 : ((((size_t)3 * (ntmax + 2) * 8) + 15) & ~(size_t)15);
+}
 
 struct UnitSmem {
   double *sumx, *sumx2, *logn, *xs, *wsc, *E;
   int *nj, *col, *freec, *lab, *pat;
 };
 
-__device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int ntp, int CC, int D) {
+__device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int ntp, int CC, int D, int big) {
   UnitSmem U;
   double *d = reinterpret_cast<double *>(base);
   U.sumx = d; d += (size_t)P * TPPMX_FAST_KSTR;
   U.sumx2 = d; d += (size_t)P * TPPMX_FAST_KSTR;
-  U.logn = d; d += ntp + 1;
+  U.logn = d; d += big ? 0 : ntp + 1;
   U.xs = d; d += 2 * fast_pp(P);
   U.wsc = d; d += KS + CC;
   U.E = d; d += (size_t)(KS + CC) * D;
@@ -77,9 +85,9 @@ __device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int nt
   U.nj = q; q += KS;
   U.col = q; q += KS + CC;
   U.freec = q; q += KS + CC;
-  U.lab = q; q += ntp + 1;
+  U.lab = q; q += big ? 0 : ntp + 1;
   U.pat = q;  // ntp + 1 entries (the prefetch of step it+1 may read one past the arm)
-  return U;
+  return U;   // big: logn / lab / pat are re-pointed at global memory by the kernel
 }
 
 constexpr unsigned TPPMX_FULL = 0xffffffffu;
@@ -233,10 +241,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const SimConst s = make_simconst(b);
 
   // ---- per-CTA tables over n (Normal-Normal log terms, utils_ct.cpp:389-400 via sim.cuh NNRow)
-  double *t_dA = reinterpret_cast<double *>(smem_raw);
+  const int big = fa.big;
+  double *t_dA = big ? fa.tabg : reinterpret_cast<double *>(smem_raw);
   double *t_HN = t_dA + (b.ntmax + 2);
   double *t_HY = t_HN + (b.ntmax + 2);
-  for (int n = lane; n <= b.ntmax; n += 32) {
+  for (int n = lane; n <= b.ntmax && !big; n += 32) {
     const NNRow r0 = b.nn_tab[n], r1 = b.nn_tab[n + 1];
     const double dP = (double)P;
     t_dA[n] = (n == 0) ? dP * r1.A0 : dP * (r1.A0 - r0.A0);
@@ -249,7 +258,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const int nt = valid ? b.arm_n[(size_t)ds * b.T + tt] : 0;
   const int nt_w = warp_max_over_units<LPU>(nt);
   const Rng rng = make_rng(seed, b.chain_id[chain]);
-  const UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC, D);
+  UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC, D, big);
 
   // global state of this unit
   double *g_sumx = b.sumx + ((size_t)chain * b.T + tt) * P * kcap;
@@ -280,9 +289,18 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     U.sumx2[e] = (j < KS) ? g_sumx2[(size_t)p * kcap + j] : 0.0;
   }
   for (int j = ul; j < KS; j += LPU) U.nj[j] = g_nj[j];
-  for (int it = ul; it <= ntp; it += LPU) {
-    U.lab[it] = (it < nt) ? g_lab[it] : 1;
-    U.pat[it] = (it < nt) ? g_pat[it] : 0;
+  if (big) {  // labels are updated in place in the batch's global array (ntmax entries, enough for
+              // every index the loop touches: lab[it] is only read for it < nt)
+    U.lab = g_lab;
+    U.pat = fa.patpad + (size_t)unit * (ntp + 1);
+    U.logn = fa.logng + (size_t)unit * (ntp + 1);
+    if (valid)
+      for (int it = ul; it <= ntp; it += LPU) U.pat[it] = (it < nt) ? g_pat[it] : 0;
+  } else {
+    for (int it = ul; it <= ntp; it += LPU) {
+      U.lab[it] = (it < nt) ? g_lab[it] : 1;
+      U.pat[it] = (it < nt) ? g_pat[it] : 0;
+    }
   }
   // column indirection: clusters 0..K-1 -> cols 0..K-1, aux m -> col K+m, the rest is free
   int nfree = 0;
@@ -606,7 +624,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       }
     }
     for (int j = ul; j < KS; j += LPU) g_nj[j] = U.nj[j];
-    for (int it = ul; it < nt; it += LPU) g_lab[it] = U.lab[it];
+    if (!big)
+      for (int it = ul; it < nt; it += LPU) g_lab[it] = U.lab[it];
     if (ul == 0) {
       b.nclu[(size_t)chain * b.T + tt] = K;
       fa.resume_l[unit] = bail_l;

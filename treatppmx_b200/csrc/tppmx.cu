@@ -883,6 +883,21 @@ static int fast_reserve(tppmx_batch *b) {
   RC(dev_alloc(b, &fa.resume_l, units));
   RC(dev_alloc(b, &fa.resume_it, units));
   RC(dev_alloc(b, &fa.bail_count, 1));
+  RC(dev_alloc(b, &fa.logng, units * (ntp + 1)));
+  RC(dev_alloc(b, &fa.patpad, units * (ntp + 1)));
+  {  // the three tables over n of sweep_fast.cuh, for arms too long to keep them in shared memory
+    std::vector<NNRow> tab = build_nn_tab(d.model, d.ntmax);
+    std::vector<double> tg((size_t)3 * (d.ntmax + 2), 0.0);
+    const double dP = (double)d.P;
+    for (int n = 0; n <= d.ntmax; n++) {
+      tg[n] = (n == 0) ? dP * tab[1].A0 : dP * (tab[n + 1].A0 - tab[n].A0);
+      tg[(size_t)(d.ntmax + 2) + n] = (n == 0) ? 0.0 : tab[n].H;
+      tg[(size_t)2 * (d.ntmax + 2) + n] = tab[n + 1].H;
+    }
+    const double *tp = nullptr;
+    RC(dev_upload(b, &tp, tg));
+    fa.tabg = const_cast<double *>(tp);
+  }
   return TPPMX_OK;
 }
 
@@ -896,8 +911,10 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     fa.ntp = (d.ntmax + 3) & ~3;
     fa.ncol = fa.KS + d.CC;
     fa.n_units = d.n_chains * d.T;
-    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D);
-    fa.tab_bytes = (int)fast_tab_bytes(d.ntmax);
+    // arms too long for shared-memory label / order / cohesion tables run in "big" mode
+    fa.big = (fast_tab_bytes(d.ntmax, 0) + 2 * fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D, 0) > 48 * 1024) ? 1 : 0;
+    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D, fa.big);
+    fa.tab_bytes = (int)fast_tab_bytes(d.ntmax, fa.big);
     b->fast_ready = true;
   }
   *smem_out = (size_t)fa.tab_bytes + (size_t)(32 / lpu) * fa.unit_bytes;
@@ -936,7 +953,15 @@ static cudaError_t fast_launch(tppmx_batch *b, size_t smem, uint64_t seed, int i
 // nothing to resume), so a whole run needs no host round trip.
 static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps, bool sync_handover, int *launches) {
   tppmx_ctx *ctx = b->ctx;
-  const int lpu = b->opt_lpu ? b->opt_lpu : 16;
+  // lanes per (chain, arm): 16 (two units per warp) for the package's shapes, where an arm holds
+  // ~4-10 clusters; long arms (config 4) hold tens of clusters -> one unit per warp
+  int lpu = b->opt_lpu;
+  if (!lpu) {
+    const DevBatch &dd = b->d;
+    const size_t ks = dd.kcap < TPPMX_FAST_KSMAX ? dd.kcap : TPPMX_FAST_KSMAX, ntp = (dd.ntmax + 3) & ~3;
+    const bool big = fast_tab_bytes(dd.ntmax, 0) + 2 * fast_unit_bytes(dd.P, (int)ks, (int)ntp, dd.CC, dd.D, 0) > 48 * 1024;
+    lpu = big ? 32 : 16;
+  }
   size_t smem = 0;
   bool use_fast = b->opt_impl != 1 && fast_eligible(b, lpu) && b->fa.lik;
   if (use_fast) {
