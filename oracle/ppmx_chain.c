@@ -164,7 +164,7 @@ static void o_hierarchy(o_ctx *c, int tt, int l) {
   const tppmx_model *m = &c->pb->model;
   const int dim = c->D, nt = c->num_treat[tt];
   const double nu0_theta = m->hP0_nu0, s0_lambda = m->hP0_s0;
-  double etamean[TPPMX_MAXD], etacov[TPPMX_MAXD * TPPMX_MAXD], splp[TPPMX_MAXD * TPPMX_MAXD];
+  double etamean[TPPMX_MAXD], etacov[TPPMX_MAXD * TPPMX_MAXD], splp[TPPMX_MAXD * TPPMX_MAXD] = {0};
   double Lambda[TPPMX_MAXD * TPPMX_MAXD], tmp[TPPMX_MAXD * TPPMX_MAXD], sptp[TPPMX_MAXD * TPPMX_MAXD];
   double fptp[TPPMX_MAXD];
   int i, k, r;
