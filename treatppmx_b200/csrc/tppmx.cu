@@ -1020,7 +1020,7 @@ static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launc
   if (d.model.cohesion == 2 && d.ncat > 0)
     return fail(ctx, TPPMX_ERR_ARG, "the (sigma,kappa) update needs ncat == 0 (as the reference, dm_ppmx_ct.cpp:942)");
   const int nth = 128;  // 3 worker warps + 1 serial warp (update.cuh)
-  const size_t smem = sizeof(double) * (64 + (size_t)d.T * d.D * d.D + 16);
+  const size_t smem = sizeof(double) * (64 + (size_t)d.T * d.D * d.D + 16 + 2 * TPPMX_MAXD * TPPMX_MAXQ);
   if (d.D == 3)
     update_kernel<3><<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
   else

@@ -407,21 +407,26 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       os[e] = v;
     }
     bar_workers(nw);
+    double *mxs = red + 16;  // [T] maxima (red[0..15] is the reduction scratch)
     for (int t = tid; t < T; t += nw) {
       double mx = os[t * G];
       for (int g = 1; g < G; g++) mx = fmax(mx, os[t * G + g]);
+      mxs[t] = mx;
+    }
+    bar_workers(nw);
+    for (int e = tid; e < T * G; e += nw) os[e] = upd_exp(os[e] - mxs[e / G]);
+    bar_workers(nw);
+    for (int t = tid; t < T; t += nw) {
       double den = 0.0;
-      for (int g = 0; g < G; g++) {
-        const double e = upd_exp(os[t * G + g] - mx);
-        os[t * G + g] = e;
-        den += e;
-      }
+      for (int g = 0; g < G; g++) den += os[t * G + g];
       double u0, u1, cw = 0.0;
       { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_SIGKAP, t, 0, 0); u0 = r2_.x; u1 = r2_.y; }
+      (void)u1;
       int pk = G - 1;
+      const double thr = u0 * den;  // u0 < cumsum(e)/den  <=>  u0*den < cumsum(e)
       for (int g = 0; g < G; g++) {
-        cw += os[t * G + g] / den;
-        if (u0 < cw) {
+        cw += os[t * G + g];
+        if (thr < cw) {
           pk = g;
           break;
         }
@@ -439,6 +444,14 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
   if (b.model.noprog != 1) {
     const double *sigma_beta = b.sigma_beta + (size_t)chain * Q * D;
     double *ljs = cur, *cu = prop, *pr = prop + (size_t)T * ntm;  // >= nobs entries each
+    // the proposal normal and the acceptance uniform of every (k, q) step, drawn up front by
+    // Q*D threads in parallel (they do not depend on the chain's evolving state)
+    double *bn = Lsig + T * D * D + 16, *bu = bn + TPPMX_MAXD * TPPMX_MAXQ;
+    for (int e = tid; e < Q * D; e += nw) {
+      bn[e] = upd_n2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)e, 0).x;
+      bu[e] = upd_log(upd_u2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)e, 1).x);
+    }
+    bar_workers(nw);
     for (int kk = 0; kk < D; kk++) {
       double sd = 0.0, dummy = 0.0;
       for (int i = tid; i < nobs; i += nw) {
@@ -453,9 +466,7 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       for (int q = 0; q < Q; q++) {
         const int h = kk + q * D;
         const double bh = beta[h];
-        double n0, n1;
-        { const double2 r2_ = upd_n2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)(kk * Q + q), 0); n0 = r2_.x; n1 = r2_.y; }
-        const double beta_p = bh + mh_beta * n0;
+        const double beta_p = bh + mh_beta * bn[kk * Q + q];
         double sn = 0.0;
         dummy = 0.0;
         for (int i = tid; i < nobs; i += nw) {
@@ -467,11 +478,11 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
           sn += c;
         }
         workers_sum2(sn, dummy, red, nw);
-        const double sb = sigma_beta[h];
-        const double log_den = sd + dnorm_log(bh, 0.0, sb), log_num = sn + dnorm_log(beta_p, 0.0, sb);
-        double u0, u1;
-        { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_BETA, 0, (uint32_t)(kk * Q + q), 1); u0 = r2_.x; u1 = r2_.y; }
-        if (upd_log(u0) < log_num - log_den) {  // same inputs in every worker thread: uniform branch
+        // dnorm(beta_p; 0, sb) - dnorm(beta; 0, sb) on the log scale: the log(sb) terms cancel (:758, :771)
+        const double isb = 1.0 / sigma_beta[h];
+        const double tp = beta_p * isb, tb = bh * isb;
+        const double ln_acp = (sn - sd) - 0.5 * (tp * tp - tb * tb);
+        if (bu[kk * Q + q] < ln_acp) {  // same inputs in every worker thread: uniform branch
           for (int i = tid; i < nobs; i += nw) {
             const double zq = z[(size_t)i * Q + q];
             lg[(size_t)i * D + kk] = __dadd_rn(__dsub_rn(lg[(size_t)i * D + kk], __dmul_rn(bh, zq)), __dmul_rn(beta_p, zq));
