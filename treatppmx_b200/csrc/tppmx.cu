@@ -43,10 +43,18 @@ struct tppmx_ctx {
   Arena spare;
   int live_batches = 0;  // tppmx_destroy is deferred until the last batch is gone
   bool closed = false;
+  // side stream of tppmx_batch_run: the summaries of a saved iteration (co-clustering counts,
+  // predictive step) run beside the updates that do not feed them
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_sweep = nullptr, ev_upd = nullptr, ev_side = nullptr;
 };
 static void ctx_release(tppmx_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamDestroy(c->stream);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_sweep) cudaEventDestroy(c->ev_sweep);
+  if (c->ev_upd) cudaEventDestroy(c->ev_upd);
+  if (c->ev_side) cudaEventDestroy(c->ev_side);
   arena_free(c->spare);
   delete c;
 }
@@ -104,7 +112,11 @@ extern "C" int tppmx_create(tppmx_ctx **out, int device) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return TPPMX_ERR_CUDA;
   tppmx_ctx *c = new tppmx_ctx();
   c->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess) {
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess ||
+      cudaStreamCreate(&c->side) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_sweep, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_upd, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return TPPMX_ERR_CUDA;
   }
@@ -199,7 +211,8 @@ static T *dev_stage(tppmx_batch *b, const T **p, size_t n, int *rc) {
   return h;
 }
 static bool fast_eligible(const tppmx_batch *b, int lpu);
-static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc);
+static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc,
+                          cudaStream_t st = nullptr);
 // one thread per new patient of an (chain, arm) block: no more threads than patients
 static inline int predict_threads(const DevBatch &d) {
   const int t = ((d.npred + 31) / 32) * 32;
@@ -1014,7 +1027,9 @@ extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, i
   return check_status(b);
 }
 
-static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launches) {
+// ev_after_update (optional): recorded between the update kernel and the gamma draws, so that work
+// which only needs eta*, beta, (Theta,Sigma), (sigma,kappa) can start beside the draws
+static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launches, cudaEvent_t ev_after_update = nullptr) {
   tppmx_ctx *ctx = b->ctx;
   const DevBatch &d = b->d;
   if (d.model.cohesion == 2 && d.ncat > 0)
@@ -1025,6 +1040,7 @@ static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launc
     update_kernel<3><<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
   else
     update_kernel<0><<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
+  if (ev_after_update) CK(ctx, cudaEventRecord(ev_after_update, ctx->stream));
   const size_t npat = (size_t)d.n_chains * d.nobs;
   jjss_kernel<<<(unsigned)((npat + 127) / 128), 128, 0, ctx->stream>>>(d, seed, iter);
   (*launches) += 2;
@@ -1048,7 +1064,8 @@ extern "C" int tppmx_batch_update(tppmx_batch *b, uint64_t seed, int32_t iter) {
   return TPPMX_OK;
 }
 
-static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do_psm, int do_pred, int *launches);
+static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do_psm, int do_pred, int *launches,
+                             cudaStream_t st = nullptr);
 
 extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_iter, int32_t burn,
                                int32_t thin, int32_t do_psm, int32_t do_pred) {
@@ -1061,12 +1078,35 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
   b->last_handovers = 0;
   int launches = 0;
   CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
+  // Saved iterations: the co-clustering counts only need the partition (ready after the sweep) and
+  // the predictive step only needs what the update kernel writes, so they run on the side stream
+  // beside the update kernel / the JJ-ss gamma draws; the next sweep waits for them.
+  bool side_pending = false;
   for (int l = iter0; l < iter0 + n_iter; l++) {
+    if (side_pending) {
+      CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+      side_pending = false;
+    }
     RC(sweep_launch(b, seed, l, 1, false, &launches));
-    RC(update_launch(b, seed, l, &launches));
-    if ((do_psm || do_pred) && (l > burn - 1) && ((l + 1) % thin == 0))  // :1060
-      RC(accumulate_launch(b, seed, l, do_psm, do_pred, &launches));
+    const bool saved = (do_psm || do_pred) && (l > burn - 1) && ((l + 1) % thin == 0);  // :1060
+    if (!saved) {
+      RC(update_launch(b, seed, l, &launches));
+      continue;
+    }
+    if (do_psm) {
+      CK(ctx, cudaEventRecord(ctx->ev_sweep, ctx->stream));
+      CK(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_sweep, 0));
+      RC(accumulate_launch(b, seed, l, 1, 0, &launches, ctx->side));
+    }
+    RC(update_launch(b, seed, l, &launches, do_pred ? ctx->ev_upd : nullptr));
+    if (do_pred) {
+      CK(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_upd, 0));
+      RC(accumulate_launch(b, seed, l, 0, 1, &launches, ctx->side));
+    }
+    CK(ctx, cudaEventRecord(ctx->ev_side, ctx->side));
+    side_pending = true;
   }
+  if (side_pending) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;
@@ -1176,8 +1216,10 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
 // capacity.  The partition size is not known on the host, so the staged capacity is kcap capped
 // at 64; chains with more clusters are rare and handled by the block itself falling back is not
 // possible mid-kernel, hence the cap decides the kernel for the whole launch.
-static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc) {
+static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc,
+                          cudaStream_t st) {
   tppmx_ctx *ctx = b->ctx;
+  if (!st) st = ctx->stream;
   const DevBatch &d = b->d;
   const tppmx_model &m = d.model;
   const int nth = predict_threads(d);
@@ -1189,12 +1231,12 @@ static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, in
     if (smem <= 200 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(predict_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("predict_fast_kernel: ") + cudaGetErrorString(e));
-      predict_fast_kernel<<<dim3(n_chains_launch, d.T), nth, smem, ctx->stream>>>(d, seed, iter, KP, dpi, dy, dc);
+      predict_fast_kernel<<<dim3(n_chains_launch, d.T), nth, smem, st>>>(d, seed, iter, KP, dpi, dy, dc);
       CK(ctx, cudaGetLastError());
       return TPPMX_OK;
     }
   }
-  predict_kernel<<<dim3(n_chains_launch, d.T), nth, 0, ctx->stream>>>(d, seed, iter, dpi, dy, dc);
+  predict_kernel<<<dim3(n_chains_launch, d.T), nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
   CK(ctx, cudaGetLastError());
   return TPPMX_OK;
 }
@@ -1214,20 +1256,22 @@ extern "C" int tppmx_batch_reset_summaries(tppmx_batch *b) {
   return TPPMX_OK;
 }
 
-static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do_psm, int do_pred, int *launches) {
+static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do_psm, int do_pred, int *launches,
+                             cudaStream_t st) {
   tppmx_ctx *ctx = b->ctx;
   const DevBatch &d = b->d;
+  if (!st) st = ctx->stream;
   if (do_psm) {
-    psm_accumulate_kernel<<<dim3(d.n_chains, d.T), 256, 0, ctx->stream>>>(d, b->psm_cnt);
+    psm_accumulate_kernel<<<dim3(d.n_chains, d.T), 256, 0, st>>>(d, b->psm_cnt);
     (*launches)++;
   }
   if (do_pred) {
-    RC(predict_launch(b, d.n_chains, seed, iter, b->pred_pi, nullptr, nullptr));
-    pi_accumulate_kernel<<<d.n_chains, 256, 0, ctx->stream>>>(d, b->pred_pi, b->pi_sum);
+    RC(predict_launch(b, d.n_chains, seed, iter, b->pred_pi, nullptr, nullptr, st));
+    pi_accumulate_kernel<<<d.n_chains, 256, 0, st>>>(d, b->pred_pi, b->pi_sum);
     (*launches) += 2;
   }
   if (do_psm || do_pred) {
-    count_saves_kernel<<<(d.n_chains + 255) / 256, 256, 0, ctx->stream>>>(d, b->psm_n, b->pi_n, do_psm, do_pred);
+    count_saves_kernel<<<(d.n_chains + 255) / 256, 256, 0, st>>>(d, b->psm_n, b->pi_n, do_psm, do_pred);
     (*launches)++;
   }
   CK(ctx, cudaGetLastError());
