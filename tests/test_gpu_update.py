@@ -119,3 +119,58 @@ def test_posterior_agrees_with_oracle_chains(ctx):
     # between-chain standard error of the oracle mean (chains are independent)
     se = Kor.mean(axis=1).std(axis=0, ddof=1) / np.sqrt(6) + Kdev.mean(axis=0).std(axis=0, ddof=1) / np.sqrt(96)
     assert (np.abs(m_dev - m_or) < 4 * se + 0.15).all(), (m_dev, m_or, se)
+
+
+def test_posterior_summaries_agree_with_oracle_chains(ctx):
+    """L3 on the summaries a user reads: co-clustering matrix and posterior-mean predictive
+    probabilities accumulated on the device against oracle chains with different seeds.  Every
+    device chain is mapped to its own copy of the dataset, so the per-dataset device summaries
+    are per-chain values and both sides give a between-chain Monte-Carlo standard error:
+    two-sample z-scores must look like noise."""
+    from treatppmx_b200.engine import Batch
+    model, dims, shared, dsets, labels, nclu, betas = build_case("default_ngg")
+    burn, keep, thin = 200, 300, 3
+    nch, nor = 48, 10
+    b = Batch(ctx, model, dims, shared, [dsets[0]] * nch, chain_dataset=list(range(nch)))
+    b.init(5005, labels, nclu, betas[0])
+    b.reset_summaries()
+    b.run(5005, 0, burn + keep, burn=burn, thin=thin, psm=True, predictive=True)
+    w = np.array([0.0, 40.0, 100.0])
+    dev = b.summaries(w)
+    pb = ob.Problem(model, dims, shared, dsets[0])
+    n_a = np.bincount(dsets[0].treat, minlength=dims.T)
+    psm_c = np.zeros((nor, dims.T, dims.ntmax, dims.ntmax))
+    pi_c = np.zeros((nor, dims.npred, dims.D, dims.T))
+    for c in range(nor):
+        st = pb.init_state(909, c, labels, nclu, betas[0])
+        pb.iterate(st, 909, c, 0, burn)
+        ns = 0
+        for l in range(burn, burn + keep):
+            pb.iterate(st, 909, c, l, 1)
+            if (l + 1) % thin == 0:
+                for t in range(dims.T):
+                    lab = st.labels[t, : n_a[t]]
+                    psm_c[c, t, : n_a[t], : n_a[t]] += lab[:, None] == lab[None, :]
+                pi_c[c] += pb.predict(st, 909, c, l)[0]
+                ns += 1
+        psm_c[c] /= ns
+        pi_c[c] /= ns
+
+    def zscores(d, o):   # d: [nch, ...] device per chain, o: [nor, ...] oracle per chain
+        se = np.sqrt(d.var(0, ddof=1) / d.shape[0] + o.var(0, ddof=1) / o.shape[0])
+        return (d.mean(0) - o.mean(0)) / np.maximum(se, 1e-3)
+
+    z_pi = zscores(dev["pi_mean"], pi_c)
+    assert np.abs(z_pi).max() < 5.0 and np.sqrt(np.mean(z_pi ** 2)) < 1.6, (np.abs(z_pi).max(), np.sqrt(np.mean(z_pi ** 2)))
+    for t in range(dims.T):
+        iu = np.triu_indices(n_a[t], 1)
+        d, o = dev["psm"][:, t][:, iu[0], iu[1]], psm_c[:, t][:, iu[0], iu[1]]
+        z = zscores(d, o)
+        assert np.abs(z).max() < 5.5 and np.sqrt(np.mean(z ** 2)) < 1.6, (t, np.abs(z).max(), np.sqrt(np.mean(z ** 2)))
+        assert np.corrcoef(d.mean(0), o.mean(0))[0, 1] > 0.95
+    # treatment choice from the pooled posterior means: identical wherever the utility gap is clear
+    util_d = np.einsum("k,pkt->tp", w, dev["pi_mean"].mean(0))
+    util_o = np.einsum("k,pkt->tp", w, pi_c.mean(0))
+    gap = np.sort(util_o, axis=0)[-1] - np.sort(util_o, axis=0)[-2]
+    clear = gap > 8.0
+    assert (util_d.argmax(0)[clear] == util_o.argmax(0)[clear]).all()
