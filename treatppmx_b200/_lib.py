@@ -8,7 +8,7 @@ import os
 from ._abi import Dataset, Dims, Model, Shared, State, c_dp, c_ip
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libtppmx.so")
+SO_PATH = os.environ.get("TPPMX_LIB") or os.path.join(_HERE, "libtppmx.so")  # TPPMX_LIB: e.g. the -DTPPMX_CHECK build
 
 # every symbol include/tppmx.h declares
 SYMBOLS = [

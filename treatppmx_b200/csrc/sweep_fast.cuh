@@ -92,6 +92,20 @@ __device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int nt
 
 constexpr unsigned TPPMX_FULL = 0xffffffffu;
 
+// Debug build (-DTPPMX_CHECK, treatppmx_b200/libtppmx_check.so): index invariants of the fast
+// kernel are verified on the device and reported through the chain's status word
+// (error code 100 + n), since compute-sanitizer is not available on the GPU pool.
+#ifdef TPPMX_CHECK
+#define TPPMX_ASSERT(cond, n)                                      \
+  do {                                                             \
+    if (!(cond)) atomicExch(&b.status[chain], 100 + (n));          \
+  } while (0)
+#else
+#define TPPMX_ASSERT(cond, n) \
+  do {                        \
+  } while (0)
+#endif
+
 // The units of a warp run CONVERGED: every collective uses the full mask (width-LPU shuffles
 // keep the units apart) and unit-specific work is predicated.  Rare events (singleton removal,
 // cluster birth, > LPU candidates) are entered warp-uniformly through __any_sync.
@@ -428,7 +442,10 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
 
       // ---- :368-457 take the patient out of its cluster
       const int zi = on ? U.lab[it] - 1 : 0;
+      TPPMX_ASSERT(zi >= 0 && zi < KS && (!on || zi < K), 1);
       const int nzi = U.nj[zi];
+      TPPMX_ASSERT(!on || nzi >= 1, 2);
+      TPPMX_ASSERT(it + 1 <= ntp, 3);
       const bool single = on && nzi <= 1;
       __syncwarp();
       if (__any_sync(TPPMX_FULL, single)) {  // singleton (:384-457), rare
@@ -494,6 +511,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       if (structural) {
         act0 = ul < K + CC;
         likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
+        TPPMX_ASSERT(!act0 || (colmap(ul, K) >= 0 && colmap(ul, K) < fa.ncol), 6);
+        TPPMX_ASSERT(nfree >= 0 && nfree <= fa.ncol, 7);
         if (!NOLIK) likv = likp[it];
       }
 
@@ -541,7 +560,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       }
 
       // ---- :820-856 assign, update sufficient statistics
+      TPPMX_ASSERT(!on || (newci >= 1 && newci <= K + CC), 4);
       const bool born = on && newci > K;
+      TPPMX_ASSERT(!born || (nfree >= 1 && K + 1 <= KS), 5);
       int lab = newci;
       if (on && !born && ul == 0) {
         U.lab[it] = lab;
