@@ -33,6 +33,15 @@ typedef struct o_rng {
   uint32_t chain;
 } o_rng;
 
+/* Variate tape (ppmx_oracle.c: oracle_tape_*).  While recording, every variate the oracle
+ * CONSUMES is appended in call order as (kind, value, aux): kind 1 = uniform, 2 = standard normal,
+ * 3 = Gamma(shape aux, scale 1).  Draws made inside a composite draw (the Box-Muller uniforms, the
+ * Marsaglia-Tsang attempts) are not recorded.  oracle/refshim replays the tape into the
+ * reference's own sources, which pins the oracle's draw order to theirs.  Single-threaded use. */
+extern int o_tape_on, o_tape_depth;
+void o_tape_rec(int kind, double val, double aux);
+#define O_TAPE_TOP() (o_tape_on && o_tape_depth == 0)
+
 /* two uniforms in (0,1): 52 random bits + 1/2, scaled by 2^-52 -> never 0, never 1 */
 static inline void o_rng_u2(const o_rng *g, uint32_t iter, uint32_t site, uint32_t arm,
                             uint32_t index, uint32_t sub, double *u0, double *u1) {
@@ -45,35 +54,53 @@ static inline void o_rng_u2(const o_rng *g, uint32_t iter, uint32_t site, uint32
   uint64_t b = (((uint64_t)o[2]) << 20) | (o[3] >> 12);
   *u0 = ((double)a + 0.5) * 0x1.0p-52;
   *u1 = ((double)b + 0.5) * 0x1.0p-52;
+  if (O_TAPE_TOP()) o_tape_rec(1, *u0, 0.0); /* callers that also consume u1 record it themselves */
 }
 
 /* two standard normals by Box-Muller on the same block */
 static inline void o_rng_n2(const o_rng *g, uint32_t iter, uint32_t site, uint32_t arm,
                             uint32_t index, uint32_t sub, double *n0, double *n1) {
   double u0, u1;
+  if (o_tape_on) o_tape_depth++;
   o_rng_u2(g, iter, site, arm, index, sub, &u0, &u1);
+  if (o_tape_on) o_tape_depth--;
   double r = sqrt(-2.0 * log(u0));
   double th = 6.283185307179586476925286766559 * u1;
   *n0 = r * cos(th);
   *n1 = r * sin(th);
+  if (O_TAPE_TOP()) o_tape_rec(2, *n0, 0.0); /* direct callers consume n0 only */
 }
 
 /* D standard normals: block b gives normals 2b, 2b+1 (sub = sub0 + b) */
 static inline void o_rng_normals(const o_rng *g, uint32_t iter, uint32_t site, uint32_t arm,
                                  uint32_t index, uint32_t sub0, int D, double *out) {
+  if (o_tape_on) o_tape_depth++;
   for (int b = 0; 2 * b < D; b++) {
     double n0, n1;
     o_rng_n2(g, iter, site, arm, index, sub0 + (uint32_t)b, &n0, &n1);
     out[2 * b] = n0;
     if (2 * b + 1 < D) out[2 * b + 1] = n1;
   }
+  if (o_tape_on) o_tape_depth--;
+  if (O_TAPE_TOP())
+    for (int k = 0; k < D; k++) o_tape_rec(2, out[k], 0.0);
 }
 
 /* Gamma(shape a, scale 1) by Marsaglia & Tsang (2000), with the U^(1/a) boost for a<1.
  * Attempt t uses block sub0+2t (normal = first Box-Muller output) and sub0+2t+1 (accept
  * uniform = u0); the boost uniform is u1 of block sub0+0xFF00.  Same draw order on device. */
+static inline double o_rng_gamma_raw(const o_rng *g, uint32_t iter, uint32_t site, uint32_t arm,
+                                     uint32_t index, uint32_t sub0, double a);
 static inline double o_rng_gamma(const o_rng *g, uint32_t iter, uint32_t site, uint32_t arm,
                                  uint32_t index, uint32_t sub0, double a) {
+  if (o_tape_on) o_tape_depth++;
+  const double v = o_rng_gamma_raw(g, iter, site, arm, index, sub0, a);
+  if (o_tape_on) o_tape_depth--;
+  if (O_TAPE_TOP()) o_tape_rec(3, v, a);
+  return v;
+}
+static inline double o_rng_gamma_raw(const o_rng *g, uint32_t iter, uint32_t site, uint32_t arm,
+                                     uint32_t index, uint32_t sub0, double a) {
   double boost = 1.0;
   if (a < 1.0) {
     double u0, u1;

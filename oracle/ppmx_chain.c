@@ -299,6 +299,7 @@ static void o_horseshoe(o_ctx *c, int l) {
   for (k = 0; k < len; k++) { /* up_lambda_hs */
     double u0, u1;
     o_rng_u2(&c->rng, (uint32_t)l, TPPMX_SITE_HS_LAMBDA, 0, (uint32_t)k, 0, &u0, &u1);
+    if (O_TAPE_TOP()) o_tape_rec(1, u1, 0.0); /* this site consumes both uniforms of the block */
     double eta = pow(lambda[k], -2.0);
     const double upsi = u0 * pow((1 + eta), -1.0); /* runif(0, 1/(1+eta)) */
     const double tempps = pow(beta[k], 2.0) / (2 * pow(tau, 2.0));
@@ -315,6 +316,7 @@ static void o_horseshoe(o_ctx *c, int l) {
     tempt = tempt / 2;
     double et = pow(tau, -2.0);
     o_rng_u2(&c->rng, (uint32_t)l, TPPMX_SITE_HS_TAU, 0, 0, 0, &u0, &u1);
+    if (O_TAPE_TOP()) o_tape_rec(1, u1, 0.0); /* both uniforms consumed */
     const double utau = u0 * pow((1.0 + et), -1.0);
     const double ubt = (1.0 - utau) / utau;
     const double shape = (((double)len) + 1.0) / 2;

@@ -1,7 +1,8 @@
 /*
  * ppmx_oracle.c — CPU oracle of the treatppmx hot path.  TEST INFRASTRUCTURE ONLY
- * (see ppmx_oracle.h for the rules and the parity-pin status: "parity unpinned" w.r.t.
- * reference-produced outputs; pinned by closed-form known-answer tests).
+ * (see ppmx_oracle.h for the rules and the parity-pin status: pinned against the reference's own
+ * sources compiled into oracle/_ref and run on this oracle's variate tape, plus closed-form
+ * known-answer tests).
  *
  * Restates, statement by statement and with the same loop structure, evaluation order and
  * quirks:
@@ -132,6 +133,38 @@ double oracle_gsimcatDM(const double *nobsj, const double *dirweights, int C, in
 }
 
 /* RNG probes */
+/* ---- variate tape (philox_ref.h) ------------------------------------------------------------- */
+int o_tape_on = 0, o_tape_depth = 0;
+static double *o_tape_buf = NULL; /* [cap][3] = kind, value, aux */
+static long o_tape_n = 0, o_tape_cap = 0;
+void o_tape_rec(int kind, double val, double aux) {
+  if (o_tape_n == o_tape_cap) {
+    o_tape_cap = o_tape_cap ? 2 * o_tape_cap : (1 << 16);
+    o_tape_buf = (double *)realloc(o_tape_buf, sizeof(double) * 3 * (size_t)o_tape_cap);
+  }
+  o_tape_buf[3 * o_tape_n + 0] = (double)kind;
+  o_tape_buf[3 * o_tape_n + 1] = val;
+  o_tape_buf[3 * o_tape_n + 2] = aux;
+  o_tape_n++;
+}
+void oracle_tape_start(void) {
+  o_tape_n = 0;
+  o_tape_depth = 0;
+  o_tape_on = 1;
+}
+long oracle_tape_stop(void) {
+  o_tape_on = 0;
+  return o_tape_n;
+}
+/* copies records [0, n) as three parallel arrays */
+void oracle_tape_get(double *kind, double *val, double *aux, long n) {
+  for (long i = 0; i < n && i < o_tape_n; i++) {
+    kind[i] = o_tape_buf[3 * i];
+    val[i] = o_tape_buf[3 * i + 1];
+    aux[i] = o_tape_buf[3 * i + 2];
+  }
+}
+
 void oracle_rng_u2(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t site, uint32_t arm,
                    uint32_t index, uint32_t sub, double *out2) {
   o_rng g = {seed, chain};

@@ -5,11 +5,18 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Nothing in
  * treatppmx_b200/ (the product) may include, link or call this.
  *
- * Parity pin status: the reference ships NO tests, golden vectors or fixtures for this path
- *  and cannot be compiled here (needs R, Rcpp, RcppArmadillo, libRmath), so the
- * oracle is pinned by closed-form known-answer tests instead (tests/test_oracle_kat.py):
- * NN / NNIG / DM marginals against scipy, and the CRP cluster-count law for the sweep.
- * With respect to reference-produced outputs it is "parity unpinned".
+ * Parity pin status: PINNED against the reference's own sources executed here.  The reference
+ * ships no tests, golden vectors or fixtures for this path and R / Rcpp /
+ * Armadillo are absent, so src/utils_ct.cpp, src/dm_ppmx_ct.cpp and src/prior_ppmx.cpp are
+ * compiled UNMODIFIED against the stand-in headers of oracle/refshim/ into oracle/_ref/libref.so
+ * (make -C oracle ref) and compared with this oracle (tests/test_oracle_vs_reference.py):
+ * helper by helper on random inputs (<= 1e-13), and as whole runs of dm_ppmx_ct /
+ * prior_ppmx_core driven by the tape of variates this oracle consumes (oracle_tape_*): all 18
+ * outputs, every switch combination the reference can run, bit-identical labels / counts /
+ * draws, <= 1e-12 on reals.  The reference's outputs are committed as tests/golden/ref_*.npz.
+ * What stays a stand-in: the library layer under the sources (R's RNG stream, Armadillo's
+ * mvnrnd / wishrnd construction, libRmath pgamma / qgamma) -- see oracle/refshim/RcppArmadillo.h.
+ * Closed-form known-answer tests remain as an independent check (tests/test_oracle_kat.py).
  *
  * State and inputs use the structs of include/tppmx.h (reference layouts).
  */
@@ -48,6 +55,12 @@ void oracle_rng_n2(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t site, 
                    uint32_t index, uint32_t sub, double *out2);
 double oracle_rng_gamma(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t site,
                         uint32_t arm, uint32_t index, double shape);
+
+/* variate tape: record every variate the oracle consumes, in call order, for replay into the
+ * reference's own sources (oracle/refshim, tests/test_oracle_vs_reference.py) */
+void oracle_tape_start(void);
+long oracle_tape_stop(void);
+void oracle_tape_get(double *kind, double *val, double *aux, long n);
 
 /* prologue of dm_ppmx_ct (src/dm_ppmx_ct.cpp:49-236) */
 int oracle_init_state(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,

@@ -1,0 +1,2 @@
+/* oracle/refshim stand-in (TEST INFRASTRUCTURE ONLY): everything lives in RcppArmadillo.h */
+#include "RcppArmadillo.h"

@@ -1,0 +1,256 @@
+/*
+ * oracle/refshim/ref_driver.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * extern "C" access to the reference's OWN functions, compiled unmodified from
+ * /root/reference/src/{utils_ct,dm_ppmx_ct,prior_ppmx}.cpp against the stand-in headers of this
+ * directory (oracle/Makefile target `ref` -> oracle/_ref/libref.so).  Used by
+ * tests/test_oracle_vs_reference.py and scripts/make_reference_golden.py to pin the oracle
+ * against the reference's statements executed here.
+ *
+ * Nothing of the reference is restated in this file: it only marshals flat arrays into the
+ * argument types the reference declares (src/utils_ct.h, src/dm_ppmx_ct.cpp:10-23,
+ * src/prior_ppmx.cpp:9-16) and copies the returned list out.
+ */
+#include "RcppArmadillo.h"
+
+#include <cstdint>
+#include <cstdio>
+
+#include "../../treatppmx_b200/csrc/incgamma.h" /* R::pgamma / R::qgamma stand-in, as the oracle */
+
+/* ---- the reference's declarations (src/utils_ct.h; the two samplers have no header) ---------- */
+#include "utils_ct.h"
+arma::vec dmvnrm(arma::mat x, arma::rowvec mean, arma::mat sigma, bool logd);
+Rcpp::List dm_ppmx_ct(int iter, int burn, int thin, int nobs, arma::vec treatments, int PPMx, int ncon,
+                      int ncat, arma::vec catvec, double alpha, arma::mat grid, arma::cube Vwm,
+                      int cohesion, int CC, int reuse, int consim, int similarity, int calibration,
+                      int coardegree, arma::mat y, arma::mat z, arma::mat zpred, int noprog,
+                      arma::vec xcon, arma::vec xcat, arma::vec xconp, arma::vec xcatp, int npred,
+                      arma::vec similparam, arma::vec hP0_mu0, double hP0_nu0, double hP0_s0,
+                      double hP0_Lambda0, int upd_hier, arma::vec initbeta, int hsp,
+                      arma::vec mhtunepar, int A, arma::vec n_a, arma::mat curr_cluster,
+                      arma::mat card_cluster, arma::vec ncluster_curr);
+Rcpp::List prior_ppmx_core(int iter, int burn, int thin, int nobs, int PPMx, int ncon, int ncat,
+                           double alpha, double sigma, arma::mat Vwm, int cohesion, int CC, int consim,
+                           int similarity, int calibration, int coardegree, arma::vec xcon,
+                           arma::vec similparam, arma::vec curr_cluster, arma::vec card_cluster,
+                           int ncluster_curr);
+
+/* ---- tape ------------------------------------------------------------------------------------- */
+namespace {
+const double *g_kind = nullptr, *g_val = nullptr, *g_aux = nullptr;
+long g_n = 0, g_pos = 0;
+std::string g_err;
+}  // namespace
+
+namespace refshim {
+double tape_pop(int kind, double aux) {
+  char buf[256];
+  if (g_pos >= g_n) {
+    snprintf(buf, sizeof buf, "tape exhausted at draw %ld (wanted kind %d)", g_pos, kind);
+    throw std::runtime_error(buf);
+  }
+  if ((int)g_kind[g_pos] != kind) {
+    snprintf(buf, sizeof buf, "tape draw %ld: the reference asks for kind %d, the oracle recorded kind %d",
+             g_pos, kind, (int)g_kind[g_pos]);
+    throw std::runtime_error(buf);
+  }
+  if (kind == TAPE_G && !(std::fabs(g_aux[g_pos] - aux) <= 1e-9 * std::fabs(aux))) {
+    snprintf(buf, sizeof buf, "tape draw %ld: gamma shape %.17g asked, %.17g recorded", g_pos, aux, g_aux[g_pos]);
+    throw std::runtime_error(buf);
+  }
+  return g_val[g_pos++];
+}
+double gammainc_lower(double a, double x) { return tppmx_gammainc(a, x); }
+double gammainc_lower_inv(double a, double p) { return tppmx_gammaincinv(a, p); }
+}  // namespace refshim
+
+static arma::vec mk_vec(const double *p, long n) {
+  arma::vec v((arma::uword)n);
+  for (long i = 0; i < n; i++) v.d[i] = p[i];
+  return v;
+}
+static arma::mat mk_mat(const double *p, long r, long c) {
+  arma::mat m((arma::uword)r, (arma::uword)c);
+  for (long i = 0; i < r * c; i++) m.d[i] = p[i];
+  return m;
+}
+static void put(double *dst, const arma::mat &m) {
+  if (dst) std::copy(m.d.begin(), m.d.end(), dst);
+}
+static void put(double *dst, const arma::cube &c) {
+  if (!dst) return;
+  for (arma::uword k = 0; k < c.n_slices; k++)
+    std::copy(c.s[k].d.begin(), c.s[k].d.end(), dst + k * c.n_rows * c.n_cols);
+}
+
+extern "C" {
+
+/* kind[i] in {1 uniform, 2 normal, 3 gamma(shape aux[i], scale 1)}, val[i] the variate */
+void ref_tape_set(const double *kind, const double *val, const double *aux, long n) {
+  g_kind = kind; g_val = val; g_aux = aux; g_n = n; g_pos = 0;
+}
+long ref_tape_pos(void) { return g_pos; }
+const char *ref_last_error(void) { return g_err.c_str(); }
+
+/* ---- src/utils_ct.cpp, function by function ---------------------------------------------------- */
+double ref_dinvgamma(double y, double a, double b, int lg) { return dinvgamma(y, a, b, lg); }
+double ref_dN_IG(double mu, double s2, double mu0, double k0, double a0, double b0, int lg) {
+  return dN_IG(mu, s2, mu0, k0, a0, b0, lg);
+}
+double ref_gsimconNN(double m0, double v2, double s20, double sumx, double sumx2, int n, int DD, int lg) {
+  return gsimconNN(m0, v2, s20, sumx, sumx2, n, DD, lg);
+}
+double ref_gsimconNNIG(double m0, double k0, double nu0, double s20, double sumx, double sumx2, int n, int DD,
+                       int lg) {
+  return gsimconNNIG(m0, k0, nu0, s20, sumx, sumx2, n, DD, lg);
+}
+double ref_gsimcatDM(const double *nobsj, const double *dirw, int C, int DD, int lg) {
+  return gsimcatDM(mk_vec(nobsj, C), mk_vec(dirw, C), C, DD, lg);
+}
+double ref_calculate_gamma(const double *eta, int D, int ncols, const double *Z, int nobs, int Q,
+                           const double *beta, int clu, int k, int i, int Log) {
+  return calculate_gamma(mk_mat(eta, D, ncols), mk_mat(Z, nobs, Q), mk_vec(beta, (long)Q * D), clu, k, i, Log);
+}
+double ref_dmvnrm_log(const double *x, const double *mean, const double *sigma, int n) {
+  return dmvnrm(mk_mat(x, 1, n), arma::rowvec(mk_mat(mean, 1, n)), mk_mat(sigma, n, n), true)(0);
+}
+double ref_dmultinom(const double *x, int size, const double *prob, int K, int Log) {
+  return dmultinom_rcpp(mk_vec(x, K), size, mk_vec(prob, K), Log);
+}
+/* eta_update (src/utils_ct.cpp:579-702): eta[D], loggamma[nobs x D], eta_flag[len] updated in place */
+int ref_eta_update(const double *JJ, double *loggamma, int nobs, int D, const double *curr_clu, int nclu_len,
+                   const double *treatments, int t, double *eta, double *eta_flag, int flag_len,
+                   const double *mu_star, const double *sigma_star, int jj, double mhtune) {
+  try {
+    Rcpp::List o = eta_update(mk_mat(JJ, nobs, D), mk_mat(loggamma, nobs, D), mk_vec(curr_clu, nclu_len),
+                              mk_vec(treatments, nobs), t, mk_vec(eta, D), mk_vec(eta_flag, flag_len),
+                              mk_vec(mu_star, D), mk_mat(sigma_star, D, D), jj, mhtune);
+    put(eta, Rcpp::as<arma::vec>(o[0]));
+    put(loggamma, Rcpp::as<arma::mat>(o[1]));
+    put(eta_flag, Rcpp::as<arma::vec>(o[2]));
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+/* beta_update (src/utils_ct.cpp:710-800): beta_temp[Q], loggamma[nobs x D], beta_flag[Q x D] in place */
+int ref_beta_update(const double *ZZ, const double *JJ, double *loggamma, int nobs, int D, int Q, double *beta_temp,
+                    double *beta_flag, double mu_beta, const double *sigma_beta, int kk, double mhtune) {
+  try {
+    Rcpp::List o = beta_update(mk_mat(ZZ, nobs, Q), mk_mat(JJ, nobs, D), mk_mat(loggamma, nobs, D),
+                               mk_vec(beta_temp, Q), mk_mat(beta_flag, Q, D), mu_beta,
+                               mk_vec(sigma_beta, (long)Q * D), kk, mhtune);
+    put(beta_temp, Rcpp::as<arma::vec>(o[0]));
+    put(loggamma, Rcpp::as<arma::mat>(o[1]));
+    put(beta_flag, Rcpp::as<arma::mat>(o[2]));
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+int ref_up_lambda_hs(const double *beta, double *lambda, int len, double tau) {
+  try {
+    put(lambda, up_lambda_hs(mk_vec(beta, len), mk_vec(lambda, len), tau));
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+int ref_up_tau_hs(const double *beta, const double *lambda, int len, double *tau) {
+  try {
+    *tau = up_tau_hs(mk_vec(beta, len), mk_vec(lambda, len), *tau);
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+/* ---- src/dm_ppmx_ct.cpp:10-1471, the whole run -------------------------------------------------
+ * Inputs are the 42 arguments in the reference's order, matrices column-major (Armadillo).  Vwm is
+ * the dense cube (vr x vc x G).  Outputs are the 18 list elements, flattened column-major; fields
+ * are laid out element after element: eta [D x ntmax] for (ll, tt) with ll fastest (Armadillo field
+ * order), pipred / ypred [npred x D x T] per saved iteration. */
+int ref_dm_ppmx_ct(int iter, int burn, int thin, int nobs, const double *treatments, int PPMx, int ncon, int ncat,
+                   const double *catvec, int ncatvec, double alpha, const double *grid, int G, const double *Vwm,
+                   int vr, int vc, int cohesion, int CC, int reuse, int consim, int similarity, int calibration,
+                   int coardegree, const double *y, int D, const double *z, int Q, const double *zpred, int noprog,
+                   const double *xcon, const double *xcat, const double *xconp, const double *xcatp, int npred,
+                   const double *similparam, const double *hP0_mu0, double hP0_nu0, double hP0_s0,
+                   double hP0_Lambda0, int upd_hier, const double *initbeta, int hsp, const double *mhtunepar, int A,
+                   const double *n_a, const double *curr_cluster, const double *card_cluster,
+                   const double *ncluster_curr, int ntmax,
+                   /* outputs */
+                   double *eta, double *beta, double *sigma_ngg, double *kappa_ngg, double *eta_acc, double *beta_acc,
+                   double *cl_lab, double *num_treat, double *pi, double *pipred, double *yispred, double *ypred,
+                   double *clupred, double *nclus, double *WAIC, double *lpml, double *theta_prior,
+                   double *sigma_prior) {
+  try {
+    arma::cube V((arma::uword)vr, (arma::uword)vc, (arma::uword)(Vwm ? G : 0));
+    if (Vwm)
+      for (int g = 0; g < G; g++)
+        for (long i = 0; i < (long)vr * vc; i++) V.s[g].d[i] = Vwm[(long)g * vr * vc + i];
+    Rcpp::List o = dm_ppmx_ct(
+        iter, burn, thin, nobs, mk_vec(treatments, nobs), PPMx, ncon, ncat, mk_vec(catvec, ncatvec), alpha,
+        mk_mat(grid, 2, G), V, cohesion, CC, reuse, consim, similarity, calibration, coardegree, mk_mat(y, nobs, D),
+        mk_mat(z, nobs, Q), mk_mat(zpred, npred, Q), noprog, mk_vec(xcon, (long)nobs * ncon),
+        mk_vec(xcat, (long)nobs * ncat), mk_vec(xconp, (long)npred * ncon), mk_vec(xcatp, (long)npred * ncat), npred,
+        mk_vec(similparam, 7), mk_vec(hP0_mu0, D), hP0_nu0, hP0_s0, hP0_Lambda0, upd_hier,
+        mk_vec(initbeta, (long)Q * D), hsp, mk_vec(mhtunepar, 2), A, mk_vec(n_a, A), mk_mat(curr_cluster, A, ntmax),
+        mk_mat(card_cluster, A, ntmax), mk_vec(ncluster_curr, A));
+    const int nout = (iter - burn) / thin;
+    const arma::field<arma::mat> &fe = o["eta"].fm;
+    if (eta)
+      for (arma::uword e = 0; e < fe.n_elem; e++) put(eta + e * (long)D * ntmax, fe.e[e]);
+    put(beta, o["beta"].m);
+    put(sigma_ngg, o["sigma_ngg"].m);
+    put(kappa_ngg, o["kappa_ngg"].m);
+    put(eta_acc, o["eta_acc"].m);
+    put(beta_acc, o["beta_acc"].m);
+    put(cl_lab, o["cl_lab"].c);
+    put(num_treat, o["num_treat"].m);
+    put(pi, o["pi"].c);
+    put(yispred, o["yispred"].c);
+    for (int ll = 0; ll < nout; ll++) {
+      if (pipred) put(pipred + (long)ll * npred * D * A, o["pipred"].fc.e[ll]);
+      if (ypred) put(ypred + (long)ll * npred * D * A, o["ypred"].fc.e[ll]);
+    }
+    put(clupred, o["clupred"].m);
+    put(nclus, o["nclus"].m);
+    if (WAIC) *WAIC = o["WAIC"].num;
+    put(lpml, o["lpml"].m);
+    put(theta_prior, o["theta_prior"].m);
+    put(sigma_prior, o["sigma_prior"].c);
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+/* ---- src/prior_ppmx.cpp:9-466 -------------------------------------------------------------------
+ * outputs: nclu[nout], njout[nobs x nout] (col-major) */
+int ref_prior_ppmx_core(int iter, int burn, int thin, int nobs, int PPMx, int ncon, int ncat, double alpha,
+                        double sigma, const double *Vwm, int vr, int vc, int cohesion, int CC, int consim,
+                        int similarity, int calibration, int coardegree, const double *xcon,
+                        const double *similparam, const double *curr_cluster, const double *card_cluster,
+                        int ncluster_curr, double *nclu, double *njout) {
+  try {
+    Rcpp::List o = prior_ppmx_core(iter, burn, thin, nobs, PPMx, ncon, ncat, alpha, sigma, mk_mat(Vwm, vr, vc),
+                                   cohesion, CC, consim, similarity, calibration, coardegree,
+                                   mk_vec(xcon, (long)nobs * ncon), mk_vec(similparam, 7), mk_vec(curr_cluster, nobs),
+                                   mk_vec(card_cluster, nobs), ncluster_curr);
+    put(nclu, o["nclu"].m);
+    put(njout, o["njout"].m);
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+} /* extern "C" */

@@ -1,0 +1,50 @@
+"""Generates tests/golden/ref_<case>.npz: the 18-element return list of the REFERENCE's own
+dm_ppmx_ct (src/dm_ppmx_ct.cpp:10-1471, compiled unmodified into oracle/_ref/libref.so against
+oracle/refshim/) for a handful of parity cases, with the Philox-contract variates (recorded from the
+oracle, tests/refrun.py:Tape) in place of R's RNG.  Needs /root/reference; run from the repo root:
+
+    python tests/golden/make_reference_golden.py
+
+The files are what the oracle (CPU test) and the CUDA drop-in tppmx_dm_ppmx_ct (GPU test) must
+reproduce where the reference itself is not available (tests/test_reference_golden.py)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.dirname(os.path.dirname(HERE)), os.path.dirname(HERE)]
+
+import refrun  # noqa: E402
+
+REF_GOLDEN = {  # name -> (iters, burn, thin, seed)
+    "default_ngg": (36, 12, 3, 99),
+    "dp_T3": (36, 12, 3, 99),
+    "nnig": (30, 10, 2, 5),
+    "calib1": (30, 10, 2, 6),
+    "calib2_sqrt": (30, 10, 2, 7),
+    "noreuse": (30, 10, 2, 8),
+    "categorical": (30, 10, 2, 9),
+    "Q3_D3": (30, 10, 2, 10),
+}
+
+
+def path(name):
+    return os.path.join(HERE, f"ref_{name}.npz")
+
+
+def main():
+    R = refrun.RefLib()
+    for name, (iters, burn, thin, seed) in REF_GOLDEN.items():
+        args, _, case = refrun.reference_args(name, iters, burn, thin, True)
+        with refrun.Tape() as tape:
+            refrun.oracle_run(case, iters, burn, thin, seed)
+        got = R.dm_ppmx_ct(args, tape)
+        assert got.pop("tape_used") == len(tape)
+        got["WAIC"] = np.array(got["WAIC"])
+        np.savez_compressed(path(name), **got)
+        print(name, "draws", len(tape), os.path.getsize(path(name)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

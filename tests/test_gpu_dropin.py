@@ -6,79 +6,9 @@ import numpy as np
 import pytest
 
 import oracle_binding as ob
-from cases import build_case
-from treatppmx_b200 import datagen
+from refrun import oracle_run as _oracle_run, reference_args as _reference_args
 
 pytestmark = pytest.mark.gpu
-
-
-def _reference_args(name, iters, burn, thin, dense_V):
-    model, dims, shared, dsets, labels, nclu, betas = build_case(name)
-    ds = dsets[0]
-    n_a = np.bincount(ds.treat, minlength=dims.T).astype(float)
-    Vwm = logV = None
-    if model.cohesion == 2:
-        if dense_V:   # the dense (max n_t + 1)^2 x G cube of R/dm_ppmx_ct.R:242-254, rows n_t-1 and n_t filled
-            nmax = int(n_a.max())
-            Vwm = np.zeros((nmax + 1, nmax + 1, dims.G), order="F")
-            for t in range(dims.T):
-                for r in (0, 1):
-                    row = int(n_a[t]) - 2 + r
-                    Vwm[row, : dims.ntmax, :] = np.exp(shared.logV[t, r])
-        else:
-            logV = shared.logV
-    sp = [model.similparam[i] for i in range(7)]
-    args = dict(
-        iter=iters, burn=burn, thin=thin, nobs=dims.nobs, treatments=ds.treat.astype(float), PPMx=model.PPMx,
-        ncon=dims.P, ncat=dims.ncat, catvec=shared.catvec.astype(float), alpha=model.alpha, grid=shared.grid,
-        Vwm=Vwm, cohesion=model.cohesion, CC=model.CC, reuse=model.reuse, consim=model.consim,
-        similarity=model.similarity, calibration=model.calibration, coardegree=model.coardegree, y=ds.y, z=ds.z,
-        zpred=ds.zpred, noprog=model.noprog, xcon=ds.xcon.ravel(), xcat=ds.xcat.astype(float).ravel(),
-        xconp=ds.xconp.ravel(), xcatp=ds.xcatp.astype(float).ravel(), npred=dims.npred, similparam=sp,
-        hP0_mu0=[model.hP0_mu0[k] for k in range(dims.D)], hP0_nu0=model.hP0_nu0, hP0_s0=model.hP0_s0,
-        hP0_Lambda0=model.hP0_Lambda0, upd_hier=model.upd_hier, initbeta=betas[0], hsp=model.hsp,
-        mhtunepar=[model.mhtune_eta, model.mhtune_beta], A=dims.T, n_a=n_a, curr_cluster=labels.astype(float),
-        card_cluster=np.zeros_like(labels, dtype=float), ncluster_curr=nclu.astype(float))
-    return args, logV, (model, dims, shared, dsets, labels, nclu, betas)
-
-
-def _oracle_run(case, iters, burn, thin, seed):
-    model, dims, shared, dsets, labels, nclu, betas = case
-    pb = ob.Problem(model, dims, shared, dsets[0])
-    st = pb.init_state(seed, 0, labels, nclu, betas[0])
-    acc = pb.new_acc()
-    nout = (iters - burn) // thin
-    T, D, nt, n, Q, npred = dims.T, dims.D, dims.ntmax, dims.nobs, dims.Q, dims.npred
-    n_a = np.bincount(dsets[0].treat, minlength=T)
-    out = dict(eta=np.zeros((D, nt, nout, T)), beta=np.zeros((Q * D, nout)), sigma_ngg=np.zeros((T, nout)),
-               kappa_ngg=np.zeros((T, nout)), cl_lab=np.zeros((T, nt, nout)), pi=np.zeros((n, D, nout)),
-               pipred=np.zeros((npred, D, T, nout)), yispred=np.zeros((n, D, nout)), ypred=np.zeros((npred, D, T, nout)),
-               clupred=np.zeros((nout * npred, T)), nclus=np.zeros((T, nout)), lpml=np.zeros(nout))
-    mnlike, mnllike, sumtot, ll = np.zeros(n), np.zeros(n), np.zeros(T), 0
-    for l in range(iters):
-        pb.iterate(st, seed, 0, l, 1, acc)
-        sumtot += st.nclu
-        if l > burn - 1 and (l + 1) % thin == 0:
-            pi, isp, like = pb.insample(st, seed, 0, l)
-            mnlike += like / nout
-            mnllike += np.log(like) / nout
-            out["lpml"][ll] = np.log(like).sum()
-            pip, yp, pc = pb.predict(st, seed, 0, l)
-            out["pi"][:, :, ll], out["yispred"][:, :, ll] = pi, isp
-            out["pipred"][..., ll], out["ypred"][..., ll] = pip, yp
-            out["clupred"][ll * npred:(ll + 1) * npred, :] = pc
-            out["sigma_ngg"][:, ll], out["kappa_ngg"][:, ll], out["nclus"][:, ll] = st.sigma, st.kappa, st.nclu
-            out["beta"][:, ll] = st.beta
-            for t in range(T):
-                out["cl_lab"][t, : n_a[t], ll] = st.labels[t, : n_a[t]]
-                out["eta"][:, : st.nclu[t], ll, t] = st.eta_star[:, : st.nclu[t], t]
-            ll += 1
-    out["eta_acc"] = acc[0] / sumtot[:, None]
-    out["beta_acc"] = acc[1].astype(float)
-    out["num_treat"] = n_a.astype(float)
-    out["WAIC"] = -2 * np.sum(2 * mnllike - np.log(mnlike))
-    out["theta_prior"], out["sigma_prior"] = st.Theta.copy(), st.Sigma.copy()
-    return out
 
 
 @pytest.mark.parametrize("name,dense_V", [("default_ngg", True), ("default_ngg", False), ("dp_T3", False), ("nnig", False)])

@@ -74,9 +74,17 @@ __global__ void insample_save_kernel(DevBatch b, TraceBufs tr, uint64_t seed, in
     tr.cl_lab[t + (size_t)T * (it + (size_t)ntm * ll)] = (it < b.arm_n[t]) ? (double)b.labels[e] : 0.0;
   }
   for (int e = tid; e < Q * D; e += nth) tr.beta[e + (size_t)Q * D * ll] = b.beta[e];
-  for (int e = tid; e < T * D * ntm; e += nth) {  // eta_out(ll, tt): columns j < nclu, else 0
+  // eta_out(ll, tt) (:1421-1427): ONE scratch matrix is zeroed per saved iteration and reused for
+  // every arm, only its columns j < nclu(tt) being overwritten, so column j >= nclu(tt) of arm tt
+  // still holds the eta of the last earlier arm that had more than j clusters (0 if none).
+  for (int e = tid; e < T * D * ntm; e += nth) {
     const int t = e / (D * ntm), k = (e / ntm) % D, j = e % ntm;
-    const double v = (j < b.nclu[t] && j < ks) ? b.eta[((size_t)t * D + k) * ks + j] : 0.0;
+    double v = 0.0;
+    for (int ts = t; ts >= 0; ts--)
+      if (j < b.nclu[ts] && j < ks) {
+        v = b.eta[((size_t)ts * D + k) * ks + j];
+        break;
+      }
     tr.eta[((size_t)ll + (size_t)nout * t) * D * ntm + k + (size_t)D * j] = v;
   }
   if (npred > 0) {
