@@ -13,6 +13,26 @@ namespace tppmx {
 #define TPPMX_LN2_HI 0.693147180369123816490
 #define TPPMX_LN2_LO 1.90821492927058770002e-10
 
+// Polynomial coefficients live in constant memory: a DFMA takes a constant-bank operand for
+// free, whereas a 64-bit literal costs two moves per use (profiles/r1_sweep_fast_*: 8 % of the
+// sweep kernel's issued instructions were UMOVs of literals).
+enum {
+  FC_SQRT2 = 0, FC_LN2_HI, FC_LN2_LO, FC_NLN2_HI, FC_NLN2_LO, FC_LOG2E,
+  FC_LOG0,            // 9 entries: 1/19, 1/17, ..., 1/3
+  FC_EXPA = FC_LOG0 + 9,   // 7 entries: 1/12!, 1/10!, ..., 1/0!
+  FC_EXPB = FC_EXPA + 7,   // 7 entries: 1/13!, 1/11!, ..., 1/1!
+  FC_STIR = FC_EXPB + 7,   // 7 entries: Stirling series
+  FC_HLN2PI = FC_STIR + 7,
+  FC_COUNT
+};
+__constant__ double FC[FC_COUNT] = {
+    1.4142135623730951, TPPMX_LN2_HI, TPPMX_LN2_LO, -TPPMX_LN2_HI, -TPPMX_LN2_LO, 1.4426950408889634,
+    1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0,
+    1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5, 1.0,
+    1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0, 1.0,
+    1.0 / 156.0, -691.0 / 360360.0, 1.0 / 1188.0, -1.0 / 1680.0, 1.0 / 1260.0, -1.0 / 360.0, 1.0 / 12.0,
+    0.91893853320467274178};
+
 // 1/a, a positive normal: hardware seed (2^-23) + two Newton steps
 __device__ __forceinline__ double fast_rcp(double a) {
   double r;
@@ -30,7 +50,7 @@ __device__ __forceinline__ double fast_log(double y) {
   const int lo = __double2loint(y);
   int e = (hi >> 20) - 1023;
   double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
-  if (m > 1.4142135623730951) {  // compiles to selects
+  if (m > FC[FC_SQRT2]) {  // compiles to selects
     m *= 0.5;
     e += 1;
   }
@@ -39,42 +59,29 @@ __device__ __forceinline__ double fast_log(double y) {
   double f = num * r;
   f = fma(fma(-f, den, num), r, f);
   const double f2 = f * f;
-  double p = 1.0 / 19.0;
-  p = fma(p, f2, 1.0 / 17.0);
-  p = fma(p, f2, 1.0 / 15.0);
-  p = fma(p, f2, 1.0 / 13.0);
-  p = fma(p, f2, 1.0 / 11.0);
-  p = fma(p, f2, 1.0 / 9.0);
-  p = fma(p, f2, 1.0 / 7.0);
-  p = fma(p, f2, 1.0 / 5.0);
-  p = fma(p, f2, 1.0 / 3.0);
+  double p = FC[FC_LOG0];
+#pragma unroll
+  for (int i = 1; i < 9; i++) p = fma(p, f2, FC[FC_LOG0 + i]);
   const double t = f * f2 * p;
   const double de = (double)e;
-  return fma(de, TPPMX_LN2_HI, fma(de, TPPMX_LN2_LO, 2.0 * (f + t)));
+  return fma(de, FC[FC_LN2_HI], fma(de, FC[FC_LN2_LO], 2.0 * (f + t)));
 }
 
 // exp(x), x <= ~1e-3 (softmax exponent after the max shift); x < -700 -> 0
 __device__ __forceinline__ double fast_exp(double x) {
-  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const double t = fma(x, FC[FC_LOG2E], 6755399441055744.0);
   const double n = t - 6755399441055744.0;
-  double r = fma(n, -TPPMX_LN2_HI, x);
-  r = fma(n, -TPPMX_LN2_LO, r);
+  double r = fma(n, FC[FC_NLN2_HI], x);
+  r = fma(n, FC[FC_NLN2_LO], r);
   // exp(r) = A(r^2) + r B(r^2): two half-length Horner chains (depth 8 instead of 14)
   const double r2 = r * r;
-  double pa = 1.0 / 479001600.0;  // even coefficients 1/12!, 1/10!, ..., 1
-  pa = fma(pa, r2, 1.0 / 3628800.0);
-  pa = fma(pa, r2, 1.0 / 40320.0);
-  pa = fma(pa, r2, 1.0 / 720.0);
-  pa = fma(pa, r2, 1.0 / 24.0);
-  pa = fma(pa, r2, 0.5);
-  pa = fma(pa, r2, 1.0);
-  double pb = 1.0 / 6227020800.0;  // odd coefficients 1/13!, 1/11!, ..., 1
-  pb = fma(pb, r2, 1.0 / 39916800.0);
-  pb = fma(pb, r2, 1.0 / 362880.0);
-  pb = fma(pb, r2, 1.0 / 5040.0);
-  pb = fma(pb, r2, 1.0 / 120.0);
-  pb = fma(pb, r2, 1.0 / 6.0);
-  pb = fma(pb, r2, 1.0);
+  double pa = FC[FC_EXPA];  // even coefficients 1/12!, 1/10!, ..., 1
+  double pb = FC[FC_EXPB];  // odd coefficients 1/13!, 1/11!, ..., 1
+#pragma unroll
+  for (int i = 1; i < 7; i++) {
+    pa = fma(pa, r2, FC[FC_EXPA + i]);
+    pb = fma(pb, r2, FC[FC_EXPB + i]);
+  }
   const double p = fma(pb, r, pa);
   const int ni = __double2loint(t);  // n as an integer (low word of the magic-number sum)
   const double out = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
@@ -92,14 +99,10 @@ __device__ __forceinline__ double lgamma_pos(double x) {
   p *= q;
   const double y = small ? x + 8.0 : x;
   const double r = fast_rcp(y), r2 = r * r;
-  double s = 1.0 / 156.0;
-  s = fma(s, r2, -691.0 / 360360.0);
-  s = fma(s, r2, 1.0 / 1188.0);
-  s = fma(s, r2, -1.0 / 1680.0);
-  s = fma(s, r2, 1.0 / 1260.0);
-  s = fma(s, r2, -1.0 / 360.0);
-  s = fma(s, r2, 1.0 / 12.0);
-  const double lg = fma(y - 0.5, fast_log(y), -y) + 0.91893853320467274178 + s * r;
+  double s = FC[FC_STIR];
+#pragma unroll
+  for (int i = 1; i < 7; i++) s = fma(s, r2, FC[FC_STIR + i]);
+  const double lg = fma(y - 0.5, fast_log(y), -y) + FC[FC_HLN2PI] + s * r;
   return lg - fast_log(small ? p : 1.0);
 }
 
