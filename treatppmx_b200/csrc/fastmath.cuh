@@ -25,7 +25,7 @@ enum {
   FC_HLN2PI = FC_STIR + 7,
   FC_COUNT
 };
-__constant__ double FC[FC_COUNT] = {
+static __constant__ double FC[FC_COUNT] = {
     1.4142135623730951, TPPMX_LN2_HI, TPPMX_LN2_LO, -TPPMX_LN2_HI, -TPPMX_LN2_LO, 1.4426950408889634,
     1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0,
     1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5, 1.0,

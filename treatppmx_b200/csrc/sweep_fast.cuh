@@ -34,38 +34,9 @@
 #include "rng.cuh"
 #include "fastmath.cuh"
 #include "sim.cuh"
+#include "sweep_fast_args.h"
 
 namespace tppmx {
-
-#define TPPMX_FAST_KSMAX 32
-#define TPPMX_FAST_KSTR 33  // smem stride of the [P][cluster] arrays; column 32 is an all-zero cluster
-
-struct FastArgs {
-  double *lik;     // [units][ncol][ntp] (+ntp pad)  likelihood table (global, L2 resident)
-  double *uq;      // [units][2][ntp+1]    uniforms, sum_p x_ip^2
-  int *resume_l;   // [units] sweep at which the unit handed over to the generic kernel, -1 = done
-  int *resume_it;  // [units] patient position of the hand-over
-  int *bail_count; // [1]
-  int KS, ntp, ncol, n_units;
-  int unit_bytes, tab_bytes;
-  // big arms (BASELINE config 4: n_t in the thousands): everything indexed by patient position or
-  // by cluster size would not fit in shared memory, so it lives in global memory (L2-resident):
-  int big;          // 1: the three tables over n and labels / patient order / cohesion table are global
-  double *tabg;     // [3][ntmax + 2]  dA, HN, HY (filled once at batch creation)
-  double *logng;    // [units][ntp + 1]
-  int *patpad;      // [units][ntp + 1] patient order of the unit, zero-padded
-};
-
-__host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }
-// bytes of shared memory of one unit
-__host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D, int big) {
-  size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (big ? 0 : (ntp + 1)) + 2 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
-  size_t in = (size_t)KS + 2 * (KS + CC) + (big ? 0 : 2 * (ntp + 1)) + 1;
-  return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
-}
-__host__ __device__ inline size_t fast_tab_bytes(int ntmax, int big) {
-  return big ? 16 : ((((size_t)3 * (ntmax + 2) * 8) + 15) & ~(size_t)15);
-}
 
 struct UnitSmem {
   double *sumx, *sumx2, *logn, *xs, *wsc, *E;
@@ -140,7 +111,7 @@ __device__ __forceinline__ int warp_max_over_units(int v) {
 // L_i(eta) without its cluster-independent part (:570-576):
 //   sum_k [ gamma_k log JJ_ik - lgamma(gamma_k) ],  gamma_k = exp(eta_k) exp(zb_ik)
 // The only call site of the lgamma code (keeps the kernel's instruction footprint small).
-__device__ __noinline__ double fast_lik(const double *E, const double *Z, const double *ljj, int D) {
+static __device__ __noinline__ double fast_lik(const double *E, const double *Z, const double *ljj, int D) {
   double w = 0.0;
   // three outcome categories per trip: the three lgamma evaluations are independent straight-line
   // code, so their dependent fma chains interleave (fp64 latency hiding inside one warp)
@@ -157,33 +128,11 @@ __device__ __noinline__ double fast_lik(const double *E, const double *Z, const 
   return w;
 }
 
-// Register version for the pre-pass: the patient's exp(zb) / log JJ stay in registers while the
-// lane walks over the candidate clusters (one L2 round trip per patient instead of one per
-// table entry).  DR = 3 or TPPMX_MAXD.
-template <int DR>
-__device__ __forceinline__ double fast_lik_reg(const double *E, const double (&Z)[DR], const double (&ljj)[DR], int D) {
-  double w = 0.0;
-#pragma unroll
-  for (int k = 0; k < DR; k += 3) {
-    if (k < D) {
-      const bool h1 = (k + 1 < DR) && (k + 1 < D), h2 = (k + 2 < DR) && (k + 2 < D);
-      const double g0 = E[k] * Z[k];
-      const double g1 = h1 ? E[k + 1] * Z[(k + 1 < DR) ? k + 1 : k] : 1.0;
-      const double g2 = h2 ? E[k + 2] * Z[(k + 2 < DR) ? k + 2 : k] : 1.0;
-      const double l0 = lgamma_pos(g0), l1 = lgamma_pos(g1), l2 = lgamma_pos(g2);
-      w += fma(g0, ljj[k], -l0);
-      if (h1) w += fma(g1, ljj[(k + 1 < DR) ? k + 1 : k], -l1);
-      if (h2) w += fma(g2, ljj[(k + 2 < DR) ? k + 2 : k], -l2);
-    }
-  }
-  return w;
-}
-
 // cold path: a unit of the warp has more than LPU candidate clusters (`mine`).  Scores in
 // chunks through U.wsc; returns newci for the units with `mine`.
 template <int LPU>
-__device__ __noinline__ int fast_score_multi(UnitSmem U, const double *t_dA, const double *t_HN,
-                                             const double *t_HY, const double *lik, int ntp, int it,
+__device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, const double *logn,
+                                             const double *lik, int ntp, int it,
                                              int K, int CC, int KS, int P, const double *xs, double qx,
                                              double uu, double dV, double simscale, double iv2,
                                              double c0, double hiv2, bool nolik, bool mine, int ul,
@@ -202,10 +151,11 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double *t_dA, con
       bb = fma(t, xs[p], bb);
     }
     const double tY = a + iv2 * (2.0 * bb + iv2 * qx);
-    const double d = t_dA[n] - hiv2 * qx + (t_HY[n] * tY - t_HN[n] * a);
+    const double2 t01 = tab2[2 * n], t23 = tab2[2 * n + 1];  // (dA, HN), (HY, -)
+    const double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a);
     const int c = occ ? U.col[j] : U.col[KS + (j - K)];
     const double lv = nolik ? 0.0 : lik[(size_t)c * ntp + it];
-    const double w = dV + U.logn[n] + simscale * d + lv;
+    const double w = dV + logn[n] + simscale * d + lv;
     U.wsc[j] = w;
     wmax = fmax(wmax, w);
   }
@@ -239,7 +189,7 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double *t_dA, con
   return newci;
 }
 
-template <int LPU, int XR, int DR, bool NOLIK>
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG>
 __global__ void __launch_bounds__(32, 12)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -254,17 +204,16 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const int Pp = fast_pp(P);
   const SimConst s = make_simconst(b);
 
-  // ---- per-CTA tables over n (Normal-Normal log terms, utils_ct.cpp:389-400 via sim.cuh NNRow)
-  const int big = fa.big;
-  double *t_dA = big ? fa.tabg : reinterpret_cast<double *>(smem_raw);
-  double *t_HN = t_dA + (b.ntmax + 2);
-  double *t_HY = t_HN + (b.ntmax + 2);
-  for (int n = lane; n <= b.ntmax && !big; n += 32) {
-    const NNRow r0 = b.nn_tab[n], r1 = b.nn_tab[n + 1];
-    const double dP = (double)P;
-    t_dA[n] = (n == 0) ? dP * r1.A0 : dP * (r1.A0 - r0.A0);
-    t_HN[n] = (n == 0) ? 0.0 : r0.H;
-    t_HY[n] = r1.H;
+  // ---- per-CTA table over n (Normal-Normal log terms, utils_ct.cpp:389-400 via sim.cuh NNRow):
+  //      entry n = (dA, HN, HY, -), built on the host (fa.tabg); staged in shared memory unless BIG
+  const double2 *tab2;
+  if constexpr (BIG) {
+    tab2 = reinterpret_cast<const double2 *>(fa.tabg);
+  } else {
+    double2 *ts = reinterpret_cast<double2 *>(smem_raw);
+    const double2 *tg = reinterpret_cast<const double2 *>(fa.tabg);
+    for (int e = lane; e < 2 * (b.ntmax + 2); e += 32) ts[e] = tg[e];
+    tab2 = ts;
   }
 
   const int chain = unit / b.T, tt = unit % b.T;
@@ -272,7 +221,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const int nt = valid ? b.arm_n[(size_t)ds * b.T + tt] : 0;
   const int nt_w = warp_max_over_units<LPU>(nt);
   const Rng rng = make_rng(seed, b.chain_id[chain]);
-  UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC, D, big);
+  UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC, D, BIG ? 1 : 0);
 
   // global state of this unit
   double *g_sumx = b.sumx + ((size_t)chain * b.T + tt) * P * kcap;
@@ -303,17 +252,24 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     U.sumx2[e] = (j < KS) ? g_sumx2[(size_t)p * kcap + j] : 0.0;
   }
   for (int j = ul; j < KS; j += LPU) U.nj[j] = g_nj[j];
-  if (big) {  // labels are updated in place in the batch's global array (ntmax entries, enough for
-              // every index the loop touches: lab[it] is only read for it < nt)
-    U.lab = g_lab;
-    U.pat = fa.patpad + (size_t)unit * (ntp + 1);
-    U.logn = fa.logng + (size_t)unit * (ntp + 1);
+  // patient-indexed arrays: shared memory, or (BIG: arms of thousands of patients) global memory.
+  // Kept in separate variables so the compiler sees one address space per instantiation.
+  int *labp, *patp;
+  double *lognp;
+  if constexpr (BIG) {  // labels are updated in place in the batch's global array (ntmax entries, enough
+                        // for every index the loop touches: lab[it] is only read for it < nt)
+    labp = g_lab;
+    patp = fa.patpad + (size_t)unit * (ntp + 1);
+    lognp = fa.logng + (size_t)unit * (ntp + 1);
     if (valid)
-      for (int it = ul; it <= ntp; it += LPU) U.pat[it] = (it < nt) ? g_pat[it] : 0;
+      for (int it = ul; it <= ntp; it += LPU) patp[it] = (it < nt) ? g_pat[it] : 0;
   } else {
+    labp = U.lab;
+    patp = U.pat;
+    lognp = U.logn;
     for (int it = ul; it <= ntp; it += LPU) {
-      U.lab[it] = (it < nt) ? g_lab[it] : 1;
-      U.pat[it] = (it < nt) ? g_pat[it] : 0;
+      labp[it] = (it < nt) ? g_lab[it] : 1;
+      patp[it] = (it < nt) ? g_pat[it] : 0;
     }
   }
   // column indirection: clusters 0..K-1 -> cols 0..K-1, aux m -> col K+m, the rest is free
@@ -326,8 +282,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     for (int f = ul; f < nfree; f += LPU) U.freec[f] = Kc + CC + f;
   }
   // cohesion by cluster size: logn[0] is the auxiliary-cluster value (:677 / :680)
-  if (ul == 0) U.logn[0] = (s.cohesion == 1) ? log(b.model.alpha) - log((double)CC) : 0.0;
-  for (int n = 1 + ul; n <= nt; n += LPU) U.logn[n] = fast_log((s.cohesion == 1) ? (double)n : (double)n - sigma);
+  if (ul == 0) lognp[0] = (s.cohesion == 1) ? log(b.model.alpha) - log((double)CC) : 0.0;
+  for (int n = 1 + ul; n <= nt; n += LPU) lognp[n] = fast_log((s.cohesion == 1) ? (double)n : (double)n - sigma);
   __syncwarp();
 
   auto dV_of = [&](int Kcur) -> double {
@@ -362,11 +318,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     }
     __syncwarp();
     if (live) {
-      // per patient (one lane each): allocation uniform, sum_p x^2, exp(beta'z), log JJ, and
-      // the likelihood-table entries of every candidate cluster
-      const int ntot = K + CC;
+      // phase A, per patient (one lane each): allocation uniform, sum_p x^2, exp(beta'z), log JJ
       for (int it = ul; it < nt; it += LPU) {
-        const int i = U.pat[it];
+        const int i = patp[it];
         const double *xi = g_x + (size_t)i * P;
         double qx = 0.0;
         for (int p = 0; p < P; p++) qx = fma(xi[p], xi[p], qx);
@@ -377,24 +331,32 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         if (!NOLIK) {
           const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
           const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
-          double Z[DR], ljj[DR];
-#pragma unroll
-          for (int k = 0; k < DR; k++) {
-            Z[k] = 1.0;
-            ljj[k] = 0.0;
-            if (k < D) {
-              double acc = 0.0;
-              for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
-              Z[k] = fast_exp(acc);
-              ljj[k] = fast_log(JJ[k]);
-              g_ez[(size_t)i * D + k] = Z[k];
-              g_ljj[(size_t)i * D + k] = ljj[k];
-            }
+          for (int k = 0; k < D; k++) {
+            double acc = 0.0;
+            for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
+            g_ez[(size_t)i * D + k] = fast_exp(acc);
+            g_ljj[(size_t)i * D + k] = fast_log(JJ[k]);
           }
-          for (int c = 0; c < ntot; c++) {
-            const int cl = colmap(c, K);
-            lik[(size_t)cl * ntp + it] = fast_lik_reg<DR>(U.E + cl * D, Z, ljj, D);
-          }
+        }
+      }
+    }
+    __syncwarp();
+    if (live && !NOLIK) {
+      // phase B, per (candidate cluster, patient) pair, flattened over the unit's lanes so that
+      // every lane carries the same number of likelihood terms whatever n_t and K are (a loop
+      // over patients with an inner loop over clusters leaves 20-40 % of the lanes idle):
+      // pair e -> (c, it) = (e / nt, e % nt), kept incrementally; consecutive lanes write
+      // consecutive rows of one table column
+      const int npair = (K + CC) * nt;
+      int c = ul / nt, it = ul - c * nt;
+      for (int e = ul; e < npair; e += LPU) {
+        const int i = patp[it];
+        const int cl = colmap(c, K);
+        lik[(size_t)cl * ntp + it] = fast_lik(U.E + cl * D, g_ez + (size_t)i * D, g_ljj + (size_t)i * D, D);
+        it += LPU;
+        while (it >= nt) {
+          it -= nt;
+          c += 1;
         }
       }
     }
@@ -406,7 +368,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     const double *likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
     double likv = 0.0, uu = uq[0], qx = uq[uqs];
     {  // operands of step 0
-      const int i0 = U.pat[0];
+      const int i0 = patp[0];
 #pragma unroll
       for (int r = 0; r < XR; r++) {
         const int p = ul + r * LPU;
@@ -429,7 +391,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       //      arrays are padded so the last step may read one entry past the arm)
       double xr_n[XR], lik_n = 0.0;
       {
-        const double *xrow = g_x + (size_t)U.pat[it + 1] * P;
+        const double *xrow = g_x + (size_t)patp[it + 1] * P;
 #pragma unroll
         for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
@@ -441,7 +403,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       bool structural = false;
 
       // ---- :368-457 take the patient out of its cluster
-      const int zi = on ? U.lab[it] - 1 : 0;
+      const int zi = on ? labp[it] - 1 : 0;
       TPPMX_ASSERT(zi >= 0 && zi < KS && (!on || zi < K), 1);
       const int nzi = U.nj[zi];
       TPPMX_ASSERT(!on || nzi >= 1, 2);
@@ -453,11 +415,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         const bool swp = single && iaux < Kc;
         if (swp)  // swap with the last cluster
           for (int ii = ul; ii < nt; ii += LPU)
-            if (U.lab[ii] == Kc) U.lab[ii] = iaux;
+            if (labp[ii] == Kc) labp[ii] = iaux;
         __syncwarp();
         if (swp) {
           if (ul == 0) {
-            U.lab[it] = Kc;
+            labp[it] = Kc;
             U.nj[iaux - 1] = U.nj[Kc - 1];
             U.nj[Kc - 1] = 1;
             const int c = U.col[iaux - 1];
@@ -539,8 +501,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
         const double a = a0 + a1, bb = b0 + b1;
         const double tY = a + iv2 * (2.0 * bb + iv2 * qx);
-        const double d = t_dA[n] - hiv2 * qx + (t_HY[n] * tY - t_HN[n] * a);
-        const double w = act0 ? dV + U.logn[n] + simscale * d + likv : -INFINITY;
+        const double2 t01 = tab2[2 * n], t23 = tab2[2 * n + 1];  // (dA, HN), (HY, -)
+        const double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a);
+        const double w = act0 ? dV + lognp[n] + simscale * d + likv : -INFINITY;
         // the shift only has to be common to the unit's lanes and close to the maximum: the
         // float-rounded maximum costs a quarter of the shuffles of an fp64 max
         const double wmax = (double)unit_maxf<LPU>((float)w);
@@ -554,7 +517,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       }
       const bool multi = on && ntot > LPU;
       if (__any_sync(TPPMX_FULL, multi)) {
-        const int r = fast_score_multi<LPU>(U, t_dA, t_HN, t_HY, lik, ntp, it, K, CC, KS, P, xs, qx, uu, dV,
+        const int r = fast_score_multi<LPU>(U, tab2, lognp, lik, ntp, it, K, CC, KS, P, xs, qx, uu, dV,
                                             simscale, iv2, c0, hiv2, NOLIK, multi, ul, sub);
         if (multi) newci = r;
       }
@@ -565,13 +528,13 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       TPPMX_ASSERT(!born || (nfree >= 1 && K + 1 <= KS), 5);
       int lab = newci;
       if (on && !born && ul == 0) {
-        U.lab[it] = lab;
+        labp[it] = lab;
         U.nj[lab - 1] += 1;
       }
       if (__any_sync(TPPMX_FULL, born)) {  // a new cluster takes the auxiliary eta (:829-845), rare
         int m = 0, newcol = 0, i = 0;
         if (born) {
-          i = U.pat[it];
+          i = patp[it];
           m = newci - K - 1;
           lab = K + 1;
           newcol = U.freec[nfree - 1];
@@ -580,7 +543,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         __syncwarp();
         if (born) {
           if (ul == 0) {
-            U.lab[it] = lab;
+            labp[it] = lab;
             U.nj[lab - 1] = 1;
             U.col[lab - 1] = U.col[KS + m];
             U.col[KS + m] = newcol;
@@ -596,7 +559,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         if (born) {
           if (!NOLIK)  // likelihood column of the refreshed auxiliary eta, remaining patients
             for (int it2 = it + 1 + ul; it2 < nt; it2 += LPU) {
-              const int i2 = U.pat[it2];
+              const int i2 = patp[it2];
               lik[(size_t)newcol * ntp + it2] =
                   fast_lik(U.E + newcol * D, g_ez + (size_t)i2 * D, g_ljj + (size_t)i2 * D, D);
             }
@@ -645,8 +608,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       }
     }
     for (int j = ul; j < KS; j += LPU) g_nj[j] = U.nj[j];
-    if (!big)
-      for (int it = ul; it < nt; it += LPU) g_lab[it] = U.lab[it];
+    if (!BIG)
+      for (int it = ul; it < nt; it += LPU) g_lab[it] = labp[it];
     if (ul == 0) {
       b.nclu[(size_t)chain * b.T + tt] = K;
       fa.resume_l[unit] = bail_l;
@@ -661,8 +624,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   // the patients it still has to visit; rewriting the visited ones is value-preserving.
   if (valid && n_sweeps > 0) {
     for (int it = ul; it < nt; it += LPU) {
-      const int i = U.pat[it];
-      const int lb = U.lab[it];
+      const int i = patp[it];
+      const int lb = labp[it];
       const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
       for (int k = 0; k < D; k++) {
         double lg = g_eta[(size_t)k * kcap + lb - 1];
@@ -671,6 +634,45 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       }
     }
   }
+}
+
+// ---- launch: instantiation picked from the batch shape (one translation unit per LPU) ----------
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG>
+static cudaError_t fast_launch5(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
+                                int n_sweeps, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int upw = 32 / LPU;
+  const int grid = (fa.n_units + upw - 1) / upw;
+  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
+  return cudaGetLastError();
+}
+template <int LPU, int XR, int DR, bool NOLIK>
+static cudaError_t fast_launch4(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
+                                int n_sweeps, cudaStream_t stream) {
+  if (fa.big) {  // big-arm mode exists for one unit per warp only (sweep_launch picks LPU = 32 for it)
+    if constexpr (LPU == 32) return fast_launch5<LPU, XR, DR, NOLIK, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
+    return cudaErrorInvalidConfiguration;
+  }
+  return fast_launch5<LPU, XR, DR, NOLIK, false>(d, fa, smem, seed, iter0, n_sweeps, stream);
+}
+template <int LPU, int XR>
+static cudaError_t fast_launch2(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
+                                int n_sweeps, cudaStream_t stream) {
+  const bool nolik = d.model.nolik != 0;
+  // DR = registers of the pre-pass that hold a patient's exp(zb) / log JJ (D <= 3 is the package's case)
+  if (d.D <= 3)
+    return nolik ? fast_launch4<LPU, XR, 3, true>(d, fa, smem, seed, iter0, n_sweeps, stream)
+                 : fast_launch4<LPU, XR, 3, false>(d, fa, smem, seed, iter0, n_sweeps, stream);
+  return nolik ? fast_launch4<LPU, XR, TPPMX_MAXD, true>(d, fa, smem, seed, iter0, n_sweeps, stream)
+               : fast_launch4<LPU, XR, TPPMX_MAXD, false>(d, fa, smem, seed, iter0, n_sweeps, stream);
+}
+template <int LPU>
+static cudaError_t fast_launch_impl(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
+                                    int n_sweeps, cudaStream_t stream) {
+  // XR = registers per lane that hold the next patient's covariate row (P <= XR * LPU)
+  if (d.P <= LPU) return fast_launch2<LPU, 1>(d, fa, smem, seed, iter0, n_sweeps, stream);
+  return fast_launch2<LPU, 4>(d, fa, smem, seed, iter0, n_sweeps, stream);
 }
 
 }  // namespace tppmx

@@ -1,0 +1,49 @@
+// sweep_fast_args.h — host-visible part of the fast sweep kernel (sweep_fast.cuh): launch
+// arguments, shared-memory sizing and the per-LPU launchers.  The kernel templates are
+// instantiated in their own translation units (sweep_fast_lpu{8,16,32}.cu) so the library builds
+// in parallel; tppmx.cu only needs this header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+namespace tppmx {
+
+#define TPPMX_FAST_KSMAX 32
+#define TPPMX_FAST_KSTR 33  // smem stride of the [P][cluster] arrays; column 32 is an all-zero cluster
+
+struct FastArgs {
+  double *lik;     // [units][ncol][ntp] (+ntp pad)  likelihood table (global, L2 resident)
+  double *uq;      // [units][2][ntp+1]    uniforms, sum_p x_ip^2
+  int *resume_l;   // [units] sweep at which the unit handed over to the generic kernel, -1 = done
+  int *resume_it;  // [units] patient position of the hand-over
+  int *bail_count; // [1]
+  int KS, ntp, ncol, n_units;
+  int unit_bytes, tab_bytes;
+  // big arms (BASELINE config 4: n_t in the thousands): everything indexed by patient position or
+  // by cluster size would not fit in shared memory, so it lives in global memory (L2-resident):
+  int big;          // 1: the three tables over n and labels / patient order / cohesion table are global
+  double *tabg;     // [ntmax + 2][4]  (dA, HN, HY, -) per cluster size n (filled once at batch creation)
+  double *logng;    // [units][ntp + 1]
+  int *patpad;      // [units][ntp + 1] patient order of the unit, zero-padded
+};
+
+__host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }
+// bytes of shared memory of one unit
+__host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D, int big) {
+  size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (big ? 0 : (ntp + 1)) + 2 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
+  size_t in = (size_t)KS + 2 * (KS + CC) + (big ? 0 : 2 * (ntp + 1)) + 1;
+  return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t fast_tab_bytes(int ntmax, int big) {
+  return big ? 16 : (size_t)4 * (ntmax + 2) * 8;  // (dA, HN, HY, -) per n
+}
+
+// Launch for LPU lanes per (chain, arm) on `stream`; picks the instantiation from the batch shape
+// (P -> XR, D -> DR, model.nolik, fa.big).  fa.big requires LPU = 32.
+cudaError_t fast_launch_lpu8(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0, int n_sweeps, cudaStream_t stream);
+cudaError_t fast_launch_lpu16(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0, int n_sweeps, cudaStream_t stream);
+cudaError_t fast_launch_lpu32(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0, int n_sweeps, cudaStream_t stream);
+
+}  // namespace tppmx

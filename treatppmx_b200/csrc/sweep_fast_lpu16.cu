@@ -1,0 +1,9 @@
+// Instantiations of sweep_fast_kernel for 16 lanes per (chain, arm) (own translation unit: parallel build).
+#include "sweep_fast.cuh"
+
+namespace tppmx {
+cudaError_t fast_launch_lpu16(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0, int n_sweeps,
+                              cudaStream_t stream) {
+  return fast_launch_impl<16>(d, fa, smem, seed, iter0, n_sweeps, stream);
+}
+}  // namespace tppmx

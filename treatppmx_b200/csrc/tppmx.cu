@@ -15,7 +15,7 @@
 #include "sim.cuh"
 #include "sweep.cuh"
 #include "summary.cuh"
-#include "sweep_fast.cuh"
+#include "sweep_fast_args.h"
 #include "update.cuh"
 #include "dropin.cuh"
 
@@ -900,12 +900,12 @@ static int fast_reserve(tppmx_batch *b) {
   RC(dev_alloc(b, &fa.patpad, units * (ntp + 1)));
   {  // the three tables over n of sweep_fast.cuh, for arms too long to keep them in shared memory
     std::vector<NNRow> tab = build_nn_tab(d.model, d.ntmax);
-    std::vector<double> tg((size_t)3 * (d.ntmax + 2), 0.0);
+    std::vector<double> tg((size_t)4 * (d.ntmax + 2), 0.0);
     const double dP = (double)d.P;
     for (int n = 0; n <= d.ntmax; n++) {
-      tg[n] = (n == 0) ? dP * tab[1].A0 : dP * (tab[n + 1].A0 - tab[n].A0);
-      tg[(size_t)(d.ntmax + 2) + n] = (n == 0) ? 0.0 : tab[n].H;
-      tg[(size_t)2 * (d.ntmax + 2) + n] = tab[n + 1].H;
+      tg[(size_t)4 * n + 0] = (n == 0) ? dP * tab[1].A0 : dP * (tab[n + 1].A0 - tab[n].A0);
+      tg[(size_t)4 * n + 1] = (n == 0) ? 0.0 : tab[n].H;
+      tg[(size_t)4 * n + 2] = tab[n + 1].H;
     }
     const double *tp = nullptr;
     RC(dev_upload(b, &tp, tg));
@@ -934,32 +934,6 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
   return TPPMX_OK;
 }
 
-template <int LPU, int XR, int DR, bool NOLIK>
-static cudaError_t fast_launch4(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int upw = 32 / LPU;
-  const int grid = (b->fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, DR, NOLIK><<<grid, 32, smem, b->ctx->stream>>>(b->d, b->fa, seed, iter0, n_sweeps);
-  return cudaGetLastError();
-}
-template <int LPU, int XR>
-static cudaError_t fast_launch2(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
-  const bool nolik = b->d.model.nolik != 0;
-  // DR = registers of the pre-pass that hold a patient's exp(zb) / log JJ (D <= 3 is the package's case)
-  if (b->d.D <= 3)
-    return nolik ? fast_launch4<LPU, XR, 3, true>(b, smem, seed, iter0, n_sweeps)
-                 : fast_launch4<LPU, XR, 3, false>(b, smem, seed, iter0, n_sweeps);
-  return nolik ? fast_launch4<LPU, XR, TPPMX_MAXD, true>(b, smem, seed, iter0, n_sweeps)
-               : fast_launch4<LPU, XR, TPPMX_MAXD, false>(b, smem, seed, iter0, n_sweeps);
-}
-template <int LPU>
-static cudaError_t fast_launch(tppmx_batch *b, size_t smem, uint64_t seed, int iter0, int n_sweeps) {
-  // XR = registers per lane that hold the next patient's covariate row (P <= XR * LPU)
-  if (b->d.P <= LPU) return fast_launch2<LPU, 1>(b, smem, seed, iter0, n_sweeps);
-  return fast_launch2<LPU, 4>(b, smem, seed, iter0, n_sweeps);
-}
-
 // Launches the sweep kernels for iterations iter0..iter0+n_sweeps-1 on the context's stream.
 // sync_handover: read the hand-over count back and launch the generic finisher only if needed
 // (one host sync); otherwise the finisher is always launched (it exits at once for chains with
@@ -969,11 +943,12 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   // lanes per (chain, arm): 16 (two units per warp) for the package's shapes, where an arm holds
   // ~4-10 clusters; long arms (config 4) hold tens of clusters -> one unit per warp
   int lpu = b->opt_lpu;
-  if (!lpu) {
+  {
     const DevBatch &dd = b->d;
     const size_t ks = dd.kcap < TPPMX_FAST_KSMAX ? dd.kcap : TPPMX_FAST_KSMAX, ntp = (dd.ntmax + 3) & ~3;
     const bool big = fast_tab_bytes(dd.ntmax, 0) + 2 * fast_unit_bytes(dd.P, (int)ks, (int)ntp, dd.CC, dd.D, 0) > 48 * 1024;
-    lpu = big ? 32 : 16;
+    if (big) lpu = 32;  // the big-arm instantiations exist for one unit per warp only
+    else if (!lpu) lpu = 16;
   }
   size_t smem = 0;
   bool use_fast = b->opt_impl != 1 && fast_eligible(b, lpu) && b->fa.lik;
@@ -984,9 +959,9 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   if (b->opt_impl == 2 && !use_fast) return fail(ctx, TPPMX_ERR_ARG, "model/shape not eligible for the fast sweep kernel");
   if (use_fast) {
     CK(ctx, cudaMemsetAsync(b->fa.bail_count, 0, sizeof(int), ctx->stream));
-    cudaError_t e = lpu == 8    ? fast_launch<8>(b, smem, seed, iter0, n_sweeps)
-                    : lpu == 32 ? fast_launch<32>(b, smem, seed, iter0, n_sweeps)
-                                : fast_launch<16>(b, smem, seed, iter0, n_sweeps);
+    cudaError_t e = lpu == 8    ? fast_launch_lpu8(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
+                    : lpu == 32 ? fast_launch_lpu32(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
+                                : fast_launch_lpu16(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("sweep_fast_kernel: ") + cudaGetErrorString(e));
     (*launches)++;
     int nb = 1;
