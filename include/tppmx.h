@@ -169,7 +169,7 @@ int tppmx_destroy(tppmx_ctx *ctx);
 const char *tppmx_last_error(const tppmx_ctx *ctx);
 
 /* Test hook: evaluates the library's device fp64 math on n inputs (which: 0 = log, 1 = exp,
- * 2 = lgamma for x > 0, the branch-free versions the fast sweep kernel uses). */
+ * 2 = lgamma for x > 0, 3 = table-driven log; the branch-free versions the fast sweep kernel uses). */
 int tppmx_probe_math(tppmx_ctx *ctx, int32_t which, const double *x, int32_t n, double *out);
 
 /* ---- batch of chains ---------------------------------------------------------------- */
