@@ -84,7 +84,7 @@ struct tppmx_batch {
   // fast sweep kernel (sweep_fast.cuh)
   int opt_impl = 0, opt_lpu = 0, opt_ks = 0;
   FastArgs fa;
-  UpdArgs ua;
+  UpdArgs ua{};
   bool fast_ready = false;
   int last_impl = 0, last_handovers = 0;
 };
@@ -319,6 +319,17 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
     if (model->cohesion == 2) {
       std::vector<double> lv(shared->logV, shared->logV + (size_t)T * 2 * d.ntmax * d.G);
       TRY(dev_upload(b, &d.logV, lv));
+      // (sigma,kappa) grid draw (update.cuh, :963): lgamma(n - sigma_g) - lgamma(1 - sigma_g) for
+      // every grid point g and cluster size n depends on the inputs only -> tabulated once
+      std::vector<double> lgt((size_t)d.G * (d.ntmax + 1), 0.0);
+      if (!b->dry)
+        for (int g = 0; g < d.G; g++) {
+          const double sg = shared->grid[2 * (size_t)g], l1 = lgamma(1.0 - sg);
+          for (int n = 1; n <= d.ntmax; n++) lgt[(size_t)g * (d.ntmax + 1) + n] = lgamma((double)n - sg) - l1;
+        }
+      const double *lgp = nullptr;
+      TRY(dev_upload(b, &lgp, lgt));
+      b->ua.lgtab = lgp;
     }
     std::vector<NNRow> tab = build_nn_tab(*model, d.ntmax);
     TRY(dev_upload(b, &d.nn_tab, tab));
@@ -1017,7 +1028,8 @@ static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launc
     update_kernel<0><<<d.n_chains, nth, smem, ctx->stream>>>(d, b->ua, seed, iter);
   if (ev_after_update) CK(ctx, cudaEventRecord(ev_after_update, ctx->stream));
   const size_t npat = (size_t)d.n_chains * d.nobs;
-  jjss_kernel<<<(unsigned)((npat + 127) / 128), 128, 0, ctx->stream>>>(d, seed, iter);
+  const unsigned nhs = (unsigned)((d.n_chains + 127) / 128);  // horseshoe blocks (update.cuh)
+  jjss_kernel<<<(unsigned)((npat + 127) / 128) + nhs, 128, 0, ctx->stream>>>(d, seed, iter);
   (*launches) += 2;
   CK(ctx, cudaGetLastError());
   return TPPMX_OK;

@@ -23,6 +23,7 @@ struct UpdArgs {
   double *pat2;  // [nc][3][T][ntmax]    per-patient current / proposed likelihood sums (+ log JJ)
   double *os;    // [nc][T][G]           (sigma,kappa) grid weights
   int *acc;      // [nc][T][kcap]        accept flags of this iteration
+  const double *lgtab;  // [G][ntmax+1]    lgamma(n - sigma_g) - lgamma(1 - sigma_g) (cohesion 2)
 };
 
 // lower Cholesky factor, column-major n x n (n <= DM).  The loops are deliberately NOT unrolled:
@@ -116,8 +117,6 @@ __device__ __forceinline__ void upd_normals(const Rng &g, uint32_t iter, uint32_
 
 // named barriers: 1 = the worker warps among themselves, 2 = workers -> serial warp hand-off
 __device__ __forceinline__ void bar_workers(int nw) { asm volatile("bar.sync 1, %0;" ::"r"(nw) : "memory"); }
-__device__ __forceinline__ void bar_arrive2(int n) { asm volatile("bar.arrive 2, %0;" ::"r"(n) : "memory"); }
-__device__ __forceinline__ void bar_sync2(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }
 
 // sum of (a, b) over the nw worker threads (warps 0 .. nw/32-1), deterministic order; the result
 // is valid in every worker thread.  red: 2 * (nw/32) doubles of shared memory.
@@ -343,50 +342,6 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
         for (int k = 0; k < D * D; k++) Sigma[t * D * D + k] = tmp[k];
       }
     }
-    bar_sync2(nth);  // the workers have finished the beta steps
-    // ================= horseshoe, utils_ct.cpp:876-915 =================
-    if (b.model.noprog != 1 && b.model.hsp == 1 && lane == 0) {
-      double *sigma_beta = b.sigma_beta + (size_t)chain * Q * D;
-      const int len = Q * D;
-      double *lambda = b.lambda + (size_t)chain * len;
-      double tau = b.tau[chain];
-      #pragma unroll 1
-      for (int k = 0; k < len; k++) {
-        double u0, u1;
-        { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_HS_LAMBDA, 0, (uint32_t)k, 0); u0 = r2_.x; u1 = r2_.y; }
-        double et = 1.0 / (lambda[k] * lambda[k]);
-        const double upsi = u0 * (1.0 / (1.0 + et));
-        const double tempps = (beta[k] * beta[k]) / (2.0 * tau * tau);
-        const double ub = (1.0 - upsi) / upsi;
-        double Fub = 1.0 - upd_exp(-tempps * ub);
-        if (Fub < 1e-4) Fub = 1e-4;
-        const double up = u1 * Fub;
-        et = -upd_log(1.0 - up) / tempps;
-        lambda[k] = 1.0 / sqrt(et);
-      }
-      double tempt = 0.0, u0, u1;
-      #pragma unroll 1
-      for (int k = 0; k < len; k++) {
-        const double r = beta[k] / lambda[k];
-        tempt += r * r;
-      }
-      tempt = tempt / 2.0;
-      double et = 1.0 / (tau * tau);
-      { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_HS_TAU, 0, 0, 0); u0 = r2_.x; u1 = r2_.y; }
-      const double utau = u0 * (1.0 / (1.0 + et));
-      const double ubt = (1.0 - utau) / utau;
-      const double shape = ((double)len + 1.0) / 2.0;
-      double Fubt = upd_gammainc(shape, ubt * tempt);
-      if (Fubt < 1e-4) Fubt = 1e-4;
-      const double ut = u1 * Fubt;
-      et = upd_gammaincinv(shape, ut) / tempt;
-      if (et < .0001) et = .0001;
-      tau = 1.0 / sqrt(et);
-      if (tau < .0001) tau = .0001;
-      b.tau[chain] = tau;
-      #pragma unroll 1
-      for (int k = 0; k < len; k++) sigma_beta[k] = lambda[k] * tau;
-    }
     return;
   }
 
@@ -398,11 +353,10 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
     double *os = ua.os + (size_t)chain * T * G;
     for (int e = tid; e < T * G; e += nw) {
       const int t = e / G, g = e - t * G;
-      const double sg = b.grid[2 * g];
       const int K = nclu[t];
       double v = 0.0;
-      const double l1 = upd_lgamma(1.0 - sg);
-      for (int j = 0; j < K; j++) v += upd_lgamma((double)njv[t * ks + j] - sg) - l1;
+      const double *lt = ua.lgtab + (size_t)g * (ntm + 1);  // lgamma(n - sigma_g) - lgamma(1 - sigma_g)
+      for (int j = 0; j < K; j++) v += lt[njv[t * ks + j]];
       v += b.logV[(((size_t)t * 2 + 1) * ntm + (K - 1)) * G + g];
       os[e] = v;
     }
@@ -498,20 +452,79 @@ __global__ void __launch_bounds__(128, 7) update_kernel(DevBatch b, UpdArgs ua, 
       }
     }
   }
-  __threadfence_block();
-  bar_arrive2(nth);  // beta is final: the serial warp may run the horseshoe
 
   (void)P;
   (void)y;
   (void)ss;
 }
 
+// ================= horseshoe, utils_ct.cpp:876-915 =================
+// lambda_h | beta, tau (slice step), tau | beta, lambda (truncated-gamma inverse CDF), one thread
+// per chain.  A strictly serial chain of ~10 transcendental calls and an incomplete-gamma
+// inversion: inside update_kernel it sat on the chain's critical path with one active lane;
+// here the chains fill whole warps and run beside the gamma draws (nothing reads
+// lambda / tau / sigma_beta before the next iteration's beta step).
+__device__ __noinline__ void horseshoe_chain(const DevBatch &b, const Rng &rng, int chain, int l) {
+  const int Q = b.Q, D = b.D;
+  const double *beta = b.beta + (size_t)chain * Q * D;
+  if (b.model.noprog != 1 && b.model.hsp == 1) {
+    double *sigma_beta = b.sigma_beta + (size_t)chain * Q * D;
+    const int len = Q * D;
+    double *lambda = b.lambda + (size_t)chain * len;
+    double tau = b.tau[chain];
+    #pragma unroll 1
+    for (int k = 0; k < len; k++) {
+      double u0, u1;
+      { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_HS_LAMBDA, 0, (uint32_t)k, 0); u0 = r2_.x; u1 = r2_.y; }
+      double et = 1.0 / (lambda[k] * lambda[k]);
+      const double upsi = u0 * (1.0 / (1.0 + et));
+      const double tempps = (beta[k] * beta[k]) / (2.0 * tau * tau);
+      const double ub = (1.0 - upsi) / upsi;
+      double Fub = 1.0 - upd_exp(-tempps * ub);
+      if (Fub < 1e-4) Fub = 1e-4;
+      const double up = u1 * Fub;
+      et = -upd_log(1.0 - up) / tempps;
+      lambda[k] = 1.0 / sqrt(et);
+    }
+    double tempt = 0.0, u0, u1;
+    #pragma unroll 1
+    for (int k = 0; k < len; k++) {
+      const double r = beta[k] / lambda[k];
+      tempt += r * r;
+    }
+    tempt = tempt / 2.0;
+    double et = 1.0 / (tau * tau);
+    { const double2 r2_ = upd_u2(rng, l, TPPMX_SITE_HS_TAU, 0, 0, 0); u0 = r2_.x; u1 = r2_.y; }
+    const double utau = u0 * (1.0 / (1.0 + et));
+    const double ubt = (1.0 - utau) / utau;
+    const double shape = ((double)len + 1.0) / 2.0;
+    double Fubt = upd_gammainc(shape, ubt * tempt);
+    if (Fubt < 1e-4) Fubt = 1e-4;
+    const double ut = u1 * Fubt;
+    et = upd_gammaincinv(shape, ut) / tempt;
+    if (et < .0001) et = .0001;
+    tau = 1.0 / sqrt(et);
+    if (tau < .0001) tau = .0001;
+    b.tau[chain] = tau;
+    #pragma unroll 1
+    for (int k = 0; k < len; k++) sigma_beta[k] = lambda[k] * tau;
+  }
+}
+
 // ================= JJ, ss gamma draws, src/dm_ppmx_ct.cpp:1042-1055 =================
 // One thread per (chain, patient), flattened over the whole batch: the draws of a patient only
 // read its own loggamma row and ss, so nothing ties them to the chain's CTA — a separate small
 // kernel keeps the update kernel's instruction footprint down and fills the machine.
+// The first ceil(n_chains / 128) blocks run the horseshoe update instead (one thread per chain):
+// they are the long-latency blocks, so they are scheduled first.
 __global__ void __launch_bounds__(128) jjss_kernel(DevBatch b, uint64_t seed, int l) {
-  const size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nhs = (b.n_chains + 127) / 128;
+  if ((int)blockIdx.x < nhs) {
+    const int chain = blockIdx.x * 128 + threadIdx.x;
+    if (chain < b.n_chains) horseshoe_chain(b, make_rng(seed, b.chain_id[chain]), chain, l);
+    return;
+  }
+  const size_t gi = (size_t)(blockIdx.x - nhs) * blockDim.x + threadIdx.x;
   if (gi >= (size_t)b.n_chains * b.nobs) return;
   const int chain = (int)(gi / b.nobs), i = (int)(gi - (size_t)chain * b.nobs);
   const int ds = b.chain_ds[chain], D = b.D;
