@@ -47,6 +47,12 @@ struct tppmx_ctx {
   // predictive step) run beside the updates that do not feed them
   cudaStream_t side = nullptr;
   cudaEvent_t ev_sweep = nullptr, ev_upd = nullptr, ev_side = nullptr;
+  // third stream of tppmx_batch_run: the horseshoe update (a ~100 us serial chain per chain that
+  // nothing reads before the NEXT iteration's beta step) runs beside the gamma draws, the
+  // summaries and the next sweep
+  cudaStream_t hs = nullptr;
+  cudaEvent_t ev_hs_go = nullptr, ev_hs_done = nullptr;
+  bool hs_pending = false;
 };
 static void ctx_release(tppmx_ctx *c) {
   cudaSetDevice(c->device);
@@ -55,6 +61,9 @@ static void ctx_release(tppmx_ctx *c) {
   if (c->ev_sweep) cudaEventDestroy(c->ev_sweep);
   if (c->ev_upd) cudaEventDestroy(c->ev_upd);
   if (c->ev_side) cudaEventDestroy(c->ev_side);
+  if (c->hs) cudaStreamDestroy(c->hs);
+  if (c->ev_hs_go) cudaEventDestroy(c->ev_hs_go);
+  if (c->ev_hs_done) cudaEventDestroy(c->ev_hs_done);
   arena_free(c->spare);
   delete c;
 }
@@ -116,7 +125,10 @@ extern "C" int tppmx_create(tppmx_ctx **out, int device) {
       cudaStreamCreate(&c->side) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_sweep, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_upd, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreate(&c->hs) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_hs_go, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_hs_done, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return TPPMX_ERR_CUDA;
   }
@@ -1015,11 +1027,25 @@ extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, i
 
 // ev_after_update (optional): recorded between the update kernel and the gamma draws, so that work
 // which only needs eta*, beta, (Theta,Sigma), (sigma,kappa) can start beside the draws
-static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launches, cudaEvent_t ev_after_update = nullptr) {
+// the main stream rejoins a horseshoe update still running on the third stream
+static int hs_join(tppmx_ctx *ctx) {
+  if (ctx->hs_pending) {
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_hs_done, 0));
+    ctx->hs_pending = false;
+  }
+  return TPPMX_OK;
+}
+
+// overlap_hs: run the horseshoe update on the context's third stream (the caller must hs_join()
+// before anything but the sweep / summaries touches the batch again); otherwise it runs in the
+// first blocks of the gamma-draw kernel.
+static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launches, cudaEvent_t ev_after_update = nullptr,
+                         bool overlap_hs = false) {
   tppmx_ctx *ctx = b->ctx;
   const DevBatch &d = b->d;
   if (d.model.cohesion == 2 && d.ncat > 0)
     return fail(ctx, TPPMX_ERR_ARG, "the (sigma,kappa) update needs ncat == 0 (as the reference, dm_ppmx_ct.cpp:942)");
+  RC(hs_join(ctx));  // the beta steps read sigma_beta of the previous horseshoe update
   const int nth = 128;  // 3 worker warps + 1 serial warp (update.cuh)
   const size_t smem = sizeof(double) * (64 + (size_t)d.T * d.D * d.D + 16 + 2 * TPPMX_MAXD * TPPMX_MAXQ);
   if (d.D == 3)
@@ -1029,7 +1055,18 @@ static int update_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int *launc
   if (ev_after_update) CK(ctx, cudaEventRecord(ev_after_update, ctx->stream));
   const size_t npat = (size_t)d.n_chains * d.nobs;
   const unsigned nhs = (unsigned)((d.n_chains + 127) / 128);  // horseshoe blocks (update.cuh)
-  jjss_kernel<<<(unsigned)((npat + 127) / 128) + nhs, 128, 0, ctx->stream>>>(d, seed, iter);
+  const bool hs_on = d.model.noprog != 1 && d.model.hsp == 1;
+  if (overlap_hs && hs_on) {
+    CK(ctx, cudaEventRecord(ctx->ev_hs_go, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(ctx->hs, ctx->ev_hs_go, 0));
+    horseshoe_kernel<<<nhs, 128, 0, ctx->hs>>>(d, seed, iter);
+    CK(ctx, cudaEventRecord(ctx->ev_hs_done, ctx->hs));
+    ctx->hs_pending = true;
+    jjss_kernel<<<(unsigned)((npat + 127) / 128), 128, 0, ctx->stream>>>(d, seed, iter, 0);
+    (*launches) += 1;
+  } else {
+    jjss_kernel<<<(unsigned)((npat + 127) / 128) + nhs, 128, 0, ctx->stream>>>(d, seed, iter, (int)nhs);
+  }
   (*launches) += 2;
   CK(ctx, cudaGetLastError());
   return TPPMX_OK;
@@ -1077,7 +1114,7 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
     RC(sweep_launch(b, seed, l, 1, false, &launches));
     const bool saved = (do_psm || do_pred) && (l > burn - 1) && ((l + 1) % thin == 0);  // :1060
     if (!saved) {
-      RC(update_launch(b, seed, l, &launches));
+      RC(update_launch(b, seed, l, &launches, nullptr, true));
       continue;
     }
     if (do_psm) {
@@ -1085,7 +1122,7 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
       CK(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_sweep, 0));
       RC(accumulate_launch(b, seed, l, 1, 0, &launches, ctx->side));
     }
-    RC(update_launch(b, seed, l, &launches, do_pred ? ctx->ev_upd : nullptr));
+    RC(update_launch(b, seed, l, &launches, do_pred ? ctx->ev_upd : nullptr, true));
     if (do_pred) {
       CK(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_upd, 0));
       RC(accumulate_launch(b, seed, l, 0, 1, &launches, ctx->side));
@@ -1094,6 +1131,7 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
     side_pending = true;
   }
   if (side_pending) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+  RC(hs_join(ctx));
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;

@@ -515,10 +515,14 @@ __device__ __noinline__ void horseshoe_chain(const DevBatch &b, const Rng &rng, 
 // One thread per (chain, patient), flattened over the whole batch: the draws of a patient only
 // read its own loggamma row and ss, so nothing ties them to the chain's CTA — a separate small
 // kernel keeps the update kernel's instruction footprint down and fills the machine.
-// The first ceil(n_chains / 128) blocks run the horseshoe update instead (one thread per chain):
-// they are the long-latency blocks, so they are scheduled first.
-__global__ void __launch_bounds__(128) jjss_kernel(DevBatch b, uint64_t seed, int l) {
-  const int nhs = (b.n_chains + 127) / 128;
+// The first nhs = ceil(n_chains / 128) blocks run the horseshoe update instead (one thread per
+// chain): they are the long-latency blocks, so they are scheduled first.  nhs = 0 when the
+// horseshoe runs as its own kernel on another stream (tppmx_batch_run).
+__global__ void __launch_bounds__(128) horseshoe_kernel(DevBatch b, uint64_t seed, int l) {
+  const int chain = blockIdx.x * 128 + threadIdx.x;
+  if (chain < b.n_chains) horseshoe_chain(b, make_rng(seed, b.chain_id[chain]), chain, l);
+}
+__global__ void __launch_bounds__(128) jjss_kernel(DevBatch b, uint64_t seed, int l, int nhs) {
   if ((int)blockIdx.x < nhs) {
     const int chain = blockIdx.x * 128 + threadIdx.x;
     if (chain < b.n_chains) horseshoe_chain(b, make_rng(seed, b.chain_id[chain]), chain, l);
