@@ -350,6 +350,11 @@ int tppmx_batch_summaries(tppmx_batch *b, const double *util_w, double *psm, dou
 int tppmx_batch_summaries_device(tppmx_batch *b, const double *util_w, double **psm, double **pi_mean,
                                  double **utility, int32_t **best_arm);
 int tppmx_batch_reset_summaries(tppmx_batch *b);
+/* npc of R/countUT.R:26-53 from the predictive means of the last tppmx_batch_summaries[_device]
+ * call: per replicate dataset, how many new patients have arg max_k E[pipred(pp, k, trtsgn_pp)]
+ * equal to the observed outcome.  trtsgn (assigned arm) and outcome (observed category) are
+ * [n_datasets][npred], 0-based; npc_out is [n_datasets]. */
+int tppmx_batch_npc(tppmx_batch *b, const int32_t *trtsgn, const int32_t *outcome, int32_t *npc_out);
 
 #ifdef __cplusplus
 }

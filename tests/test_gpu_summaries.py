@@ -49,6 +49,13 @@ def test_psm_and_predictive_means(ctx, name):
     util = np.einsum("k,npkt->ntp", w, pi_ref)
     np.testing.assert_allclose(out["utility"], util, rtol=1e-12)
     assert (out["best_arm"] == util.argmax(axis=1)).all()
+    # npc (R/countUT.R:26-53): which.max over categories under the assigned arm == observed outcome
+    rng = np.random.default_rng(8)
+    trt = rng.integers(0, dims.T, (nd, dims.npred))
+    obs = rng.integers(0, dims.D, (nd, dims.npred))
+    want_npc = [sum(int(np.argmax(out["pi_mean"][ds, pp, :, trt[ds, pp]]) == obs[ds, pp]) for pp in range(dims.npred))
+                for ds in range(nd)]
+    assert b.npc(trt, obs).tolist() == want_npc
     # diagonal of the co-clustering matrix is 1 for real patients
     for ds in range(nd):
         for t in range(dims.T):

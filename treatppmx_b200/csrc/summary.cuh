@@ -65,6 +65,36 @@ __global__ void summarise_kernel(DevBatch b, const int *psm, const int *psm_n, c
   }
 }
 
+// npc (R/countUT.R:26-53; Ma, Stingo & Hobbs 2019): per replicate dataset, the number of new
+// patients whose most probable outcome category under the arm they were assigned to by design
+// (which.max over the D predictive means, first maximum on ties, :37-38) equals the outcome that
+// was observed.  pi_mean is the [npred x D x T] col-major posterior mean of pipred.
+__global__ void npc_kernel(DevBatch b, const double *pi_mean, const int *trtsgn, const int *outcome, int *npc) {
+  const int ds = blockIdx.x, T = b.T, D = b.D, npred = b.npred;
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const size_t n1 = (size_t)npred * D * T;
+  int mine = 0;
+  for (int pp = threadIdx.x; pp < npred; pp += blockDim.x) {
+    const int t = trtsgn[(size_t)ds * npred + pp];
+    if (t < 0 || t >= T) continue;
+    int best = 0;
+    double pb = -INFINITY;
+    for (int k = 0; k < D; k++) {
+      const double v = pi_mean[(size_t)ds * n1 + pp + (size_t)npred * (k + (size_t)D * t)];
+      if (v > pb) {
+        pb = v;
+        best = k;
+      }
+    }
+    mine += (best == outcome[(size_t)ds * npred + pp]);
+  }
+  atomicAdd(&cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) npc[ds] = cnt;
+}
+
 // per-dataset save counters: how many (chain, save) pairs went into the sums
 __global__ void count_saves_kernel(DevBatch b, int *psm_n, int *pi_n, int do_psm, int do_pi) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;

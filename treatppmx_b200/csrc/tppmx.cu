@@ -1363,6 +1363,28 @@ extern "C" int tppmx_batch_summaries(tppmx_batch *b, const double *util_w, doubl
   return TPPMX_OK;
 }
 
+extern "C" int tppmx_batch_npc(tppmx_batch *b, const int32_t *trtsgn, const int32_t *outcome, int32_t *npc_out) {
+  if (!b || !trtsgn || !outcome || !npc_out) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (d.npred < 1) return fail(ctx, TPPMX_ERR_ARG, "batch has npred == 0");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)d.n_datasets * d.npred;
+  int *dbuf = nullptr;
+  CK(ctx, cudaMalloc(&dbuf, sizeof(int) * (2 * n + d.n_datasets)));
+  cudaError_t e = cudaMemcpyAsync(dbuf, trtsgn, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dbuf + n, outcome, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    npc_kernel<<<d.n_datasets, 128, 0, ctx->stream>>>(d, b->pi_mean, dbuf, dbuf + n, dbuf + 2 * n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(npc_out, dbuf + 2 * n, sizeof(int) * d.n_datasets, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dbuf);
+  if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("npc: ") + cudaGetErrorString(e));
+  return TPPMX_OK;
+}
+
 // ---- drop-in for dm_ppmx_ct (reference src/dm_ppmx_ct.cpp:10-1472), one chain -----------------------
 extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppmx_ppmxct_out *o) {
   if (!ctx || ctx->closed) return TPPMX_ERR_ARG;

@@ -194,6 +194,17 @@ class Batch:
                                                         f(ut, c_dp), f(ba, c_ip)))
         return dict(psm=psm, pi_mean=None if pim is None else pim.transpose(0, 3, 2, 1), utility=ut, best_arm=ba)
 
+    def npc(self, trtsgn, outcome):
+        """npc of R/countUT.R:26-53 per replicate dataset, from the predictive means of the last
+        summaries() call: trtsgn / outcome are [n_datasets, npred], 0-based."""
+        nd, npred = len(self.datasets), self.dims.npred
+        t = np.ascontiguousarray(np.asarray(trtsgn, dtype=np.int32).reshape(nd, npred))
+        o = np.ascontiguousarray(np.asarray(outcome, dtype=np.int32).reshape(nd, npred))
+        out = np.zeros(nd, dtype=np.int32)
+        self.ctx.check(self.ctx.L.tppmx_batch_npc(self.h, t.ctypes.data_as(c_ip), o.ctypes.data_as(c_ip),
+                                                  out.ctypes.data_as(c_ip)))
+        return out
+
     def summaries_device(self, util_w=None):
         """The same arrays left on the device as DeviceArray views (C-order shapes as in summaries(),
         pi_mean as [nd, T, D, npred])."""
