@@ -128,6 +128,28 @@ static __device__ __noinline__ double fast_lik(const double *E, const double *Z,
   return w;
 }
 
+// Register version for the pre-pass: the patient's exp(zb) / log JJ stay in registers while the
+// lane walks over the candidate clusters (one L2 round trip per patient instead of one per
+// table entry).  DR = 3 or TPPMX_MAXD.
+template <int DR>
+__device__ __forceinline__ double fast_lik_reg(const double *E, const double (&Z)[DR], const double (&ljj)[DR], int D) {
+  double w = 0.0;
+#pragma unroll
+  for (int k = 0; k < DR; k += 3) {
+    if (k < D) {
+      const bool h1 = (k + 1 < DR) && (k + 1 < D), h2 = (k + 2 < DR) && (k + 2 < D);
+      const double g0 = E[k] * Z[k];
+      const double g1 = h1 ? E[k + 1] * Z[(k + 1 < DR) ? k + 1 : k] : 1.0;
+      const double g2 = h2 ? E[k + 2] * Z[(k + 2 < DR) ? k + 2 : k] : 1.0;
+      const double l0 = lgamma_pos(g0), l1 = lgamma_pos(g1), l2 = lgamma_pos(g2);
+      w += fma(g0, ljj[k], -l0);
+      if (h1) w += fma(g1, ljj[(k + 1 < DR) ? k + 1 : k], -l1);
+      if (h2) w += fma(g2, ljj[(k + 2 < DR) ? k + 2 : k], -l2);
+    }
+  }
+  return w;
+}
+
 // cold path: a unit of the warp has more than LPU candidate clusters (`mine`).  Scores in
 // chunks through U.wsc; returns newci for the units with `mine`.
 template <int LPU>
@@ -317,50 +339,91 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       }
     }
     __syncwarp();
-    if (live) {
-      // phase A, per patient (one lane each): allocation uniform, sum_p x^2, exp(beta'z), log JJ
-      for (int it = ul; it < nt; it += LPU) {
-        const int i = patp[it];
-        const double *xi = g_x + (size_t)i * P;
-        double qx = 0.0;
-        for (int p = 0; p < P; p++) qx = fma(xi[p], xi[p], qx);
-        double uu, u1;
-        rng_u2(rng, l, TPPMX_SITE_ALLOC_U, tt, (uint32_t)i, 0, uu, u1);
-        uq[it] = uu;
-        uq[uqs + it] = qx;
-        if (!NOLIK) {
-          const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
-          const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
-          for (int k = 0; k < D; k++) {
-            double acc = 0.0;
-            for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
-            g_ez[(size_t)i * D + k] = fast_exp(acc);
-            g_ljj[(size_t)i * D + k] = fast_log(JJ[k]);
+    if constexpr (BIG) {
+      // long arms: one lane per patient keeps exp(beta'z) / log JJ in registers while it walks over
+      // the candidate clusters (one L2 round trip per patient; the arm's rows are not cache resident)
+      if (live) {
+        const int ntot = K + CC;
+        for (int it = ul; it < nt; it += LPU) {
+          const int i = patp[it];
+          const double *xi = g_x + (size_t)i * P;
+          double qx = 0.0;
+          for (int p = 0; p < P; p++) qx = fma(xi[p], xi[p], qx);
+          double uu, u1;
+          rng_u2(rng, l, TPPMX_SITE_ALLOC_U, tt, (uint32_t)i, 0, uu, u1);
+          uq[it] = uu;
+          uq[uqs + it] = qx;
+          if (!NOLIK) {
+            const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
+            const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
+            double Z[DR], ljj[DR];
+#pragma unroll
+            for (int k = 0; k < DR; k++) {
+              Z[k] = 1.0;
+              ljj[k] = 0.0;
+              if (k < D) {
+                double acc = 0.0;
+                for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
+                Z[k] = fast_exp(acc);
+                ljj[k] = fast_log(JJ[k]);
+                g_ez[(size_t)i * D + k] = Z[k];
+                g_ljj[(size_t)i * D + k] = ljj[k];
+              }
+            }
+            for (int c = 0; c < ntot; c++) {
+              const int cl = colmap(c, K);
+              lik[(size_t)cl * ntp + it] = fast_lik_reg<DR>(U.E + cl * D, Z, ljj, D);
+            }
           }
         }
       }
-    }
-    __syncwarp();
-    if (live && !NOLIK) {
-      // phase B, per (candidate cluster, patient) pair, flattened over the unit's lanes so that
-      // every lane carries the same number of likelihood terms whatever n_t and K are (a loop
-      // over patients with an inner loop over clusters leaves 20-40 % of the lanes idle):
-      // pair e -> (c, it) = (e / nt, e % nt), kept incrementally; consecutive lanes write
-      // consecutive rows of one table column
-      const int npair = (K + CC) * nt;
-      int c = ul / nt, it = ul - c * nt;
-      for (int e = ul; e < npair; e += LPU) {
-        const int i = patp[it];
-        const int cl = colmap(c, K);
-        lik[(size_t)cl * ntp + it] = fast_lik(U.E + cl * D, g_ez + (size_t)i * D, g_ljj + (size_t)i * D, D);
-        it += LPU;
-        while (it >= nt) {
-          it -= nt;
-          c += 1;
+      __syncwarp();
+    } else {
+      if (live) {
+        // phase A, per patient (one lane each): allocation uniform, sum_p x^2, exp(beta'z), log JJ
+        for (int it = ul; it < nt; it += LPU) {
+          const int i = patp[it];
+          const double *xi = g_x + (size_t)i * P;
+          double qx = 0.0;
+          for (int p = 0; p < P; p++) qx = fma(xi[p], xi[p], qx);
+          double uu, u1;
+          rng_u2(rng, l, TPPMX_SITE_ALLOC_U, tt, (uint32_t)i, 0, uu, u1);
+          uq[it] = uu;
+          uq[uqs + it] = qx;
+          if (!NOLIK) {
+            const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
+            const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
+            for (int k = 0; k < D; k++) {
+              double acc = 0.0;
+              for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
+              g_ez[(size_t)i * D + k] = fast_exp(acc);
+              g_ljj[(size_t)i * D + k] = fast_log(JJ[k]);
+            }
+          }
         }
       }
+      __syncwarp();
+      if (live && !NOLIK) {
+        // phase B, per (candidate cluster, patient) pair, flattened over the unit's lanes so that
+        // every lane carries the same number of likelihood terms whatever n_t and K are (a loop
+        // over patients with an inner loop over clusters leaves 20-40 % of the lanes idle):
+        // pair e -> (c, it) = (e / nt, e % nt), kept incrementally; consecutive lanes write
+        // consecutive rows of one table column
+        const int npair = (K + CC) * nt;
+        int c = ul / nt, it = ul - c * nt;
+        for (int e = ul; e < npair; e += LPU) {
+          const int i = patp[it];
+          const int cl = colmap(c, K);
+          lik[(size_t)cl * ntp + it] = fast_lik(U.E + cl * D, g_ez + (size_t)i * D, g_ljj + (size_t)i * D, D);
+          it += LPU;
+          while (it >= nt) {
+            it -= nt;
+            c += 1;
+          }
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
 
     // =========================== sequential reallocation steps ===========================
     double dV = dV_of(K);
