@@ -80,11 +80,14 @@ constexpr unsigned TPPMX_FULL = 0xffffffffu;
 // The units of a warp run CONVERGED: every collective uses the full mask (width-LPU shuffles
 // keep the units apart) and unit-specific work is predicated.  Rare events (singleton removal,
 // cluster birth, > LPU candidates) are entered warp-uniformly through __any_sync.
-template <int LPU>
-__device__ __forceinline__ float unit_maxf(float v) {
-#pragma unroll
-  for (int o = LPU / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(TPPMX_FULL, v, o, LPU));
-  return v;
+// maximum over the unit's lanes: one redux.sync on an order-preserving integer image of the
+// float instead of log2(LPU) shuffle + max levels (the step's dependent chain is what bounds it)
+__device__ __forceinline__ float unit_maxf(float v, unsigned unit_mask) {
+  int i = __float_as_int(v);
+  i ^= (i >> 31) & 0x7fffffff;
+  i = __reduce_max_sync(unit_mask, i);
+  i ^= (i >> 31) & 0x7fffffff;
+  return __int_as_float(i);
 }
 template <int LPU>
 __device__ __forceinline__ double unit_sum(double v) {
@@ -219,6 +222,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   extern __shared__ __align__(16) char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPU, ul = lane % LPU;
+  const unsigned unit_mask = (LPU == 32) ? TPPMX_FULL : (((1u << (LPU & 31)) - 1u) << (sub * LPU));
   const int unit_raw = blockIdx.x * UPW + sub;
   const bool valid = unit_raw < fa.n_units;
   const int unit = valid ? unit_raw : 0;  // lanes of a missing unit shadow unit 0 read-only
@@ -569,7 +573,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         const double w = act0 ? dV + lognp[n] + simscale * d + likv : -INFINITY;
         // the shift only has to be common to the unit's lanes and close to the maximum: the
         // float-rounded maximum costs a quarter of the shuffles of an fp64 max
-        const double wmax = (double)unit_maxf<LPU>((float)w);
+        const double wmax = (double)unit_maxf((float)w, unit_mask);
         const double e0 = act0 ? fast_exp(w - wmax) : 0.0;
         const double cum = unit_incl_scan<LPU>(e0, ul);
         const double den = __shfl_sync(TPPMX_FULL, cum, LPU - 1, LPU);
