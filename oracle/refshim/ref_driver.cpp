@@ -36,15 +36,44 @@ Rcpp::List prior_ppmx_core(int iter, int burn, int thin, int nobs, int PPMx, int
                            arma::vec similparam, arma::vec curr_cluster, arma::vec card_cluster,
                            int ncluster_curr);
 
-/* ---- tape ------------------------------------------------------------------------------------- */
+/* ---- tape (per thread: bench.py times one chain per host thread) ------------------------------- */
 namespace {
-const double *g_kind = nullptr, *g_val = nullptr, *g_aux = nullptr;
-long g_n = 0, g_pos = 0;
-std::string g_err;
+thread_local const double *g_kind = nullptr, *g_val = nullptr, *g_aux = nullptr;
+thread_local long g_n = 0, g_pos = 0;
+thread_local std::string g_err;
+/* With no tape set (ref_rng_free) the variates come from a free-running generator instead: the
+ * timing legs of bench.py need R's RNG replaced by SOMETHING, not by particular values.
+ * splitmix64 uniforms, Box-Muller normals, Marsaglia-Tsang gammas. */
+thread_local uint64_t g_rng = 0x9E3779B97F4A7C15ull;
+double fr_unif() {
+  uint64_t z = (g_rng += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return ((double)(z >> 11) + 0.5) * 0x1.0p-53;
+}
+double fr_norm() { return std::sqrt(-2.0 * std::log(fr_unif())) * std::cos(6.283185307179586 * fr_unif()); }
+double fr_gamma(double a) {
+  double boost = 1.0;
+  if (a < 1.0) {
+    boost = std::exp(std::log(fr_unif()) / a);
+    a += 1.0;
+  }
+  const double d = a - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
+  for (;;) {
+    const double x = fr_norm();
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    const double u = fr_unif(), x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2 || std::log(u) < 0.5 * x2 + d * (1.0 - v + std::log(v))) return boost * d * v;
+  }
+}
 }  // namespace
 
 namespace refshim {
 double tape_pop(int kind, double aux) {
+  if (!g_kind) return kind == TAPE_U ? fr_unif() : kind == TAPE_N ? fr_norm() : fr_gamma(aux);
   char buf[256];
   if (g_pos >= g_n) {
     snprintf(buf, sizeof buf, "tape exhausted at draw %ld (wanted kind %d)", g_pos, kind);
@@ -89,6 +118,12 @@ extern "C" {
 /* kind[i] in {1 uniform, 2 normal, 3 gamma(shape aux[i], scale 1)}, val[i] the variate */
 void ref_tape_set(const double *kind, const double *val, const double *aux, long n) {
   g_kind = kind; g_val = val; g_aux = aux; g_n = n; g_pos = 0;
+}
+/* no tape: free-running stand-in generator, seeded per thread (timing only) */
+void ref_rng_free(uint64_t seed) {
+  g_kind = g_val = g_aux = nullptr;
+  g_n = g_pos = 0;
+  g_rng = seed * 0x9E3779B97F4A7C15ull + 1;
 }
 long ref_tape_pos(void) { return g_pos; }
 const char *ref_last_error(void) { return g_err.c_str(); }

@@ -28,7 +28,12 @@ RETURN_NAMES = ("eta", "beta", "sigma_ngg", "kappa_ngg", "eta_acc", "beta_acc", 
 
 def reference_args(name, iters, burn, thin, dense_V):
     model, dims, shared, dsets, labels, nclu, betas = build_case(name)
-    ds = dsets[0]
+    args, logV = reference_args_of(model, dims, shared, dsets[0], labels, nclu, betas[0], iters, burn, thin, dense_V)
+    return args, logV, (model, dims, shared, dsets, labels, nclu, betas)
+
+
+def reference_args_of(model, dims, shared, ds, labels, nclu, beta0, iters, burn, thin, dense_V):
+    """The reference's 42 arguments (src/dm_ppmx_ct.cpp:10-23) for one dataset of a problem."""
     n_a = np.bincount(ds.treat, minlength=dims.T).astype(float)
     Vwm = logV = None
     if model.cohesion == 2:
@@ -54,10 +59,10 @@ def reference_args(name, iters, burn, thin, dense_V):
         zpred=ds.zpred, noprog=model.noprog, xcon=ds.xcon.ravel(), xcat=ds.xcat.astype(float).ravel(),
         xconp=ds.xconp.ravel(), xcatp=ds.xcatp.astype(float).ravel(), npred=dims.npred, similparam=sp,
         hP0_mu0=[model.hP0_mu0[k] for k in range(dims.D)], hP0_nu0=model.hP0_nu0, hP0_s0=model.hP0_s0,
-        hP0_Lambda0=model.hP0_Lambda0, upd_hier=model.upd_hier, initbeta=betas[0], hsp=model.hsp,
+        hP0_Lambda0=model.hP0_Lambda0, upd_hier=model.upd_hier, initbeta=beta0, hsp=model.hsp,
         mhtunepar=[model.mhtune_eta, model.mhtune_beta], A=dims.T, n_a=n_a, curr_cluster=labels.astype(float),
         card_cluster=card, ncluster_curr=nclu.astype(float))
-    return args, logV, (model, dims, shared, dsets, labels, nclu, betas)
+    return args, logV
 
 
 def oracle_run(case, iters, burn, thin, seed):
@@ -169,11 +174,16 @@ class RefLib:
         self._keep = [kind, val, aux]
         self.L.ref_tape_set(self._p(kind), self._p(val), self._p(aux), len(val))
 
+    def rng_free(self, seed: int):
+        """no tape on the calling thread: variates from the driver's free-running generator (timing)"""
+        self.L.ref_rng_free(C.c_uint64(seed))
+
     def tape_pos(self) -> int:
         return self.L.ref_tape_pos()
 
-    def dm_ppmx_ct(self, args: dict, tape: Tape) -> dict:
-        """The reference's dm_ppmx_ct(42 arguments) -> its 18-element list, with `tape` as R's RNG."""
+    def dm_ppmx_ct(self, args: dict, tape, outputs: bool = True) -> dict:
+        """The reference's dm_ppmx_ct(42 arguments) -> its 18-element list, with `tape` as R's RNG
+        (tape = an int seeds the free-running stand-in generator instead: timing runs)."""
         a = args
         f = lambda x, order="F": np.require(np.asarray(x, dtype=np.float64), requirements=[order, "A", "O"])
         y, z = f(a["y"]), f(a["z"])
@@ -200,7 +210,10 @@ class RefLib:
         P = lambda x: self._p(x) if x is not None else C.POINTER(C.c_double)()
         (treat, catvec, grid, V, y, z, zpred, xcon, xcat, xconp, xcatp, simil, mu0, initbeta, mht, n_a, cc, card,
          nclu) = ins
-        self.set_tape(tape.kind, tape.val, tape.aux)
+        if isinstance(tape, int):
+            self.rng_free(tape)
+        else:
+            self.set_tape(tape.kind, tape.val, tape.aux)
         i, d = C.c_int, C.c_double
         rc = self.L.ref_dm_ppmx_ct(
             i(a["iter"]), i(a["burn"]), i(a["thin"]), i(n), P(treat), i(a["PPMx"]), i(a["ncon"]), i(a["ncat"]),
@@ -212,7 +225,7 @@ class RefLib:
             P(cc), P(card), P(nclu), i(ntmax),
             *[P(out[k]) for k in RETURN_NAMES])
         if rc != 0:
-            raise RuntimeError(f"reference run failed after {self.tape_pos()} of {len(tape)} draws: {self.err()}")
+            raise RuntimeError(f"reference run failed after {self.tape_pos()} draws: {self.err()}")
         out["tape_used"] = self.tape_pos()
         out["WAIC"] = float(out["WAIC"][0])
         return out

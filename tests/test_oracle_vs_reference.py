@@ -222,3 +222,18 @@ def test_reference_prior_ppmx_core_on_the_oracle_tape(ref, cohesion, similarity,
     assert ref.tape_pos() == len(u)
     assert nclu.tolist() == want_K
     np.testing.assert_array_equal(njout, np.array(want_nj).T)
+
+
+def test_reference_runs_on_the_free_running_generator(ref):
+    """bench.py's timing leg: no tape, R's RNG replaced by the driver's own generator.  The run must
+    be a valid chain (this is not a parity check)."""
+    args, _, case = refrun.reference_args("default_ngg", 30, 10, 2, True)
+    out = ref.dm_ppmx_ct(args, 4242)
+    dims = case[1]
+    n_a = np.bincount(case[3][0].treat, minlength=dims.T)
+    assert ((out["nclus"] >= 1) & (out["nclus"] <= n_a[:, None])).all()
+    np.testing.assert_allclose(out["pi"].sum(axis=1), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(out["pipred"].sum(axis=1), 1.0, rtol=1e-12)
+    assert np.isfinite(out["WAIC"]) and np.isfinite(out["lpml"]).all()
+    out2 = ref.dm_ppmx_ct(args, 4242)
+    np.testing.assert_array_equal(out["cl_lab"], out2["cl_lab"])      # seeded: reproducible
