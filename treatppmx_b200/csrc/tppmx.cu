@@ -21,6 +21,14 @@
 
 using namespace tppmx;
 
+// Host <-> device copy ordered on the context's own stream, then waited for.  The library never
+// uses the legacy default stream (whose copies would wait for, and stall, every other context's
+// streams): contexts on different host threads overlap freely.
+static cudaError_t cpy_sync(cudaStream_t st, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+  const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+}
+
 // One device allocation + one pinned host mirror of its upload region per batch.  A destroyed
 // batch leaves its arena with the context, so create/destroy cycles (one batch per group of
 // replicate datasets) cost no cudaMalloc / cudaFree after the first.
@@ -121,12 +129,12 @@ extern "C" int tppmx_create(tppmx_ctx **out, int device) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return TPPMX_ERR_CUDA;
   tppmx_ctx *c = new tppmx_ctx();
   c->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess ||
-      cudaStreamCreate(&c->side) != cudaSuccess ||
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_sweep, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_upd, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess ||
-      cudaStreamCreate(&c->hs) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->hs, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_hs_go, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_hs_done, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
@@ -158,12 +166,12 @@ extern "C" int tppmx_probe_math(tppmx_ctx *ctx, int32_t which, const double *x, 
   double *dx = nullptr, *dy = nullptr;
   CK(ctx, cudaMalloc(&dx, sizeof(double) * n));
   CK(ctx, cudaMalloc(&dy, sizeof(double) * n));
-  cudaError_t e = cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+  cudaError_t e = cpy_sync(ctx->stream, dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     probe_math_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(which, dx, n, dy);
     e = cudaStreamSynchronize(ctx->stream);
   }
-  if (e == cudaSuccess) e = cudaMemcpy(out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cpy_sync(ctx->stream, out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
   cudaFree(dx);
   cudaFree(dy);
   if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("probe_math: ") + cudaGetErrorString(e));
@@ -669,13 +677,25 @@ extern "C" int tppmx_batch_init(tppmx_batch *b, uint64_t seed, const int32_t *in
 // ---- state upload / download (reference layouts <-> device layouts) --------------------------
 template <class T>
 static int h2d(tppmx_batch *b, T *dst, const std::vector<T> &h) {
-  CK(b->ctx, cudaMemcpy(dst, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  CK(b->ctx, cpy_sync(b->ctx->stream, dst, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   return TPPMX_OK;
 }
 template <class T>
 static int d2h(tppmx_batch *b, std::vector<T> &h, const T *src) {
-  CK(b->ctx, cudaMemcpy(h.data(), src, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+  CK(b->ctx, cpy_sync(b->ctx->stream, h.data(), src, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
   return TPPMX_OK;
+}
+
+// Device -> caller memory.  Caller buffers are pageable, and a pageable cudaMemcpy crawls (~2 GB/s)
+// and holds driver locks other host threads need; large results therefore land in the batch's
+// pinned mirror first (free once the upload of tppmx_batch_create has been consumed, which
+// stream order guarantees) and are copied out by the host.
+static cudaError_t d2h_out(tppmx_batch *b, void *dst, const void *src, size_t bytes) {
+  cudaStream_t st = b->ctx->stream;
+  if (bytes < (64u << 10) || bytes > b->ar.hcap || !b->ar.hbase) return cpy_sync(st, dst, src, bytes, cudaMemcpyDeviceToHost);
+  const cudaError_t e = cpy_sync(st, b->ar.hbase, src, bytes, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) memcpy(dst, b->ar.hbase, bytes);
+  return e;
 }
 
 extern "C" int tppmx_batch_set_state(tppmx_batch *b, int32_t chain, const tppmx_state *s) {
@@ -746,7 +766,7 @@ extern "C" int tppmx_batch_set_state(tppmx_batch *b, int32_t chain, const tppmx_
   }
 #define PUT(field, dptr, count)                                                        \
   if (s->field && (count) > 0) {                                                       \
-    CK(b->ctx, cudaMemcpy((dptr) + (size_t)chain * (count), s->field, sizeof(*s->field) * (count), cudaMemcpyHostToDevice)); \
+    CK(b->ctx, cpy_sync(b->ctx->stream, (dptr) + (size_t)chain * (count), s->field, sizeof(*s->field) * (count), cudaMemcpyHostToDevice)); \
   }
   PUT(ss, d.ss, (size_t)n);
   PUT(beta, d.beta, (size_t)Q * D);
@@ -782,7 +802,7 @@ extern "C" int tppmx_batch_get_state(tppmx_batch *b, int32_t chain, tppmx_state 
     for (int t = 0; t < T; t++)
       for (int j = 0; j < nt; j++) s->nj[t + (size_t)T * j] = j < ks ? h[(size_t)t * ks + j] : 0;
   }
-  if (s->nclu) CK(b->ctx, cudaMemcpy(s->nclu, d.nclu + (size_t)chain * T, sizeof(int) * T, cudaMemcpyDeviceToHost));
+  if (s->nclu) CK(b->ctx, cpy_sync(b->ctx->stream, s->nclu, d.nclu + (size_t)chain * T, sizeof(int) * T, cudaMemcpyDeviceToHost));
   for (int which = 0; which < 2; which++) {
     double *dst = which ? s->sumx2 : s->sumx;
     if (!dst || P == 0) continue;
@@ -828,7 +848,7 @@ extern "C" int tppmx_batch_get_state(tppmx_batch *b, int32_t chain, tppmx_state 
   }
 #define GET(field, dptr, count)                                                        \
   if (s->field && (count) > 0) {                                                       \
-    CK(b->ctx, cudaMemcpy(s->field, (dptr) + (size_t)chain * (count), sizeof(*s->field) * (count), cudaMemcpyDeviceToHost)); \
+    CK(b->ctx, cpy_sync(b->ctx->stream, s->field, (dptr) + (size_t)chain * (count), sizeof(*s->field) * (count), cudaMemcpyDeviceToHost)); \
   }
   GET(ss, d.ss, (size_t)n);
   GET(beta, d.beta, (size_t)Q * D);
@@ -851,21 +871,30 @@ extern "C" int tppmx_batch_get_partitions(tppmx_batch *b, int32_t *labels, int32
   CK(b->ctx, cudaStreamSynchronize(b->ctx->stream));
   const int T = d.T, nt = d.ntmax;
   if (labels) {
-    std::vector<int> h((size_t)d.n_chains * st_labels(d));
-    RC(d2h(b, h, d.labels));
+    const size_t nlab = (size_t)d.n_chains * st_labels(d);
+    std::vector<int> hv;
+    const int *h;
+    if (nlab * sizeof(int) <= b->ar.hcap && b->ar.hbase) {  // through the pinned mirror, transposed from there
+      CK(b->ctx, cpy_sync(b->ctx->stream, b->ar.hbase, d.labels, nlab * sizeof(int), cudaMemcpyDeviceToHost));
+      h = reinterpret_cast<const int *>(b->ar.hbase);
+    } else {
+      hv.resize(nlab);
+      RC(d2h(b, hv, d.labels));
+      h = hv.data();
+    }
     for (int c = 0; c < d.n_chains; c++)
       for (int t = 0; t < T; t++)
         for (int it = 0; it < nt; it++)
           labels[(size_t)c * T * nt + t + (size_t)T * it] = h[((size_t)c * T + t) * nt + it];
   }
-  if (nclu) CK(b->ctx, cudaMemcpy(nclu, d.nclu, sizeof(int) * (size_t)d.n_chains * T, cudaMemcpyDeviceToHost));
+  if (nclu) CK(b->ctx, cpy_sync(b->ctx->stream, nclu, d.nclu, sizeof(int) * (size_t)d.n_chains * T, cudaMemcpyDeviceToHost));
   return TPPMX_OK;
 }
 
 // ---- launches ---------------------------------------------------------------------------------
 static int check_status(tppmx_batch *b) {
   std::vector<int> st((size_t)b->d.n_chains);
-  CK(b->ctx, cudaMemcpy(st.data(), b->d.status, st.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(b->ctx, cpy_sync(b->ctx->stream, st.data(), b->d.status, st.size() * sizeof(int), cudaMemcpyDeviceToHost));
   for (size_t c = 0; c < st.size(); c++)
     if (st[c] != 0) {
       char buf[160];
@@ -1155,7 +1184,7 @@ extern "C" int tppmx_batch_get_acceptance(tppmx_batch *b, int32_t chain, int32_t
       for (int j = 0; j < nt; j++) eta_acc[t + (size_t)T * j] = j < ks ? h[(size_t)t * ks + j] : 0;
   }
   if (beta_acc && d.Q > 0)
-    CK(b->ctx, cudaMemcpy(beta_acc, d.beta_flag + (size_t)chain * d.Q * d.D, sizeof(int) * d.Q * d.D, cudaMemcpyDeviceToHost));
+    CK(b->ctx, cpy_sync(b->ctx->stream, beta_acc, d.beta_flag + (size_t)chain * d.Q * d.D, sizeof(int) * d.Q * d.D, cudaMemcpyDeviceToHost));
   return TPPMX_OK;
 }
 
@@ -1203,9 +1232,9 @@ extern "C" int tppmx_score_patient(tppmx_batch *b, int32_t chain, int32_t arm, i
   score_kernel<<<1, 32, 0, ctx->stream>>>(d, b->scratch_chain, arm, it, seed, iter, dw, dw + W, dk);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   int K = 0;
-  if (e == cudaSuccess) e = cudaMemcpy(&K, dk, sizeof(int), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && logw_out) e = cudaMemcpy(logw_out, dw, sizeof(double) * (K + d.CC), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && prob_out) e = cudaMemcpy(prob_out, dw + W, sizeof(double) * (K + d.CC), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cpy_sync(ctx->stream, &K, dk, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && logw_out) e = cpy_sync(ctx->stream, logw_out, dw, sizeof(double) * (K + d.CC), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && prob_out) e = cpy_sync(ctx->stream, prob_out, dw + W, sizeof(double) * (K + d.CC), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("score_kernel: ") + cudaGetErrorString(e));
   if (K_out) *K_out = K;
   return TPPMX_OK;
@@ -1225,9 +1254,9 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
   RC(predict_launch(b, d.n_chains, seed, iter, dpi, dy, dc));
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  if (e == cudaSuccess && pipred) e = cudaMemcpy(pipred, dpi, n1 * sizeof(double), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && ypred) e = cudaMemcpy(ypred, dy, n1 * sizeof(double), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && predclass) e = cudaMemcpy(predclass, dc, n2 * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && pipred) e = d2h_out(b, pipred, dpi, n1 * sizeof(double));
+  if (e == cudaSuccess && ypred) e = d2h_out(b, ypred, dy, n1 * sizeof(double));
+  if (e == cudaSuccess && predclass) e = d2h_out(b, predclass, dc, n2 * sizeof(int));
   if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("predict_kernel: ") + cudaGetErrorString(e));
   float ms = 0;
   cudaEventElapsedTime(&ms, b->ev0, b->ev1);
@@ -1354,12 +1383,12 @@ extern "C" int tppmx_batch_summaries(tppmx_batch *b, const double *util_w, doubl
   const size_t npsm = (size_t)d.n_datasets * d.T * d.ntmax * d.ntmax, n1 = (size_t)d.n_datasets * d.npred * d.D * d.T;
   if (psm) {
     if (!dp) return fail(ctx, TPPMX_ERR_CAPACITY, "co-clustering counts were not reserved (ntmax too large)");
-    CK(ctx, cudaMemcpy(psm, dp, sizeof(double) * npsm, cudaMemcpyDeviceToHost));
+    CK(ctx, d2h_out(b, psm, dp, sizeof(double) * npsm));
   }
   if ((pi_mean || utility || best_arm) && d.npred < 1) return fail(ctx, TPPMX_ERR_ARG, "batch has npred == 0");
-  if (pi_mean) CK(ctx, cudaMemcpy(pi_mean, dm, sizeof(double) * n1, cudaMemcpyDeviceToHost));
-  if (utility) CK(ctx, cudaMemcpy(utility, du, sizeof(double) * d.n_datasets * d.npred * d.T, cudaMemcpyDeviceToHost));
-  if (best_arm) CK(ctx, cudaMemcpy(best_arm, db, sizeof(int32_t) * d.n_datasets * d.npred, cudaMemcpyDeviceToHost));
+  if (pi_mean) CK(ctx, d2h_out(b, pi_mean, dm, sizeof(double) * n1));
+  if (utility) CK(ctx, d2h_out(b, utility, du, sizeof(double) * d.n_datasets * d.npred * d.T));
+  if (best_arm) CK(ctx, cpy_sync(ctx->stream, best_arm, db, sizeof(int32_t) * d.n_datasets * d.npred, cudaMemcpyDeviceToHost));
   return TPPMX_OK;
 }
 
@@ -1490,7 +1519,7 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
   }
   if (!rc) rc = check_status(B);
   auto dl = [&](double *dst, const double *src, size_t n) {
-    if (!rc && dst && n && cudaMemcpy(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (!rc && dst && n && cpy_sync(ctx->stream, dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: download");
   };
   if (nout > 0) {
