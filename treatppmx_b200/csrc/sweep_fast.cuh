@@ -430,6 +430,10 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     }
 
     // =========================== sequential reallocation steps ===========================
+    // more candidates than lanes in some unit of the warp?  Changes only with the number of
+    // clusters, so the per-step vote is skipped while it cannot be true.
+    bool anymulti = __any_sync(TPPMX_FULL, live && K + CC > LPU);
+    int labcur = labp[0];
     double dV = dV_of(K);
     bool act0 = ul < K + CC;
     const double *likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
@@ -466,11 +470,12 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
       }
       const double uu_n = uq[it + 1], qx_n = uq[uqs + it + 1];
+      const int lab_n = labp[it + 1];  // label of the next patient (re-read after a relabelling)
       if (!NOLIK) lik_n = likp[it + 1];
       bool structural = false;
 
       // ---- :368-457 take the patient out of its cluster
-      const int zi = on ? labp[it] - 1 : 0;
+      const int zi = on ? labcur - 1 : 0;
       TPPMX_ASSERT(zi >= 0 && zi < KS && (!on || zi < K), 1);
       const int nzi = U.nj[zi];
       TPPMX_ASSERT(!on || nzi >= 1, 2);
@@ -523,16 +528,18 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           dV = dV_of(K);
           structural = true;
         }
+        anymulti = __any_sync(TPPMX_FULL, live && K + CC > LPU);
       }
       if (on && !single) {
         if (ul == 0) U.nj[zi] = nzi - 1;
 #pragma unroll
         for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
-          if (p < P) {
-            const double xv = xs[p];
-            U.sumx[p * KSTR + zi] = __dsub_rn(U.sumx[p * KSTR + zi], xv);
-            U.sumx2[p * KSTR + zi] = __dsub_rn(U.sumx2[p * KSTR + zi], __dmul_rn(xv, xv));
+          if (p < P) {  // both loads before either store: the two arrays may alias for all the
+                        // compiler knows, and a load queued behind a store doubles the latency
+            const double xv = xs[p], s1 = U.sumx[p * KSTR + zi], s2 = U.sumx2[p * KSTR + zi];
+            U.sumx[p * KSTR + zi] = __dsub_rn(s1, xv);
+            U.sumx2[p * KSTR + zi] = __dsub_rn(s2, __dmul_rn(xv, xv));
           }
         }
       }
@@ -583,7 +590,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         newci = hit ? __ffs(hit) : ntot;  // :807 default when rounding leaves uu >= total
       }
       const bool multi = on && ntot > LPU;
-      if (__any_sync(TPPMX_FULL, multi)) {
+      if (anymulti && __any_sync(TPPMX_FULL, multi)) {
         const int r = fast_score_multi<LPU>(U, tab2, lognp, lik, ntp, it, K, CC, KS, P, xs, qx, uu, dV,
                                             simscale, iv2, c0, hiv2, NOLIK, multi, ul, sub);
         if (multi) newci = r;
@@ -634,15 +641,16 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           dV = dV_of(K);
           structural = true;
         }
+        anymulti = __any_sync(TPPMX_FULL, live && K + CC > LPU);
       }
       if (on) {
 #pragma unroll
         for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
           if (p < P) {
-            const double xv = xs[p];
-            U.sumx[p * KSTR + lab - 1] = __dadd_rn(U.sumx[p * KSTR + lab - 1], xv);
-            U.sumx2[p * KSTR + lab - 1] = __dadd_rn(U.sumx2[p * KSTR + lab - 1], __dmul_rn(xv, xv));
+            const double xv = xs[p], s1 = U.sumx[p * KSTR + lab - 1], s2 = U.sumx2[p * KSTR + lab - 1];
+            U.sumx[p * KSTR + lab - 1] = __dadd_rn(s1, xv);
+            U.sumx2[p * KSTR + lab - 1] = __dadd_rn(s2, __dmul_rn(xv, xv));
           }
         }
       }
@@ -656,10 +664,12 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       qx = qx_n;
       likv = lik_n;
       __syncwarp();
+      labcur = lab_n;
       if (structural) {
         act0 = ul < K + CC;
         likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
         if (!NOLIK) likv = likp[it + 1];
+        labcur = labp[it + 1];
       }
     }
   }
