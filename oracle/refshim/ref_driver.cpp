@@ -150,61 +150,6 @@ double ref_calculate_gamma(const double *eta, int D, int ncols, const double *Z,
 double ref_dmvnrm_log(const double *x, const double *mean, const double *sigma, int n) {
   return dmvnrm(mk_mat(x, 1, n), arma::rowvec(mk_mat(mean, 1, n)), mk_mat(sigma, n, n), true)(0);
 }
-double ref_dmultinom(const double *x, int size, const double *prob, int K, int Log) {
-  return dmultinom_rcpp(mk_vec(x, K), size, mk_vec(prob, K), Log);
-}
-/* eta_update (src/utils_ct.cpp:579-702): eta[D], loggamma[nobs x D], eta_flag[len] updated in place */
-int ref_eta_update(const double *JJ, double *loggamma, int nobs, int D, const double *curr_clu, int nclu_len,
-                   const double *treatments, int t, double *eta, double *eta_flag, int flag_len,
-                   const double *mu_star, const double *sigma_star, int jj, double mhtune) {
-  try {
-    Rcpp::List o = eta_update(mk_mat(JJ, nobs, D), mk_mat(loggamma, nobs, D), mk_vec(curr_clu, nclu_len),
-                              mk_vec(treatments, nobs), t, mk_vec(eta, D), mk_vec(eta_flag, flag_len),
-                              mk_vec(mu_star, D), mk_mat(sigma_star, D, D), jj, mhtune);
-    put(eta, Rcpp::as<arma::vec>(o[0]));
-    put(loggamma, Rcpp::as<arma::mat>(o[1]));
-    put(eta_flag, Rcpp::as<arma::vec>(o[2]));
-    return 0;
-  } catch (const std::exception &e) {
-    g_err = e.what();
-    return 1;
-  }
-}
-/* beta_update (src/utils_ct.cpp:710-800): beta_temp[Q], loggamma[nobs x D], beta_flag[Q x D] in place */
-int ref_beta_update(const double *ZZ, const double *JJ, double *loggamma, int nobs, int D, int Q, double *beta_temp,
-                    double *beta_flag, double mu_beta, const double *sigma_beta, int kk, double mhtune) {
-  try {
-    Rcpp::List o = beta_update(mk_mat(ZZ, nobs, Q), mk_mat(JJ, nobs, D), mk_mat(loggamma, nobs, D),
-                               mk_vec(beta_temp, Q), mk_mat(beta_flag, Q, D), mu_beta,
-                               mk_vec(sigma_beta, (long)Q * D), kk, mhtune);
-    put(beta_temp, Rcpp::as<arma::vec>(o[0]));
-    put(loggamma, Rcpp::as<arma::mat>(o[1]));
-    put(beta_flag, Rcpp::as<arma::mat>(o[2]));
-    return 0;
-  } catch (const std::exception &e) {
-    g_err = e.what();
-    return 1;
-  }
-}
-int ref_up_lambda_hs(const double *beta, double *lambda, int len, double tau) {
-  try {
-    put(lambda, up_lambda_hs(mk_vec(beta, len), mk_vec(lambda, len), tau));
-    return 0;
-  } catch (const std::exception &e) {
-    g_err = e.what();
-    return 1;
-  }
-}
-int ref_up_tau_hs(const double *beta, const double *lambda, int len, double *tau) {
-  try {
-    *tau = up_tau_hs(mk_vec(beta, len), mk_vec(lambda, len), *tau);
-    return 0;
-  } catch (const std::exception &e) {
-    g_err = e.what();
-    return 1;
-  }
-}
-
 /* ---- src/dm_ppmx_ct.cpp:10-1471, the whole run -------------------------------------------------
  * Inputs are the 42 arguments in the reference's order, matrices column-major (Armadillo).  Vwm is
  * the dense cube (vr x vc x G).  Outputs are the 18 list elements, flattened column-major; fields

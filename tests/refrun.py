@@ -151,13 +151,9 @@ class RefLib:
                            ("ref_gsimconNN", [d, d, d, d, d, i, i, i]),
                            ("ref_gsimconNNIG", [d, d, d, d, d, d, i, i, i]), ("ref_gsimcatDM", [dp, dp, i, i, i]),
                            ("ref_calculate_gamma", [dp, i, i, dp, i, i, dp, i, i, i, i]),
-                           ("ref_dmvnrm_log", [dp, dp, dp, i]), ("ref_dmultinom", [dp, i, dp, i, i])):
+                           ("ref_dmvnrm_log", [dp, dp, dp, i])):
             getattr(L, name).restype = d
             getattr(L, name).argtypes = args
-        L.ref_eta_update.argtypes = [dp, dp, i, i, dp, i, dp, i, dp, dp, i, dp, dp, i, d]
-        L.ref_beta_update.argtypes = [dp, dp, dp, i, i, i, dp, dp, d, dp, i, d]
-        L.ref_up_lambda_hs.argtypes = [dp, dp, i, d]
-        L.ref_up_tau_hs.argtypes = [dp, dp, i, dp]
         self._keep = []
 
     @staticmethod
