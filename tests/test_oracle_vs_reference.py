@@ -4,8 +4,8 @@ oracle/_ref/libref.so is /root/reference/src/{utils_ct,dm_ppmx_ct,prior_ppmx}.cp
 unmodified against the stand-in headers of oracle/refshim/ (R, Rcpp and Armadillo are absent from
 this image).  Two levels:
 
-* function by function (src/utils_ct.cpp): similarity / density / likelihood helpers and the
-  on random inputs, <= 1e-13 relative (the Metropolis / horseshoe updates are covered by the whole runs);
+* function by function (src/utils_ct.cpp): similarity / density / likelihood helpers on random
+  inputs, <= 1e-13 relative (the Metropolis / horseshoe updates are covered by the whole runs);
 * whole runs of dm_ppmx_ct (src/dm_ppmx_ct.cpp:10-1471): the oracle records every variate it
   consumes, in call order, on a tape; the reference is then run with that tape as its R RNG.  It
   must consume the tape exactly (same kinds, same gamma shapes, same count) and return the same
