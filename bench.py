@@ -83,7 +83,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -331,13 +331,14 @@ def run_native(args, rank: int, world: int, local_rank: int):
     it = 0
     batch.run(seed, it, args.burn)
     it += args.burn
-    for _ in range(args.warmup):
-        batch.sweep(seed, it, args.sweeps)
-        it += args.sweeps
-
+    # clocks are sampled from the warm-up steps on (same kernel, same load): the timed region of the
+    # default run lasts ~50 ms, less than nvidia-smi needs to start
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        batch.sweep(seed, it, args.sweeps)
+        it += args.sweeps
     barrier()
     t_wall0 = time.perf_counter()
     ms_steps, launches = [], 0
