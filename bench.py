@@ -71,13 +71,16 @@ def algorithmic_bytes_per_realloc(dims, CC: int, Kbar: float) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons.  nvidia-smi needs about a second to deliver its first
+    line, longer than the default timed region, so the process is started early and the samples are
+    cut to the [mark_start, mark_end] window by nvidia-smi's own timestamps."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -90,6 +93,12 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
@@ -97,28 +106,35 @@ class ClockSampler:
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        sm, mx, reasons, total = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
+            total += 1
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.t0 is not None and not (self.t0 - 0.02 <= ts <= (self.t1 or time.time()) + 0.02):
+                    continue
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_whole_run": total, "reasons": sorted(reasons),
+                "window": "warm-up steps, timed steps, full iterations and e2e calls (all under load)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -310,6 +326,9 @@ def run_native(args, rank: int, world: int, local_rank: int):
 
     from treatppmx_b200.engine import Batch, Context
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     w = build_workload(args, rank)
     dims, model = w["dims"], w["model"]
     nchains = int(w["chain_ds"].size)
@@ -331,11 +350,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     it = 0
     batch.run(seed, it, args.burn)
     it += args.burn
-    # clocks are sampled from the warm-up steps on (same kernel, same load): the timed region of the
-    # default run lasts ~50 ms, less than nvidia-smi needs to start
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_start()
     for _ in range(args.warmup):
         batch.sweep(seed, it, args.sweeps)
         it += args.sweeps
@@ -352,7 +367,6 @@ def run_native(args, rank: int, world: int, local_rank: int):
         it += args.sweeps
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
 
     dev_ms = float(sum(ms_steps))
     lab, ncl = batch.get_partitions()
@@ -458,6 +472,9 @@ def run_native(args, rank: int, world: int, local_rank: int):
     for c in ctxs[1:]:
         c.close()
     e2e_s = min(e2e_serial_s, e2e_pipe_s)
+
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
 
     # reduce over ranks: max time, sum work
     full_ms = (nchains * 1e3 / full["gibbs_iterations_per_sec"]) if full else 0.0   # ms per iteration of all chains
