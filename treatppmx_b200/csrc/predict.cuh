@@ -10,6 +10,7 @@
 #include "rng.cuh"
 #include "sim.cuh"
 #include "sweep.cuh"
+#include "fastmath.cuh"
 
 namespace tppmx {
 
@@ -175,7 +176,8 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
 // only.  A block stages t [P][K] and the coefficients in shared memory once; a thread then needs
 // P fused multiply-adds per cluster and no transcendental before the softmax.
 // dynamic smem: ((P + 3) * KP + P * nth + (KP + 1) * nth) doubles, KP = clusters staged (>= K).
-__global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t seed, int iter, int KP,
+// kmin: arms with fewer occupied clusters were handled by predict_reg_kernel (block-uniform exit).
+__global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t seed, int iter, int KP, int kmin,
                                                            double *pipred, double *ypred, int *predclass) {
   extern __shared__ double psm[];
   const int chain = blockIdx.x, tt = blockIdx.y, tid = threadIdx.x, nth = blockDim.x;
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t 
   const Rng rng = make_rng(seed, b.chain_id[chain]);
   const ArmView A = arm_view_global(b, chain, tt, ds);
   const int K = A.K, CC = b.CC, D = b.D, P = b.P, npred = b.npred;
+  if (K < kmin) return;
   double *ts = psm;                  // [P][KP]
   double *c0s = ts + (size_t)P * KP; // [KP] x 3
   double *c1s = c0s + KP, *c2s = c1s + KP;
@@ -268,6 +271,188 @@ __global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t 
       }
       pred_emit(b, rng, A, iter, tt, pp, ds, newci, K, beta, Theta, Sigma, obase, chain, pipred, ypred, predclass);
     }
+  }
+}
+
+// ---- register variant of the fast kernel: the shape the package produces (P <= 16 covariates,
+// D <= 3 outcome categories) with at most KR occupied clusters in the arm (decided per block: an
+// arm with more is left to predict_fast_kernel, launched behind this one with kmin = KR + 1).
+// The new patient's covariates live in registers and its K weights in KR x 128 doubles of shared
+// memory (8 KB against the 53 KB predict_fast_kernel needs for kcap + 1 of them), so several
+// blocks share an SM;
+// everything that does not depend on the patient is hoisted to the block prologue: t_jp, the
+// three weight coefficients, eta*, beta, Theta and the Cholesky factor of Sigma (an auxiliary
+// pick costs one matrix-vector product instead of a per-thread factorisation that a whole warp
+// waits for).  Softmax by fast_exp with the division-free draw of the sweep kernel.
+// Config 5 (10 000 new patients x 3 arms x 1024 chains): 5.5 ms -> see DESIGN.md.
+#define TPPMX_PRED_KR 16
+template <int PR>
+__global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_t seed, int iter, double *pipred,
+                                                          double *ypred, int *predclass) {
+  constexpr int KR = TPPMX_PRED_KR, DR = 3;
+  __shared__ double ts[PR][KR];
+  __shared__ double cs[3][KR];
+  __shared__ double etas[DR][KR];
+  __shared__ double Ls[DR * DR], Ths[DR], betas[DR * TPPMX_MAXQ];
+  __shared__ double ws[KR][128];  // the thread's weights, column tid
+  const int chain = blockIdx.x, tt = blockIdx.y, tid = threadIdx.x, nth = blockDim.x;
+  const int ds = b.chain_ds[chain];
+  const ArmView A = arm_view_global(b, chain, tt, ds);
+  const int K = A.K;
+  if (K > KR) return;  // block-uniform: predict_fast_kernel takes this arm
+  const SimConst s = make_simconst(b);
+  const Rng rng = make_rng(seed, b.chain_id[chain]);
+  const int CC = b.CC, D = b.D, P = b.P, Q = b.Q, npred = b.npred;
+  const double sigma = b.sigma[(size_t)chain * b.T + tt];
+  const int idxs = b.idxs[chain];
+  const double scale = (s.calibration == 2) ? s.calscale : 1.0;
+  double dV = 0.0;
+  if (s.cohesion == 2 && K >= 1) {
+    const size_t base = ((size_t)tt * 2) * b.ntmax;
+    dV = b.logV[(base + b.ntmax + (K - 1)) * b.G + idxs] - b.logV[(base + (K - 1)) * b.G + idxs];
+  }
+  const double dP = (double)P;
+  for (int j = tid; j < KR; j += nth) {  // per-cluster coefficients (as predict_fast_kernel)
+    double a = 0.0;
+    for (int p = 0; p < PR; p++) {
+      const double t = (j < K && p < P) ? fma(A.sumx[(size_t)p * A.ks + j], s.iv2, s.c0) : 0.0;
+      ts[p][j] = t;
+      a = fma(t, t, a);
+    }
+    if (j < K) {
+      const int n = A.nj[j];
+      const NNRow r0 = b.nn_tab[n], r1 = b.nn_tab[n + 1];
+      const double coh = (s.cohesion == 1) ? log((double)n) : dV + log((double)n - sigma);
+      cs[0][j] = coh + scale * (dP * (r1.A0 - r0.A0) + (r1.H - r0.H) * a);
+      cs[1][j] = scale * 2.0 * s.iv2 * r1.H;
+      cs[2][j] = scale * (r1.H * s.iv2 * s.iv2 - s.hiv2);
+      for (int k = 0; k < D; k++) etas[k][j] = A.eta[(size_t)k * A.ks + j];
+    }
+  }
+  if (tid == 0) {  // chol_lower(Sigma) as pred_emit forms it, Theta
+    const double *Sigma = b.Sigma + ((size_t)chain * b.T + tt) * D * D;
+    for (int a = 0; a < D; a++)
+      for (int c = 0; c <= a; c++) {
+        double sum = Sigma[a + D * c];
+        for (int k = 0; k < c; k++) sum -= Ls[a + D * k] * Ls[c + D * k];
+        Ls[a + D * c] = (a == c) ? sqrt(sum) : sum / Ls[c + D * c];
+      }
+    for (int k = 0; k < D; k++) Ths[k] = b.Theta[((size_t)chain * b.T + tt) * D + k];
+  }
+  for (int e = tid; e < Q * D; e += nth) betas[e] = b.beta[(size_t)chain * Q * D + e];
+  const NNRow q1 = b.nn_tab[1];
+  const double a_aux = dP * s.c0 * s.c0;
+  const double coh_aux = (s.cohesion == 1) ? log(b.model.alpha) - log((double)CC) : dV;
+  const size_t obase = (size_t)chain * npred * D * b.T;
+  __syncthreads();
+
+  for (int pp = tid; pp < npred; pp += nth) {
+    double x[PR], qx = 0.0, sx = 0.0;
+    {
+      const double *xr = b.xp + ((size_t)ds * npred + pp) * P;
+#pragma unroll
+      for (int p = 0; p < PR; p++) {
+        x[p] = (p < P) ? xr[p] : 0.0;
+        qx = fma(x[p], x[p], qx);
+        sx += x[p];
+      }
+    }
+    double wmax;
+    {
+      const double tY = a_aux + s.iv2 * (2.0 * s.c0 * sx + s.iv2 * qx);
+      wmax = coh_aux + scale * (dP * q1.A0 - s.hiv2 * qx + q1.H * tY);  // the auxiliary clusters' weight
+    }
+    const double w_aux = wmax;
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+      double bj = 0.0;
+#pragma unroll
+      for (int p = 0; p < PR; p++) bj = fma(ts[p][j], x[p], bj);
+      const double w = cs[0][j] + cs[1][j] * bj + cs[2][j] * qx;
+      ws[j][tid] = w;
+      wmax = fmax(wmax, w);
+    }
+    double den = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+      const double e = fast_exp(ws[j][tid] - wmax);
+      ws[j][tid] = e;
+      den += e;
+    }
+    const double e_aux = fast_exp(w_aux - wmax);
+    for (int m = 0; m < CC; m++) den += e_aux;
+    double uu, u1;
+    rng_u2(rng, iter, TPPMX_SITE_PRED_U, tt, (uint32_t)pp, 0, uu, u1);
+    // :1351-1360 first j with uu < cumsum(e)/den, i.e. uu*den < cumsum(e); default K + CC (quirk 7)
+    const double thr = uu * den;
+    int newci = K + CC;
+    bool found = false;
+    double cw = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+      cw += ws[j][tid];
+      if (!found && thr < cw) {
+        newci = j + 1;
+        found = true;
+      }
+    }
+    for (int m = 0; m < CC; m++) {
+      cw += e_aux;
+      if (!found && thr < cw) {
+        newci = K + m + 1;
+        found = true;
+      }
+    }
+    // :1366-1382 eta_pred, pi = softmax(eta_pred + beta' zpred) without max-shift, one multinomial draw
+    double ep[DR];
+    if (newci <= K) {
+#pragma unroll
+      for (int k = 0; k < DR; k++) ep[k] = (k < D) ? etas[k][newci - 1] : 0.0;
+    } else {
+      double zn[4];
+      rng_normals(rng, iter, TPPMX_SITE_PRED_ETA, tt, (uint32_t)pp, D, zn, 1);
+#pragma unroll
+      for (int k = 0; k < DR; k++) {
+        double acc = (k < D) ? Ths[k] : 0.0;
+        for (int r = 0; r <= k && k < D; r++) acc += Ls[k + D * r] * zn[r];
+        ep[k] = acc;
+      }
+    }
+    const double *zp = b.zpred + ((size_t)ds * npred + pp) * Q;
+    double pr[DR], sumrow = 0.0;
+#pragma unroll
+    for (int k = 0; k < DR; k++) {
+      pr[k] = 0.0;
+      if (k < D) {
+        double lg = ep[k];
+        for (int q = 0; q < Q; q++) lg += betas[k + q * D] * zp[q];
+        pr[k] = fast_exp(lg);
+        sumrow += pr[k];
+      }
+    }
+    const double rs = fast_rcp(sumrow);
+    double uy, uy1, cwy = 0.0;
+    rng_u2(rng, iter, TPPMX_SITE_PRED_Y, tt, (uint32_t)pp, 0, uy, uy1);
+    int pick = D - 1;
+    bool got = false;
+#pragma unroll
+    for (int k = 0; k < DR; k++)
+      if (k < D) {
+        pr[k] *= rs;
+        cwy += pr[k];
+        if (!got && uy < cwy) {
+          pick = k;
+          got = true;
+        }
+      }
+#pragma unroll
+    for (int k = 0; k < DR; k++)
+      if (k < D) {
+        const size_t o = obase + pp + (size_t)npred * (k + (size_t)D * tt);
+        if (pipred) pipred[o] = pr[k];
+        if (ypred) ypred[o] = (k == pick) ? 1.0 : 0.0;
+      }
+    if (predclass) predclass[(size_t)chain * npred * b.T + pp + (size_t)npred * tt] = newci;
   }
 }
 

@@ -1285,7 +1285,18 @@ static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, in
     if (smem <= 200 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(predict_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("predict_fast_kernel: ") + cudaGetErrorString(e));
-      predict_fast_kernel<<<dim3(n_chains_launch, d.T), nth, smem, st>>>(d, seed, iter, KP, dpi, dy, dc);
+      // arms with at most TPPMX_PRED_KR clusters (all but a few) go through the register kernel,
+      // the rest through the staged one; each block decides for itself and the other exits at once
+      int kmin = 0;
+      if (d.P <= 16 && d.D <= 3 && d.Q <= TPPMX_MAXQ) {
+        const dim3 grid(n_chains_launch, d.T);
+        if (d.P <= 4) predict_reg_kernel<4><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
+        else if (d.P <= 8) predict_reg_kernel<8><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
+        else if (d.P <= 12) predict_reg_kernel<12><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
+        else predict_reg_kernel<16><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
+        kmin = TPPMX_PRED_KR + 1;
+      }
+      predict_fast_kernel<<<dim3(n_chains_launch, d.T), nth, smem, st>>>(d, seed, iter, KP, kmin, dpi, dy, dc);
       CK(ctx, cudaGetLastError());
       return TPPMX_OK;
     }
