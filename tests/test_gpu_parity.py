@@ -183,6 +183,27 @@ def test_predict_matches_oracle(ctx, name):
         np.testing.assert_allclose(pi[c].sum(axis=1), 1.0, atol=1e-12)
 
 
+def test_predict_split_between_register_and_staged_kernels(ctx):
+    """An arm with more than 16 clusters is scored by predict_fast_kernel, the others by
+    predict_reg_kernel, in the same call: both against the oracle."""
+    batch, pbs, (model, dims, shared, dsets, labels, nclu, betas), cds = _mk(ctx, "default_ngg", n_chains=2)
+    n_a = np.bincount(dsets[0].treat, minlength=dims.T)
+    lab = np.zeros_like(labels)
+    ncl = np.zeros_like(nclu)
+    for t, k in enumerate([20, 3][: dims.T]):
+        lab[t, : n_a[t]] = (np.arange(n_a[t]) % k) + 1
+        ncl[t] = k
+    batch.init(21, lab, ncl, betas[0])
+    pi, yp, pc = batch.predict(21, 7)
+    for c in range(2):
+        st = batch.get_state(c)
+        assert st.nclu.tolist() == [20, 3]
+        pi2, yp2, pc2 = pbs[0].predict(st, 21, c, 7)
+        assert (pc[c] == pc2).all()
+        np.testing.assert_allclose(pi[c], pi2, rtol=REL_TOL, atol=0)
+        assert (yp[c] == yp2).all()
+
+
 def test_capacity_error_is_reported(ctx):
     batch, pbs, (model, dims, shared, dsets, labels, nclu, betas), cds = _mk(ctx, "dp_T3", kcap=5)
     batch.init(1, labels, nclu, betas[0])
