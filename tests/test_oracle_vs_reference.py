@@ -135,6 +135,13 @@ def test_reference_run_on_the_oracle_tape(ref, name, over):
     _compare(got, want, tape)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("name", ["default_ngg", "dp_T3", "noreuse"])
+def test_reference_run_other_seeds(ref, name, seed):
+    got, want, tape = _run_both(ref, name, {}, iters=60, burn=20, thin=4, seed=1000 + seed)
+    _compare(got, want, tape)
+
+
 def test_reference_run_long_default(ref):
     got, want, tape = _run_both(ref, "default_ngg", {}, iters=400, burn=100, thin=5, seed=5)
     _compare(got, want, tape)
