@@ -505,6 +505,11 @@ bad:
 extern "C" int tppmx_batch_destroy(tppmx_batch *b) {
   if (!b) return TPPMX_OK;
   cudaSetDevice(b->ctx->device);
+  // nothing of this batch may still be running when its arena is handed on: the main stream orders
+  // itself, the side streams are only ever busy here after an error return out of tppmx_batch_run
+  cudaStreamSynchronize(b->ctx->side);
+  cudaStreamSynchronize(b->ctx->hs);
+  b->ctx->hs_pending = false;
   if (b->ar.dbase) {  // leave the arena with the context for the next batch (keep the larger one)
     Arena &sp = b->ctx->spare;
     if (b->ar.dcap > sp.dcap || (b->ar.dcap == sp.dcap && b->ar.hcap > sp.hcap)) {
