@@ -1,7 +1,7 @@
 set -x
 python -m pytest tests -m gpu -q > gpurun_out/r1z_gputests.log 2>&1; tail -3 gpurun_out/r1z_gputests.log
 TPPMX_LIB=$PWD/treatppmx_b200/libtppmx_check.so python -m pytest tests/test_gpu_fast_sweep.py tests/test_gpu_parity.py tests/test_gpu_edge_cases.py tests/test_gpu_large_n.py tests/test_gpu_update.py -m gpu -q > gpurun_out/r1z_gputests_check.log 2>&1; tail -2 gpurun_out/r1z_gputests_check.log
-python __graft_entry__.py smoke 2>&1 | tail -1
+python __graft_entry__.py smoke > gpurun_out/r1z_smoke.log 2>&1; tail -1 gpurun_out/r1z_smoke.log
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1z_bench_reference.json 2>/dev/null
 python bench.py > gpurun_out/r1z_bench.json 2> gpurun_out/r1z_bench.err; tail -2 gpurun_out/r1z_bench.err
 B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
