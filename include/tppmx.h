@@ -39,7 +39,8 @@ enum {
   TPPMX_ERR_ARG = 1,        /* bad argument / unsupported switch combination            */
   TPPMX_ERR_CUDA = 2,       /* CUDA runtime error (text in tppmx_last_error)             */
   TPPMX_ERR_CAPACITY = 3,   /* a chain needed more than kcap clusters in one arm         */
-  TPPMX_ERR_NOMEM = 4
+  TPPMX_ERR_NOMEM = 4,
+  TPPMX_ERR_INTERRUPTED = 5 /* the caller's interrupt flag was raised (tppmx_set_interrupt_flag) */
 };
 
 /* ---- RNG sites: counter-based Philox4x32-10 ------------------------------------------
@@ -166,6 +167,14 @@ typedef struct tppmx_batch tppmx_batch;
 int tppmx_version(void);
 int tppmx_create(tppmx_ctx **ctx, int device);
 int tppmx_destroy(tppmx_ctx *ctx);
+/* Interruptibility of the long calls (the reference is interruptible only through R's own checks;
+ * a blocking C call is not).  tppmx_batch_run and tppmx_dm_ppmx_ct drain the device every
+ * `check_every` iterations (>= 1; 64 keeps the cost below 1 %) and read *flag: non-zero stops the
+ * run with TPPMX_ERR_INTERRUPTED, the batch left in the state after the last completed iteration
+ * (tppmx_dm_ppmx_ct returns without filling its outputs).  The flag is only ever read, from the
+ * calling thread: an Rcpp shim passes &R_interrupts_pending, another host a flag its signal handler
+ * or another thread sets.  flag == NULL switches the checks off (default). */
+int tppmx_set_interrupt_flag(tppmx_ctx *ctx, const volatile int32_t *flag, int32_t check_every);
 const char *tppmx_last_error(const tppmx_ctx *ctx);
 
 /* Test hook: evaluates the library's device fp64 math on n inputs (which: 0 = log, 1 = exp,

@@ -41,3 +41,20 @@ def test_dm_ppmx_ct_rejects_bad_arguments():
     with pytest.raises(_lib.TppmxError):
         dm_ppmx_ct(ctx, **args, seed=1, logV_compact=logV)
     ctx.close()
+
+
+def test_dm_ppmx_ct_is_interruptible():
+    from treatppmx_b200 import _lib
+    from treatppmx_b200.engine import Context
+    from treatppmx_b200.ppmxct import dm_ppmx_ct
+    args, logV, _ = _reference_args("default_ngg", 40, 10, 2, False)
+    ctx = Context(0)
+    flag = np.ones(1, dtype=np.int32)
+    ctx.set_interrupt_flag(flag, check_every=3)
+    with pytest.raises(_lib.TppmxError) as ei:
+        dm_ppmx_ct(ctx, **args, seed=1, logV_compact=logV)
+    assert ei.value.code == 5 and "iteration 2" in str(ei.value)
+    flag[0] = 0
+    out = dm_ppmx_ct(ctx, **args, seed=1, logV_compact=logV)     # the context stays usable
+    assert out["nclus"].shape[-1] == 15
+    ctx.close()

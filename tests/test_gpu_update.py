@@ -174,3 +174,34 @@ def test_posterior_summaries_agree_with_oracle_chains(ctx):
     gap = np.sort(util_o, axis=0)[-1] - np.sort(util_o, axis=0)[-2]
     clear = gap > 8.0
     assert (util_d.argmax(0)[clear] == util_o.argmax(0)[clear]).all()
+
+
+def test_run_stops_at_the_interrupt_flag():
+    """tppmx_set_interrupt_flag: a raised flag stops tppmx_batch_run at the next check with
+    TPPMX_ERR_INTERRUPTED and leaves the batch in the state after a completed iteration - the same
+    state an uninterrupted run of that many iterations reaches."""
+    from treatppmx_b200 import _lib
+    from treatppmx_b200.engine import Batch, Context
+    model, dims, shared, dsets, labels, nclu, betas = build_case("default_ngg")
+    ctx = Context(0)
+    flag = np.zeros(1, dtype=np.int32)
+    ctx.set_interrupt_flag(flag, check_every=5)
+    b = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0, 0])
+    b.init(3, labels, nclu, betas[0])
+    b.run(3, 0, 12)                      # flag down: runs through
+    flag[0] = 1
+    with pytest.raises(_lib.TppmxError) as ei:
+        b.run(3, 12, 40)
+    assert ei.value.code == 5 and "iteration 16" in str(ei.value)   # first check after 5 iterations: 12..16 done
+    got = b.get_state(0)
+    ctx.set_interrupt_flag(None)
+    b2 = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0, 0])
+    b2.init(3, labels, nclu, betas[0])
+    b2.run(3, 0, 17)
+    want = b2.get_state(0)
+    assert (got.labels == want.labels).all() and (got.nclu == want.nclu).all()
+    np.testing.assert_array_equal(got.beta, want.beta)
+    np.testing.assert_array_equal(got.JJ, want.JJ)
+    b.close()
+    b2.close()
+    ctx.close()

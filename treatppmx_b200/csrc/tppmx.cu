@@ -61,6 +61,9 @@ struct tppmx_ctx {
   cudaStream_t hs = nullptr;
   cudaEvent_t ev_hs_go = nullptr, ev_hs_done = nullptr;
   bool hs_pending = false;
+  // tppmx_set_interrupt_flag
+  const volatile int32_t *interrupt = nullptr;
+  int check_every = 64;
 };
 static void ctx_release(tppmx_ctx *c) {
   cudaSetDevice(c->device);
@@ -148,6 +151,13 @@ extern "C" int tppmx_destroy(tppmx_ctx *c) {
   if (!c) return TPPMX_OK;
   c->closed = true;
   if (c->live_batches == 0) ctx_release(c);
+  return TPPMX_OK;
+}
+
+extern "C" int tppmx_set_interrupt_flag(tppmx_ctx *ctx, const volatile int32_t *flag, int32_t check_every) {
+  if (!ctx || (flag && check_every < 1)) return TPPMX_ERR_ARG;
+  ctx->interrupt = flag;
+  if (flag) ctx->check_every = check_every;
   return TPPMX_OK;
 }
 
@@ -1140,10 +1150,19 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
   // the predictive step only needs what the update kernel writes, so they run on the side stream
   // beside the update kernel / the JJ-ss gamma draws; the next sweep waits for them.
   bool side_pending = false;
+  int interrupted_at = -1;
   for (int l = iter0; l < iter0 + n_iter; l++) {
     if (side_pending) {
       CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
       side_pending = false;
+    }
+    if (ctx->interrupt && l > iter0 && (l - iter0) % ctx->check_every == 0) {  // tppmx_set_interrupt_flag
+      RC(hs_join(ctx));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      if (*ctx->interrupt) {
+        interrupted_at = l - 1;
+        break;
+      }
     }
     RC(sweep_launch(b, seed, l, 1, false, &launches));
     const bool saved = (do_psm || do_pred) && (l > burn - 1) && ((l + 1) % thin == 0);  // :1060
@@ -1166,6 +1185,12 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
   }
   if (side_pending) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
   RC(hs_join(ctx));
+  if (interrupted_at >= 0) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    char buf[96];
+    snprintf(buf, sizeof buf, "interrupted after iteration %d", interrupted_at);
+    return fail(ctx, TPPMX_ERR_INTERRUPTED, buf);
+  }
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;
@@ -1517,6 +1542,15 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
 
   int launches = 0, ll = 0;
   for (int l = 0; l < a->iter && !rc; l++) {
+    if (ctx->interrupt && l > 0 && l % ctx->check_every == 0) {  // tppmx_set_interrupt_flag
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: kernel failure");
+      if (!rc && *ctx->interrupt) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "interrupted after iteration %d", l - 1);
+        rc = fail(ctx, TPPMX_ERR_INTERRUPTED, buf);
+      }
+      if (rc) break;
+    }
     rc = sweep_launch(B, a->seed, l, 1, false, &launches);
     if (!rc) rc = update_launch(B, a->seed, l, &launches);
     if (rc) break;

@@ -39,6 +39,13 @@ class Context:
         if rc != 0:
             raise _lib.TppmxError(rc, self.err())
 
+    def set_interrupt_flag(self, flag, check_every: int = 64):
+        """flag: a one-element int32 numpy array the caller (another thread, a signal handler) sets to
+        non-zero to stop tppmx_batch_run / tppmx_dm_ppmx_ct (TppmxError code 5); None switches it off."""
+        self._flag = flag   # keep the buffer alive
+        self.check(self.L.tppmx_set_interrupt_flag(self.h, flag.ctypes.data_as(c_ip) if flag is not None else c_ip(),
+                                                   check_every))
+
     def probe_math(self, which: str, x):
         """Device fp64 log / exp / lgamma of the fast sweep kernel on an array (test hook)."""
         x = np.ascontiguousarray(x, dtype=np.float64)
