@@ -223,7 +223,9 @@ int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sw
 /* Kernel selection.  The library has two sweep kernels with identical results:
  *   fast    — default switches (PPMx=1, consim=1, similarity=1, calibration 0|2, ncat=0,
  *             reuse=1): cluster statistics staged in shared memory, likelihood terms hoisted
- *             into a parallel pre-pass, TPPMX_OPT_LANES_PER_UNIT (8|16|32) lanes per (chain,arm)
+ *             into a parallel pre-pass, TPPMX_OPT_LANES_PER_UNIT (8|16|32) lanes per (chain,arm);
+ *             arms too long for shared-memory label tables (thousands of patients) always
+ *             run with 32
  *   generic — every switch combination of the reference, one warp per (chain, arm)
  * TPPMX_OPT_SWEEP_IMPL: 0 = automatic (fast when eligible), 1 = generic, 2 = fast (error if
  * the model is not eligible).  A (chain, arm) that outgrows the fast kernel's staged cluster
