@@ -232,8 +232,8 @@ def run_reference(args, rank: int, world: int):
     w = build_workload(args, 0)
     ncores = os.cpu_count() or 1
     # each step is a bounded sample: ~ (target) seconds of all-core work
-    total_budget = 60.0
-    per_step = max(1.0, total_budget / max(args.steps + args.warmup, 1))
+    total_budget = 60.0 * args.cpu_scale
+    per_step = max(1.0 * min(args.cpu_scale, 1.0), total_budget / max(args.steps + args.warmup, 1))
     rates, secs, nsw = [], [], 0
     for s in range(args.warmup + args.steps):
         r, desc, dt, nsw = cpu_oracle_rate(w, ncores, per_step, sweeps_hint=nsw)
@@ -255,9 +255,9 @@ def run_reference(args, rank: int, world: int):
         "gpu_launches": 0,
     }
     # the reference's own code where it can be timed: whole iterations through dm_ppmx_ct
-    fr = cpu_oracle_full_rate(w, ncores, 6.0)
+    fr = cpu_oracle_full_rate(w, ncores, 6.0 * args.cpu_scale)
     out["full_iteration"] = {"cpu_port_gibbs_iterations_per_sec": fr[0], "cpu_port_sample": fr[1]}
-    rr = cpu_reference_full_rate(w, ncores, 8.0)
+    rr = cpu_reference_full_rate(w, ncores, 8.0 * args.cpu_scale)
     if rr is not None:
         out["full_iteration"].update({"reference_gibbs_iterations_per_sec": rr[0], "reference_kind": "reference",
                                       "reference_reallocations_per_sec": rr[0] * w["dims"].nobs, "reference_sample": rr[1]})
@@ -605,6 +605,7 @@ def main():
     ap.add_argument("--sweep-impl", default="auto", choices=["auto", "generic", "fast"])
     ap.add_argument("--lpu", type=int, default=0, help="lanes per (chain, arm) of the fast kernel: 0=default, 8|16|32")
     ap.add_argument("--e2e-inflight", type=int, default=3, help="batches in flight of the e2e measurement (host threads)")
+    ap.add_argument("--cpu-scale", type=float, default=1.0, help="scales the time budgets of the CPU legs (tests use a small value)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
