@@ -128,6 +128,28 @@ void ref_rng_free(uint64_t seed) {
 long ref_tape_pos(void) { return g_pos; }
 const char *ref_last_error(void) { return g_err.c_str(); }
 
+/* ---- the stand-in containers themselves (checked against numpy in tests/test_oracle_vs_reference.py):
+ * inverse, upper Cholesky factor, covariance (rows = observations, divided by N), row means, a
+ * matrix product through sub-views, for an n x n SPD matrix A and an m x n data matrix X */
+int ref_shim_linalg(const double *A, int n, const double *X, int m, double *inv_out, double *chol_out, double *cov_out,
+                    double *mean_out, double *prod_out) {
+  try {
+    arma::mat a = mk_mat(A, n, n), x = mk_mat(X, m, n);
+    put(inv_out, arma::inv(a));
+    put(chol_out, arma::chol(a));
+    put(cov_out, arma::cov(x, 1));
+    put(mean_out, arma::mean(x.t(), 1));
+    arma::mat p(n, n);
+    for (int j = 0; j < n; j++) p.col(j) = a * a.col(j);   /* sub-view in, sub-view out */
+    p(arma::span::all, arma::span(0, 0)) = p.col(0) * 1.0;
+    put(prod_out, p);
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
 /* ---- src/utils_ct.cpp, function by function ---------------------------------------------------- */
 double ref_dinvgamma(double y, double a, double b, int lg) { return dinvgamma(y, a, b, lg); }
 double ref_dN_IG(double mu, double s2, double mu0, double k0, double a0, double b0, int lg) {

@@ -36,6 +36,27 @@ def _p(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+# ---- the stand-in containers ---------------------------------------------------------------------------
+def test_shim_linear_algebra_matches_numpy(ref):
+    """The pin is only as good as the stand-in headers: inverse, Cholesky, covariance, means and a
+    product through sub-views against numpy."""
+    rng = np.random.default_rng(11)
+    dp = C.POINTER(C.c_double)
+    ref.L.ref_shim_linalg.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp, dp, dp, dp]
+    for n, m in ((1, 3), (3, 10), (5, 40)):
+        B = rng.normal(size=(n, n))
+        A = np.asfortranarray(B @ B.T + n * np.eye(n))
+        X = np.asfortranarray(rng.normal(size=(m, n)))
+        inv, ch, cov, prod = (np.zeros((n, n), order="F") for _ in range(4))
+        mean = np.zeros(n)
+        assert ref.L.ref_shim_linalg(_p(A), n, _p(X), m, _p(inv), _p(ch), _p(cov), _p(mean), _p(prod)) == 0, ref.err()
+        np.testing.assert_allclose(inv, np.linalg.inv(A), rtol=1e-11)
+        np.testing.assert_allclose(ch, np.linalg.cholesky(A).T, rtol=1e-12, atol=1e-14)   # upper: A = R'R
+        np.testing.assert_allclose(cov, np.cov(X, rowvar=False, bias=True).reshape(n, n), rtol=1e-11, atol=1e-14)
+        np.testing.assert_allclose(mean, X.mean(axis=0), rtol=1e-13)
+        np.testing.assert_allclose(prod, A @ A, rtol=1e-12)
+
+
 # ---- src/utils_ct.cpp, function by function ---------------------------------------------------------
 def test_similarity_functions_match_reference(ref):
     rng = np.random.default_rng(1)
