@@ -5,6 +5,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "fastmath.cuh"
+
 namespace tppmx {
 
 struct Rng {
@@ -55,6 +57,14 @@ __device__ __forceinline__ void rng_n2(const Rng &g, uint32_t iter, uint32_t sit
   n1 = r * s;
 }
 
+// the first normal of the block only (what the gamma sampler consumes): no sine, branch-free log
+__device__ __forceinline__ double rng_n1(const Rng &g, uint32_t iter, uint32_t site, uint32_t arm,
+                                         uint32_t index, uint32_t sub) {
+  double u0, u1;
+  rng_u2(g, iter, site, arm, index, sub, u0, u1);
+  return sqrt(-2.0 * fast_log(u0)) * cos(6.283185307179586476925286766559 * u1);
+}
+
 // D standard normals: block b gives normals 2b, 2b+1
 __device__ __forceinline__ void rng_normals(const Rng &g, uint32_t iter, uint32_t site,
                                             uint32_t arm, uint32_t index, int D, double *out,
@@ -74,21 +84,21 @@ __device__ inline double rng_gamma(const Rng &g, uint32_t iter, uint32_t site, u
   if (a < 1.0) {
     double u0, u1;
     rng_u2(g, iter, site, arm, index, 0xFF00u, u0, u1);
-    boost = exp(log(u1) / a);
+    boost = fast_exp(fast_log(u1) / a);  // u1 in (0,1): the exponent is <= 0
     a += 1.0;
   }
   const double d = a - 1.0 / 3.0;
   const double c = 1.0 / sqrt(9.0 * d);
   for (uint32_t t = 0; t < 0x7F00u; t++) {
-    double x, xx, u, uu;
-    rng_n2(g, iter, site, arm, index, 2 * t, x, xx);
+    double u, uu;
+    const double x = rng_n1(g, iter, site, arm, index, 2 * t);
     double v = 1.0 + c * x;
     if (v <= 0.0) continue;
     v = v * v * v;
     rng_u2(g, iter, site, arm, index, 2 * t + 1, u, uu);
     const double x2 = x * x;
     if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
-    if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+    if (fast_log(u) < 0.5 * x2 + d * (1.0 - v + fast_log(v))) return boost * d * v;
   }
   return boost * d;
 }
