@@ -16,6 +16,7 @@
 //   depend on n only and come from a table (NNRow) built once per batch.
 #pragma once
 #include "layout.h"
+#include "fastmath.cuh"
 
 namespace tppmx {
 
@@ -176,10 +177,13 @@ __device__ __forceinline__ double cohesion_term(const SimConst &s, bool occ, int
 __device__ __forceinline__ double lik_term(int D, const double *eta, int estride,
                                            const double *__restrict__ zb,
                                            const double *__restrict__ ljj) {
+  // branch-free fp64 exp / lgamma (fastmath.cuh): libdevice's lgamma alone is ~3x the instructions
+  // and diverges across lanes; this term is most of what the generic kernel computes per step
   double w = 0.0;
   for (int k = 0; k < D; k++) {
-    const double g = exp(eta[(size_t)k * estride] + zb[k]);
-    w += g * ljj[k] - lgamma(g);
+    const double lgk = eta[(size_t)k * estride] + zb[k];
+    const double g = lgk > 709.0 ? INFINITY : fast_exp(lgk);
+    w += g * ljj[k] - lgamma_pos(g);
   }
   return w;
 }

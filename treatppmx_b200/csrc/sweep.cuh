@@ -185,8 +185,8 @@ __device__ inline ScoreOut score_clusters(const DevBatch &b, const SimConst &s, 
     double sgN = 0.0, sgY = 0.0;
     for (int c0 = 0; c0 < ntot; c0 += 32) {
       const int j = c0 + lane;
-      if (j < ntot) sgN += exp(A.gN[j] - mN);
-      if (j < K) sgY += exp(A.gY[j] - mY);
+      if (j < ntot) sgN += fast_exp(A.gN[j] - mN);
+      if (j < K) sgY += fast_exp(A.gY[j] - mY);
     }
     sgN = warp_sum(sgN);
     sgY = warp_sum(sgY);
@@ -212,7 +212,7 @@ __device__ inline ScoreOut score_clusters(const DevBatch &b, const SimConst &s, 
   double den = 0.0;
   if (!multi) {
     if (logw_out && lane < ntot) logw_out[lane] = w0;
-    o.e0 = (lane < ntot) ? exp(w0 - wmax) : 0.0;
+    o.e0 = (lane < ntot) ? fast_exp(w0 - wmax) : 0.0;
     den = o.e0;
   } else {
     __syncwarp();
@@ -222,7 +222,7 @@ __device__ inline ScoreOut score_clusters(const DevBatch &b, const SimConst &s, 
       if (j < ntot) {
         const double w = A.w[j];
         if (logw_out) logw_out[j] = w;
-        const double e = exp(w - wmax);
+        const double e = fast_exp(w - wmax);
         A.w[j] = e;
         den += e;
       }
