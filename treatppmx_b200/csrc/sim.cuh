@@ -45,17 +45,17 @@ __device__ __forceinline__ SimConst make_simconst(const DevBatch &b) {
 
 __device__ __forceinline__ double dnorm_log(double x, double mu, double sd) {
   const double t = (x - mu) / sd;
-  return -(TPPMX_LN_SQRT_2PI + 0.5 * t * t + log(sd));
+  return -(TPPMX_LN_SQRT_2PI + 0.5 * t * t + fast_log(sd));
 }
 
 // dN_IG(mu, sig2; m, k, a, b) on the log scale, utils_ct.cpp:181-200 (+ dinvgamma :161-176)
 __device__ __forceinline__ double dnig_log(double mu, double sig2, double m, double k, double a,
                                            double b) {
-  return dnorm_log(mu, m, sqrt(sig2 / k)) + (a * log(b) - lgamma(a) - (a + 1.0) * log(sig2) - b / sig2);
+  return dnorm_log(mu, m, sqrt(sig2 / k)) + (a * fast_log(b) - lgamma_pos(a) - (a + 1.0) * fast_log(sig2) - b / sig2);
 }
 
 // gsimconNNIG, utils_ct.cpp:427-459 (generic path; not the default similarity)
-__device__ inline double gsim_nnig(const SimConst &c, double sumx, double sumx2, int n, int DD) {
+static __device__ __noinline__ double gsim_nnig(const SimConst &c, double sumx, double sumx2, int n, int DD) {
   const double mu = 10.0, v2 = 0.1;
   const double dn = (double)n;
   const double xbar = sumx * (1.0 / dn);
@@ -81,7 +81,7 @@ __device__ inline double gsim_nnig(const SimConst &c, double sumx, double sumx2,
 }
 
 // gsimcatDM, utils_ct.cpp:468-495, for counts cnt[c*cstride] (+1 at category `add`, -1 = none)
-__device__ inline double gsim_cat(const SimConst &s, const int *cnt, int cstride, int add, int C,
+static __device__ __noinline__ double gsim_cat(const SimConst &s, const int *cnt, int cstride, int add, int C,
                                   int DD, bool zero_counts) {
   int sumc = 0;
   double tmp1 = 0.0, tmp2 = 0.0, tmp3 = 0.0, tmp4 = 0.0, tmp5 = 0.0, tmp6 = 0.0;
@@ -91,16 +91,16 @@ __device__ inline double gsim_cat(const SimConst &s, const int *cnt, int cstride
     const double dn = (double)nc;
     sumc += nc;
     tmp1 += s.dirw;
-    tmp2 += lgamma(s.dirw);
+    tmp2 += lgamma_pos(s.dirw);
     tmp3 += dn + s.dirw;
-    tmp4 += lgamma(dn + s.dirw);
+    tmp4 += lgamma_pos(dn + s.dirw);
     if (DD) {
       tmp5 += 2.0 * dn + s.dirw;
-      tmp6 += lgamma(2.0 * dn + s.dirw);
+      tmp6 += lgamma_pos(2.0 * dn + s.dirw);
     }
   }
-  double out = (lgamma(tmp1) - tmp2) + (tmp4 - lgamma(tmp3));
-  if (DD) out = (lgamma(tmp3) - tmp4) + (tmp6 - lgamma(tmp5));
+  double out = (lgamma_pos(tmp1) - tmp2) + (tmp4 - lgamma_pos(tmp3));
+  if (DD) out = (lgamma_pos(tmp3) - tmp4) + (tmp6 - lgamma_pos(tmp5));
   if (sumc == 0) out = 0.0;
   return out;
 }
