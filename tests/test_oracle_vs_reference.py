@@ -125,7 +125,10 @@ def test_dmvnrm_and_calculate_gamma_match_reference(ref):
 # (sigma, kappa) update, src/dm_ppmx_ct.cpp:928, 942), so those cases run with DP cohesion here.
 RUNS = [("default_ngg", {}), ("dp_T3", {}), ("nnig", {}), ("nnig_dd", {}), ("calib1", {}), ("calib2_sqrt", {}),
         ("calib2", {}), ("noreuse", {}), ("ppm_only", {}), ("categorical", {}), ("Q3_D3", {}),
-        ("double_dipper", {"cohesion": 1}), ("cat_dd_calib1", {"cohesion": 1})]
+        ("double_dipper", {"cohesion": 1}), ("cat_dd_calib1", {"cohesion": 1}),
+        # the switches of the update part: no prognostic coefficients, frozen hierarchy, no horseshoe
+        ("default_ngg", {"noprog": 1}), ("dp_T3", {"upd_hier": 0}), ("default_ngg", {"hsp": 0}),
+        ("dp_T3", {"noprog": 1, "upd_hier": 0, "hsp": 0})]
 
 
 def _run_both(ref, name, over, iters, burn, thin, seed):
@@ -150,7 +153,7 @@ def _compare(got, want, tape):
     assert got["WAIC"] == pytest.approx(want["WAIC"], rel=1e-12)
 
 
-@pytest.mark.parametrize("name,over", RUNS, ids=[r[0] for r in RUNS])
+@pytest.mark.parametrize("name,over", RUNS, ids=[r[0] + "".join(f"-{k}{v}" for k, v in r[1].items()) for r in RUNS])
 def test_reference_run_on_the_oracle_tape(ref, name, over):
     got, want, tape = _run_both(ref, name, over, iters=40, burn=10, thin=3, seed=11)
     _compare(got, want, tape)
