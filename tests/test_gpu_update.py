@@ -74,6 +74,30 @@ def test_run_lockstep_with_oracle(ctx, name):
         _compare(b.get_state(c), st, dims, f"{name} chain {c} after {niter} iterations")
 
 
+@pytest.mark.parametrize("over", [dict(hsp=0), dict(upd_hier=0), dict(noprog=1, hsp=0, upd_hier=0)],
+                         ids=["hsp0", "upd_hier0", "noprog1-hsp0-upd_hier0"])
+def test_run_lockstep_with_the_update_switches_off(ctx, over):
+    """The switches of the update part (no horseshoe / frozen hierarchy / no prognostic coefficients):
+    tppmx_batch_run (horseshoe on its own stream when on) and single tppmx_batch_update calls
+    (horseshoe inside the gamma-draw kernel) against the oracle."""
+    from treatppmx_b200.engine import Batch
+    model, dims, shared, dsets, labels, nclu, betas = build_case("default_ngg")
+    for k, v in over.items():
+        setattr(model, k, v)
+    nchains, niter = 3, 12
+    pb = ob.Problem(model, dims, shared, dsets[0])
+    b = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0] * nchains)
+    b.init(29, labels, nclu, betas[0])
+    b.run(29, 0, niter)
+    for l in range(niter, niter + 3):
+        b.sweep(29, l, 1)
+        b.update(29, l)
+    for c in range(nchains):
+        st = pb.init_state(29, c, labels, nclu, betas[0])
+        pb.iterate(st, 29, c, 0, niter + 3)
+        _compare(b.get_state(c), st, dims, f"{over} chain {c}")
+
+
 def test_run_accumulates_on_saved_iterations(ctx):
     from treatppmx_b200.engine import Batch
     model, dims, shared, dsets, labels, nclu, betas = build_case("default_ngg", n_datasets=2)
