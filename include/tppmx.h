@@ -220,6 +220,18 @@ int tppmx_score_patient(tppmx_batch *b, int32_t chain, int32_t arm, int32_t it,
  * frozen.  Iteration numbers iter0..iter0+n_sweeps-1 key the RNG.  */
 int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sweeps);
 
+/* Parity hook of the PRODUCTION kernel.  Runs ONE sweep (iteration `iter`) of every chain exactly
+ * as tppmx_batch_sweep does, through an instantiation of the fast sweep kernel that also records,
+ * for every step of chain `chain`, the normalised allocation probabilities the draw is made from
+ * (reference pweight, src/dm_ppmx_ct.cpp:791-802) and the number of occupied clusters after the
+ * removal.  The state advances like a normal sweep, so lock-step with the oracle is kept.
+ *   prob_out [T][ntmax][stride] (row = position in the arm; entries 0..K+CC-1 are filled)
+ *   K_out    [T][ntmax]         (-1: the step was not run by the fast kernel -- hand-over -- or
+ *                                lies beyond the arm)
+ * stride >= min(kcap, 32) + CC.  Fails when the model is not eligible for the fast kernel. */
+int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t chain,
+                            int32_t stride, double *prob_out, int32_t *K_out);
+
 /* Kernel selection.  The library has two sweep kernels with identical results:
  *   fast    — default switches (PPMx=1, consim=1, similarity=1, calibration 0|2, ncat=0,
  *             reuse=1): cluster statistics staged in shared memory, likelihood terms hoisted

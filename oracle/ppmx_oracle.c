@@ -753,6 +753,36 @@ int oracle_sweep(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32
   return 0;
 }
 
+/* One sweep (iteration l) that also records, per step, the normalised allocation probabilities
+ * pweight (:791-802) and the number of occupied clusters after the removal: what the device's
+ * probe instantiation of the production kernel is compared with (tppmx_batch_sweep_probe).
+ * prob_out [T][ntmax][stride], K_out [T][ntmax]; entries beyond min(K+CC, stride) are left. */
+int oracle_sweep_probe(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,
+                       int32_t l, int32_t stride, double *prob_out, int32_t *K_out) {
+  o_ctx cc, *c = &cc;
+  if (o_ctx_open(c, pb, s, seed, chain_id)) return 1;
+  const tppmx_model *m = &pb->model;
+  double *row = (double *)malloc(sizeof(double) * (size_t)(c->ntmax + c->CC));
+  for (int tt = 0; tt < c->T; tt++) {
+    if (m->reuse == 1)
+      for (int mm = 0; mm < c->CC; mm++)
+        o_rng_normals(&c->rng, (uint32_t)l, TPPMX_SITE_AUX_SWEEP, (uint32_t)tt, (uint32_t)mm, 0, c->D, &ETAE(0, mm, tt));
+    int it = 0;
+    for (int i = 0; i < c->nobs; i++) {
+      if (pb->data.treat[i] != tt) continue;
+      int K = 0;
+      o_realloc_patient(c, tt, it, i, l, 0, NULL, row, &K);
+      const int ntot = K + c->CC, ncp = ntot < stride ? ntot : stride;
+      memcpy(prob_out + ((size_t)tt * c->ntmax + it) * stride, row, sizeof(double) * ncp);
+      K_out[(size_t)tt * c->ntmax + it] = K;
+      it += 1;
+    }
+  }
+  free(row);
+  o_ctx_close(c);
+  return 0;
+}
+
 /* ---------------------------------------------------------------------------------------
  * posterior predictive, src/dm_ppmx_ct.cpp:1081-1384
  * ------------------------------------------------------------------------------------- */

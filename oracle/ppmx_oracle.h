@@ -76,6 +76,11 @@ int oracle_score_patient(const oracle_problem *pb, const tppmx_state *s, int32_t
 int oracle_sweep(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,
                  int32_t iter0, int32_t n_sweeps);
 
+/* one sweep (iteration l) recording each step's pweight (:791-802) and K after removal:
+ * prob_out [T][ntmax][stride], K_out [T][ntmax] */
+int oracle_sweep_probe(const oracle_problem *pb, tppmx_state *s, uint64_t seed, uint32_t chain_id,
+                       int32_t l, int32_t stride, double *prob_out, int32_t *K_out);
+
 /* src/dm_ppmx_ct.cpp:1081-1384 */
 int oracle_predict(const oracle_problem *pb, const tppmx_state *s, uint64_t seed,
                    uint32_t chain_id, int32_t iter, double *pipred, double *ypred,

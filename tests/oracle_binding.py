@@ -57,6 +57,7 @@ def lib():
                                            c_dp, c_dp, c_ip]
         L.oracle_sweep.argtypes = [P, S, u64, u32, C.c_int32, C.c_int32]
         L.oracle_predict.argtypes = [P, S, u64, u32, C.c_int32, c_dp, c_dp, c_ip]
+        L.oracle_sweep_probe.argtypes = [P, S, u64, u32, C.c_int32, C.c_int32, c_dp, c_ip]
         i32p = c_ip
         L.oracle_update_iter.argtypes = [P, S, u64, u32, C.c_int32, i32p, i32p]
         L.oracle_iterate.argtypes = [P, S, u64, u32, C.c_int32, C.c_int32, i32p, i32p]
@@ -115,6 +116,17 @@ class Problem:
         cs = s.cstruct()
         rc = lib().oracle_sweep(C.byref(self.c), C.byref(cs), seed, chain_id, iter0, n_sweeps)
         assert rc == 0, rc
+
+    def sweep_probe(self, s: HostState, seed, chain_id, iter_, stride):
+        """One sweep recording every step's allocation probabilities: (prob [T, ntmax, stride], K [T, ntmax])."""
+        d = self.dims
+        prob = np.zeros((d.T, d.ntmax, stride))
+        K = np.full((d.T, d.ntmax), -1, dtype=np.int32)
+        cs = s.cstruct()
+        rc = lib().oracle_sweep_probe(C.byref(self.c), C.byref(cs), seed, chain_id, iter_, stride,
+                                      prob.ctypes.data_as(c_dp), K.ctypes.data_as(c_ip))
+        assert rc == 0, rc
+        return prob, K
 
     def new_acc(self):
         d = self.dims

@@ -16,7 +16,7 @@ SYMBOLS = [
     "tppmx_batch_create", "tppmx_batch_destroy", "tppmx_batch_init",
     "tppmx_batch_set_state", "tppmx_batch_get_state", "tppmx_batch_get_partitions",
     "tppmx_score_patient",
-    "tppmx_batch_sweep", "tppmx_batch_set_option", "tppmx_batch_get_info",
+    "tppmx_batch_sweep", "tppmx_batch_sweep_probe", "tppmx_batch_set_option", "tppmx_batch_get_info",
     "tppmx_batch_last_timing", "tppmx_batch_predict",
     "tppmx_batch_accumulate", "tppmx_batch_summaries", "tppmx_batch_summaries_device",
     "tppmx_batch_reset_summaries", "tppmx_batch_update", "tppmx_batch_run", "tppmx_batch_get_acceptance",
@@ -58,6 +58,7 @@ def load():
     L.tppmx_batch_get_partitions.argtypes = [vp, c_ip, c_ip]
     L.tppmx_score_patient.argtypes = [vp, i32, i32, i32, u64, i32, c_dp, c_dp, c_ip]
     L.tppmx_batch_sweep.argtypes = [vp, u64, i32, i32]
+    L.tppmx_batch_sweep_probe.argtypes = [vp, u64, i32, i32, i32, c_dp, c_ip]
     L.tppmx_batch_set_option.argtypes = [vp, i32, i32]
     L.tppmx_batch_get_info.argtypes = [vp, i32, c_ip]
     L.tppmx_batch_last_timing.argtypes = [vp, c_dp, c_ip]

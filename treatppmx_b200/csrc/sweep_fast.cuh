@@ -161,7 +161,7 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
                                              int K, int CC, int KS, int P, const double *xs, double qx,
                                              double uu, double dV, double simscale, double iv2,
                                              double c0, double hiv2, bool nolik, bool mine, int ul,
-                                             int sub) {
+                                             int sub, double *prow, int pstride) {
   const int ntot = mine ? K + CC : 0;
   const int ntot_w = warp_max_over_units<LPU>(ntot);
   double wmax = -INFINITY;
@@ -195,6 +195,8 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
   }
   __syncwarp();
   den = unit_sum<LPU>(den);
+  if (prow && mine)  // parity probe: the normalised probabilities the draw is made from
+    for (int j = ul; j < ntot && j < pstride; j += LPU) prow[j] = U.wsc[j] / den;
   const double thr = uu * den;
   int newci = ntot;
   bool found = false;
@@ -214,7 +216,7 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
   return newci;
 }
 
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG>
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
 __global__ void __launch_bounds__(32, 12)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -588,11 +590,23 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         unsigned hit = __ballot_sync(TPPMX_FULL, act0 && (uu * den < cum));
         hit = (LPU == 32) ? hit : ((hit >> (sub * LPU)) & ((1u << LPU) - 1u));
         newci = hit ? __ffs(hit) : ntot;  // :807 default when rounding leaves uu >= total
+        if constexpr (PROBE) {
+          const int pu = unit - fa.probe_unit0;
+          if (on && pu >= 0 && pu < fa.probe_nunits) {
+            if (act0 && ul < fa.probe_stride) fa.probe[((size_t)pu * ntp + it) * fa.probe_stride + ul] = e0 / den;
+            if (ul == 0) fa.probe_k[(size_t)pu * ntp + it] = K;
+          }
+        }
       }
       const bool multi = on && ntot > LPU;
       if (anymulti && __any_sync(TPPMX_FULL, multi)) {
+        double *prow = nullptr;
+        if constexpr (PROBE) {
+          const int pu = unit - fa.probe_unit0;
+          if (pu >= 0 && pu < fa.probe_nunits) prow = fa.probe + ((size_t)pu * ntp + it) * fa.probe_stride;
+        }
         const int r = fast_score_multi<LPU>(U, tab2, lognp, lik, ntp, it, K, CC, KS, P, xs, qx, uu, dV,
-                                            simscale, iv2, c0, hiv2, NOLIK, multi, ul, sub);
+                                            simscale, iv2, c0, hiv2, NOLIK, multi, ul, sub, prow, fa.probe_stride);
         if (multi) newci = r;
       }
 
@@ -714,15 +728,24 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
 }
 
 // ---- launch: instantiation picked from the batch shape (one translation unit per LPU) ----------
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG>
-static cudaError_t fast_launch5(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
+static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
+}
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG>
+static cudaError_t fast_launch5(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
+                                int n_sweeps, cudaStream_t stream) {
+  if (fa.probe) {  // parity probe: instantiated for the package's case (D <= 3, likelihood on) only
+    if constexpr (DR == 3 && !NOLIK) return fast_launch6<LPU, XR, DR, NOLIK, BIG, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
+    return cudaErrorInvalidConfiguration;
+  }
+  return fast_launch6<LPU, XR, DR, NOLIK, BIG, false>(d, fa, smem, seed, iter0, n_sweeps, stream);
 }
 template <int LPU, int XR, int DR, bool NOLIK>
 static cudaError_t fast_launch4(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,

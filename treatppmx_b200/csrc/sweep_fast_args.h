@@ -27,6 +27,12 @@ struct FastArgs {
   double *tabg;     // [ntmax + 2][4]  (dA, HN, HY, -) per cluster size n (filled once at batch creation)
   double *logng;    // [units][ntp + 1]
   int *patpad;      // [units][ntp + 1] patient order of the unit, zero-padded
+  // parity probe (tppmx_batch_sweep_probe): the PROBE instantiations record, for the units
+  // probe_unit0 .. probe_unit0 + probe_nunits - 1, every step's normalised allocation probabilities
+  // (exactly the e / den the draw is made from) and the number of occupied clusters after removal
+  double *probe;    // [probe_nunits][ntp][probe_stride], nullptr = production instantiation
+  int *probe_k;     // [probe_nunits][ntp], -1 = step not visited by the fast kernel (hand-over)
+  int probe_stride, probe_unit0, probe_nunits;
 };
 
 __host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }

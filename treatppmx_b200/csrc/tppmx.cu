@@ -1069,6 +1069,62 @@ extern "C" int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, i
   return check_status(b);
 }
 
+// Parity probe of the PRODUCTION sweep kernel (include/tppmx.h): one sweep of every chain through the
+// PROBE instantiation of sweep_fast_kernel, which records each step's normalised allocation
+// probabilities for the units of `chain`.
+extern "C" int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t chain, int32_t stride,
+                                       double *prob_out, int32_t *K_out) {
+  if (!b || !prob_out || !K_out) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (chain < 0 || chain >= d.n_chains) return fail(ctx, TPPMX_ERR_ARG, "chain out of range");
+  const int ksmax = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
+  if (stride < ksmax + d.CC) return fail(ctx, TPPMX_ERR_ARG, "stride must be >= min(kcap, 32) + CC");
+  if (b->opt_impl == 1 || !b->fa.lik) return fail(ctx, TPPMX_ERR_ARG, "the probe exists for the fast sweep kernel only");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const int T = d.T, ntp = (d.ntmax + 3) & ~3;
+  const size_t np = (size_t)T * ntp * stride, nk = (size_t)T * ntp;
+  double *dp = nullptr;
+  int *dk = nullptr;
+  CK(ctx, cudaMalloc(&dp, sizeof(double) * np));
+  if (cudaMalloc(&dk, sizeof(int) * nk) != cudaSuccess) {
+    cudaFree(dp);
+    return fail(ctx, TPPMX_ERR_NOMEM, "probe buffers");
+  }
+  cudaMemsetAsync(dp, 0, sizeof(double) * np, ctx->stream);
+  cudaMemsetAsync(dk, 0xFF, sizeof(int) * nk, ctx->stream);
+  b->fa.probe = dp;
+  b->fa.probe_k = dk;
+  b->fa.probe_stride = stride;
+  b->fa.probe_unit0 = chain * T;
+  b->fa.probe_nunits = T;
+  const int impl0 = b->opt_impl;
+  b->opt_impl = 2;
+  b->last_handovers = 0;
+  int launches = 0;
+  int rc = sweep_launch(b, seed, iter, 1, true, &launches);
+  b->opt_impl = impl0;
+  b->fa.probe = nullptr;
+  b->fa.probe_k = nullptr;
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "sweep probe: kernel failure");
+  if (!rc) {
+    std::vector<double> hp(np);
+    std::vector<int> hk(nk);
+    cudaError_t e = cpy_sync(ctx->stream, hp.data(), dp, sizeof(double) * np, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cpy_sync(ctx->stream, hk.data(), dk, sizeof(int) * nk, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, std::string("sweep probe: ") + cudaGetErrorString(e));
+    for (int t = 0; t < T && !rc; t++)
+      for (int it = 0; it < d.ntmax; it++) {
+        K_out[(size_t)t * d.ntmax + it] = hk[(size_t)t * ntp + it];
+        memcpy(prob_out + ((size_t)t * d.ntmax + it) * stride, hp.data() + ((size_t)t * ntp + it) * stride, sizeof(double) * stride);
+      }
+  }
+  cudaFree(dp);
+  cudaFree(dk);
+  if (!rc) rc = check_status(b);
+  return rc;
+}
+
 // ev_after_update (optional): recorded between the update kernel and the gamma draws, so that work
 // which only needs eta*, beta, (Theta,Sigma), (sigma,kappa) can start beside the draws
 // the main stream rejoins a horseshoe update still running on the third stream

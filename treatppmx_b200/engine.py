@@ -141,6 +141,18 @@ class Batch:
     def sweep(self, seed: int, iter0: int, n_sweeps: int):
         self.ctx.check(self.ctx.L.tppmx_batch_sweep(self.h, seed, iter0, n_sweeps))
 
+    def sweep_probe(self, seed: int, iter_: int, chain: int):
+        """One sweep of every chain through the probe instantiation of the fast sweep kernel: returns
+        (prob [T, ntmax, W], K [T, ntmax]) of `chain` -- each step's normalised allocation
+        probabilities and occupied-cluster count (-1 where the fast kernel did not run the step)."""
+        d = self.dims
+        W = min(d.kcap if d.kcap > 0 else d.ntmax, 32) + self.model.CC
+        prob = np.zeros((d.T, d.ntmax, W))
+        K = np.zeros((d.T, d.ntmax), dtype=np.int32)
+        self.ctx.check(self.ctx.L.tppmx_batch_sweep_probe(self.h, seed, iter_, chain, W, prob.ctypes.data_as(c_dp),
+                                                          K.ctypes.data_as(c_ip)))
+        return prob, K
+
     # kernel selection (include/tppmx.h: TPPMX_OPT_*, TPPMX_INFO_*)
     IMPL = {"auto": 0, "generic": 1, "fast": 2}
 
