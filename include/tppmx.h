@@ -178,7 +178,8 @@ int tppmx_set_interrupt_flag(tppmx_ctx *ctx, const volatile int32_t *flag, int32
 const char *tppmx_last_error(const tppmx_ctx *ctx);
 
 /* Test hook: evaluates the library's device fp64 math on n inputs (which: 0 = log, 1 = exp,
- * 2 = lgamma for x > 0, 3 = table-driven log; the branch-free versions the fast sweep kernel uses). */
+ * 2 = lgamma for x > 0 in Stirling form, 3 = table-driven log, 4 = table-driven lgamma; the
+ * branch-free versions the kernels use). */
 int tppmx_probe_math(tppmx_ctx *ctx, int32_t which, const double *x, int32_t n, double *out);
 
 /* ---- batch of chains ---------------------------------------------------------------- */

@@ -51,7 +51,7 @@ __device__ __forceinline__ double dnorm_log(double x, double mu, double sd) {
 // dN_IG(mu, sig2; m, k, a, b) on the log scale, utils_ct.cpp:181-200 (+ dinvgamma :161-176)
 __device__ __forceinline__ double dnig_log(double mu, double sig2, double m, double k, double a,
                                            double b) {
-  return dnorm_log(mu, m, sqrt(sig2 / k)) + (a * fast_log(b) - lgamma_pos(a) - (a + 1.0) * fast_log(sig2) - b / sig2);
+  return dnorm_log(mu, m, sqrt(sig2 / k)) + (a * fast_log(b) - lgamma_fast(a) - (a + 1.0) * fast_log(sig2) - b / sig2);
 }
 
 // gsimconNNIG, utils_ct.cpp:427-459 (generic path; not the default similarity)
@@ -91,16 +91,16 @@ static __device__ __noinline__ double gsim_cat(const SimConst &s, const int *cnt
     const double dn = (double)nc;
     sumc += nc;
     tmp1 += s.dirw;
-    tmp2 += lgamma_pos(s.dirw);
+    tmp2 += lgamma_fast(s.dirw);
     tmp3 += dn + s.dirw;
-    tmp4 += lgamma_pos(dn + s.dirw);
+    tmp4 += lgamma_fast(dn + s.dirw);
     if (DD) {
       tmp5 += 2.0 * dn + s.dirw;
-      tmp6 += lgamma_pos(2.0 * dn + s.dirw);
+      tmp6 += lgamma_fast(2.0 * dn + s.dirw);
     }
   }
-  double out = (lgamma_pos(tmp1) - tmp2) + (tmp4 - lgamma_pos(tmp3));
-  if (DD) out = (lgamma_pos(tmp3) - tmp4) + (tmp6 - lgamma_pos(tmp5));
+  double out = (lgamma_fast(tmp1) - tmp2) + (tmp4 - lgamma_fast(tmp3));
+  if (DD) out = (lgamma_fast(tmp3) - tmp4) + (tmp6 - lgamma_fast(tmp5));
   if (sumc == 0) out = 0.0;
   return out;
 }
@@ -183,7 +183,7 @@ __device__ __forceinline__ double lik_term(int D, const double *eta, int estride
   for (int k = 0; k < D; k++) {
     const double lgk = eta[(size_t)k * estride] + zb[k];
     const double g = lgk > 709.0 ? INFINITY : fast_exp(lgk);
-    w += g * ljj[k] - lgamma_pos(g);
+    w += g * ljj[k] - lgamma_fast(g);
   }
   return w;
 }

@@ -123,7 +123,8 @@ static __device__ __noinline__ double fast_lik(const double *E, const double *Z,
     const double g0 = E[k] * Z[k];
     const double g1 = h1 ? E[k + 1] * Z[k + 1] : 1.0;
     const double g2 = h2 ? E[k + 2] * Z[k + 2] : 1.0;
-    const double l0 = lgamma_pos(g0), l1 = lgamma_pos(g1), l2 = lgamma_pos(g2);
+    double l0, l1, l2;
+    lgamma_fast3(g0, g1, g2, l0, l1, l2);
     w += fma(g0, ljj[k], -l0);
     if (h1) w += fma(g1, ljj[k + 1], -l1);
     if (h2) w += fma(g2, ljj[k + 2], -l2);
@@ -144,7 +145,8 @@ __device__ __forceinline__ double fast_lik_reg(const double *E, const double (&Z
       const double g0 = E[k] * Z[k];
       const double g1 = h1 ? E[k + 1] * Z[(k + 1 < DR) ? k + 1 : k] : 1.0;
       const double g2 = h2 ? E[k + 2] * Z[(k + 2 < DR) ? k + 2 : k] : 1.0;
-      const double l0 = lgamma_pos(g0), l1 = lgamma_pos(g1), l2 = lgamma_pos(g2);
+      double l0, l1, l2;
+    lgamma_fast3(g0, g1, g2, l0, l1, l2);
       w += fma(g0, ljj[k], -l0);
       if (h1) w += fma(g1, ljj[(k + 1 < DR) ? k + 1 : k], -l1);
       if (h2) w += fma(g2, ljj[(k + 2 < DR) ? k + 2 : k], -l2);

@@ -87,7 +87,7 @@ __device__ __forceinline__ double d_dmvn_log(const double *x, int xstride, const
 // Out-of-line copies of the heavy helpers: the kernel has ~15 call sites of Philox / gamma /
 // lgamma; inlined, the code grows to ~270 KB and the instruction cache, not the math, bounds it
 // (profiles/r1_update_kernel_*: stall_no_instruction 3.8 per issue).
-__device__ __noinline__ double upd_lgamma(double x) { return lgamma_pos(x); }
+__device__ __noinline__ double upd_lgamma(double x) { return lgamma_fast(x); }
 __device__ __noinline__ double upd_gamma(Rng g, uint32_t iter, uint32_t site, uint32_t arm, uint32_t index, double a) {
   return rng_gamma(g, iter, site, arm, index, a);
 }

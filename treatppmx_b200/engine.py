@@ -50,7 +50,7 @@ class Context:
         """Device fp64 log / exp / lgamma of the fast sweep kernel on an array (test hook)."""
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = np.empty_like(x)
-        self.check(self.L.tppmx_probe_math(self.h, {"log": 0, "exp": 1, "lgamma": 2, "logtab": 3}[which],
+        self.check(self.L.tppmx_probe_math(self.h, {"log": 0, "exp": 1, "lgamma": 2, "logtab": 3, "lgammatab": 4}[which],
                                            x.ctypes.data_as(c_dp), x.size, out.ctypes.data_as(c_dp)))
         return out
 
