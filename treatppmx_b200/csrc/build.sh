@@ -23,6 +23,12 @@ build_variant() {  # $1 = output .so, $2 = object dir, rest = extra flags
   echo "built ${out}"
 }
 
+# experiment builds: TPPMX_VARIANT=name [TPPMX_NVCC_EXTRA="-DX=1 ..."] -> libtppmx_name.so (A/B runs
+# select it with TPPMX_LIB=...); the default build is untouched
+if [ -n "${TPPMX_VARIANT:-}" ]; then
+  build_variant "${HERE}/../libtppmx_${TPPMX_VARIANT}.so" "${HERE}/build/obj_${TPPMX_VARIANT}"
+  exit 0
+fi
 build_variant "${HERE}/../libtppmx.so" "${HERE}/build/obj"
 # optional debug variant with device-side index assertions (tests: TPPMX_LIB=.../libtppmx_check.so)
 if [ "${TPPMX_BUILD_CHECK:-0}" = "1" ]; then

@@ -137,7 +137,7 @@ __device__ __forceinline__ double lgamma_pos(double x) {
   return lg - fast_log_tab(small ? p : 1.0);
 }
 
-// lgamma(x), x > 0, table-driven: on [2^EMIN, 2^EMAX) the top four mantissa bits pick one of 16
+// lgamma(x), x > 0, table-driven (an OPTION, see lgamma_fast below): on [2^EMIN, 2^EMAX) the top four mantissa bits pick one of 16
 // intervals per octave and a degree-7 polynomial in (x - midpoint) (scripts/gen_lgammatab.py;
 // 64-byte rows read through the L1).  The midpoint is recovered from the bits of x and x - midpoint
 // is exact, so the error is one rounding of the leading coefficient: <= 8e-16 (1 + |lgamma|),
@@ -155,27 +155,59 @@ __device__ __forceinline__ double lgamma_tab_core(double x, bool &oor) {
   oor = (unsigned)idx >= (unsigned)TPPMX_LGT_ROWS;
   idx = oor ? 0 : idx;
   const double t = x - __hiloint2double((hi & 0xFFFF0000) | 0x00008000, 0);
-  const double2 *row = reinterpret_cast<const double2 *>(LGTAB) + 4 * idx;
-  const double2 c01 = __ldg(row), c23 = __ldg(row + 1), c45 = __ldg(row + 2), c67 = __ldg(row + 3);
+  // one 64-byte row = two 256-bit loads (LDG.E.256, sm_100): the lanes of a warp hit different rows,
+  // and every load instruction costs the L1 one tag look-up per lane whatever its width
+  const double *row = LGTAB + 8 * idx;
+  double c0, c1, c2, c3, c4, c5, c6, c7;
+#ifdef TPPMX_LGAMMA_LDG128
+  {
+    const double2 *r2 = reinterpret_cast<const double2 *>(row);
+    const double2 c01 = __ldg(r2), c23 = __ldg(r2 + 1), c45 = __ldg(r2 + 2), c67 = __ldg(r2 + 3);
+    c0 = c01.x; c1 = c01.y; c2 = c23.x; c3 = c23.y; c4 = c45.x; c5 = c45.y; c6 = c67.x; c7 = c67.y;
+  }
+#else
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3) : "l"(row));
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c4), "=d"(c5), "=d"(c6), "=d"(c7) : "l"(row + 4));
+#endif
   const double t2 = t * t;
-  double pe = fma(c67.x, t2, c45.x), po = fma(c67.y, t2, c45.y);  // even / odd halves: depth 4, not 7
-  pe = fma(pe, t2, c23.x);
-  po = fma(po, t2, c23.y);
-  pe = fma(pe, t2, c01.x);
-  po = fma(po, t2, c01.y);
+  double pe = fma(c6, t2, c4), po = fma(c7, t2, c5);  // even / odd halves: depth 4, not 7
+  pe = fma(pe, t2, c2);
+  po = fma(po, t2, c3);
+  pe = fma(pe, t2, c0);
+  po = fma(po, t2, c1);
   return fma(po, t, pe);
 }
 
-__device__ __forceinline__ double lgamma_fast(double x) {
+__device__ __forceinline__ double lgamma_tab(double x) {
   bool oor;
   double l = lgamma_tab_core(x, oor);
   if (__builtin_expect(oor, 0)) l = lgamma_cold(x);
   return l;
 }
 
+// What the kernels call.  Measured on B200 (1024 chains, bench workload, profiles/r2_lgamma_ab.txt):
+// the table form executes 12 % fewer instructions in the sweep kernel but is 1.7 % SLOWER
+// (1.247e9 against 1.268e9 reallocations/s; with 128-bit row loads 1.203e9): every lane of a warp
+// reads a different 64-byte row, each load instruction costs the L1 one tag look-up per lane, and
+// the kernel is bound by the latency of its dependent chains, not by issue slots.  The Stirling
+// form stays the default; -DTPPMX_LGAMMA_TABLE selects the table.
+__device__ __forceinline__ double lgamma_fast(double x) {
+#ifdef TPPMX_LGAMMA_TABLE
+  return lgamma_tab(x);
+#else
+  return lgamma_pos(x);
+#endif
+}
+
 // three at once: the table evaluations are straight-line and interleave (twelve loads in flight,
 // three independent fma chains); one rarely taken branch repairs out-of-table arguments
 __device__ __forceinline__ void lgamma_fast3(double x0, double x1, double x2, double &l0, double &l1, double &l2) {
+#ifndef TPPMX_LGAMMA_TABLE
+  l0 = lgamma_pos(x0);
+  l1 = lgamma_pos(x1);
+  l2 = lgamma_pos(x2);
+  return;
+#endif
   bool o0, o1, o2;
   l0 = lgamma_tab_core(x0, o0);
   l1 = lgamma_tab_core(x1, o1);

@@ -218,8 +218,11 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
   return newci;
 }
 
+#ifndef TPPMX_FAST_MINB
+#define TPPMX_FAST_MINB 12
+#endif
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
-__global__ void __launch_bounds__(32, 12)
+__global__ void __launch_bounds__(32, TPPMX_FAST_MINB)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
   constexpr int KSTR = TPPMX_FAST_KSTR;

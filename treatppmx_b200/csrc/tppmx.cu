@@ -166,7 +166,7 @@ extern "C" const char *tppmx_last_error(const tppmx_ctx *c) { return c ? c->err.
 __global__ void probe_math_kernel(int which, const double *x, int n, double *out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = which == 0 ? fast_log(x[i]) : which == 1 ? fast_exp(x[i]) : which == 2 ? lgamma_pos(x[i]) : which == 3 ? fast_log_tab(x[i]) : lgamma_fast(x[i]);
+  out[i] = which == 0 ? fast_log(x[i]) : which == 1 ? fast_exp(x[i]) : which == 2 ? lgamma_pos(x[i]) : which == 3 ? fast_log_tab(x[i]) : lgamma_tab(x[i]);
 }
 
 extern "C" int tppmx_probe_math(tppmx_ctx *ctx, int32_t which, const double *x, int32_t n, double *out) {
