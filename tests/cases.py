@@ -1,6 +1,8 @@
 """Shared definitions of the parity cases (used by the GPU tests and the golden generator)."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from treatppmx_b200 import datagen
@@ -25,7 +27,26 @@ CASES = {
 }
 
 
+SIMUPATS_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "simupats_config1.npz")
+# BASELINE config 1: ppmxct() on the bundled simupats data through the genmech recipe, default
+# switches; NGG cohesion with the in-repo V table, and DP cohesion (no third-party table involved)
+SIMUPATS_CASES = {"simupats_ngg": dict(cohesion=2), "simupats_dp": dict(cohesion=1, alpha=1.0)}
+
+
+def build_simupats_case(name: str):
+    """(model, dims, shared, [dataset], labels, nclu, [beta0]) of config 1 from the committed fixture
+    (tests/golden/make_simupats_fixture.py; the GPU box has no /root/reference)."""
+    from treatppmx_b200 import simupats
+    f = np.load(SIMUPATS_FIXTURE)
+    sim = dict(cov=f["cov"], Y=f["Y"], treatment=f["treatment"])
+    model, dims, shared, dsets, labels, nclu, beta0 = simupats.ppmxct_inputs(
+        sim, init=(f["init_labels"], f["init_nclu"]), **SIMUPATS_CASES[name])
+    return model, dims, shared, dsets, labels, nclu, [beta0]
+
+
 def build_case(name: str, n_datasets: int = 1, seed: int = 20240001, kcap: int = 0):
+    if name in SIMUPATS_CASES:
+        return build_simupats_case(name)
     mkw, dkw = CASES[name]
     dkw = dict(dkw)
     dkw.setdefault("n", 152)

@@ -26,6 +26,10 @@ REF_GOLDEN = {  # name -> (iters, burn, thin, seed)
     "noreuse": (30, 10, 2, 8),
     "categorical": (30, 10, 2, 9),
     "Q3_D3": (30, 10, 2, 10),
+    # BASELINE config 1: the bundled simupats data (tests/golden/simupats_config1.npz), ppmxct()'s default
+    # chain length iter = 1100 / burn = 100, thinned to 50 saved iterations to keep the file small
+    "simupats_ngg": (1100, 100, 20, 121),
+    "simupats_dp": (1100, 100, 20, 122),
 }
 
 
@@ -35,7 +39,10 @@ def path(name):
 
 def main():
     R = refrun.RefLib()
+    only = sys.argv[1:]
     for name, (iters, burn, thin, seed) in REF_GOLDEN.items():
+        if only and name not in only:
+            continue
         args, _, case = refrun.reference_args(name, iters, burn, thin, True)
         with refrun.Tape() as tape:
             refrun.oracle_run(case, iters, burn, thin, seed)
