@@ -352,6 +352,37 @@ typedef struct tppmx_ppmxct_out { /* names of the returned list, :1453-1471 */
 
 int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *in, tppmx_ppmxct_out *out);
 
+/* ---- drop-in for the package's second sampler ------------------------------------------------
+ * tppmx_prior_ppmx_core runs what prior_ppmx_core() runs (reference src/prior_ppmx.cpp:9-466;
+ * .Call entry _treatppmx_prior_ppmx_core, src/RcppExports.cpp:189; R wrapper R/prior_ppmx.R:32-132):
+ * the reallocation sweep with ONE arm, continuous covariates only and NO likelihood term, from the
+ * same 21 arguments in the reference's order and layouts, into the two elements of its returned
+ * list.  Entirely on the device: one sweep launch per iteration and one save kernel per saved
+ * iteration ((l > burn-1) && (l+1) % thin == 0, :455), nothing returns to the host in between.
+ * Extra inputs: the leading dimensions of Vwm, `seed`, and n_chains (>= 1 independent replicas of
+ * the run, Philox stream ids 0..n_chains-1; the reference runs one). */
+typedef struct tppmx_prior_args {
+  int32_t iter, burn, thin, nobs, PPMx, ncon, ncat;
+  double alpha, sigma;
+  const double *Vwm;           /* Vwm_rows x Vwm_cols col-major, V_{n,k} itself (not its log); rows    */
+  int32_t Vwm_rows, Vwm_cols;  /* nobs-2 and nobs-1 are read (:239); may be NULL when cohesion == 1     */
+  int32_t cohesion, CC, consim, similarity, calibration, coardegree;
+  const double *xcon;          /* nobs x ncon row-major (as.vector(t(xcon)), R/prior_ppmx.R:121)        */
+  const double *similparam;    /* [7]                                                                  */
+  const double *curr_cluster;  /* [nobs] 1-based labels                                                */
+  const double *card_cluster;  /* [nobs] (recomputed from curr_cluster)                                */
+  int32_t ncluster_curr;
+  uint64_t seed;
+  int32_t n_chains;
+} tppmx_prior_args;
+
+typedef struct tppmx_prior_out { /* names of the returned list, src/prior_ppmx.cpp:463-465 */
+  double *nclu;   /* [n_chains][nout]                        number of clusters per saved iteration */
+  double *njout;  /* [n_chains][nobs x nout col-major]       cluster sizes per saved iteration      */
+} tppmx_prior_out;
+
+int tppmx_prior_ppmx_core(tppmx_ctx *ctx, const tppmx_prior_args *in, tppmx_prior_out *out);
+
 /* ---- posterior summaries on the device (what a multi-GPU run gathers) ----------------------
  * The package returns per-iteration cl_lab / pipred (src/dm_ppmx_ct.cpp:1402-1404, :1396) and
  * leaves the co-clustering matrix (mcclust::comp.psm, R/treatppmx.R:29) and the treatment

@@ -18,9 +18,14 @@
 
 #include "../../treatppmx_b200/csrc/incgamma.h" /* R::pgamma / R::qgamma stand-in, as the oracle */
 
-/* ---- the reference's declarations (src/utils_ct.h; the two samplers have no header) ---------- */
+/* ---- the reference's declarations (src/utils_ct.h; the two samplers have no header) ----------
+ * REFDRV_SHIM_ONLY (oracle/Makefile target `shim`): the same driver over the CUDA library's Rcpp shim
+ * (treatppmx_b200/csrc/rcpp_shim/treatppmx_shim.cpp), which defines the two samplers with the
+ * reference's signatures; the helper-by-helper entry points below need the reference and are left out. */
+#ifndef REFDRV_SHIM_ONLY
 #include "utils_ct.h"
 arma::vec dmvnrm(arma::mat x, arma::rowvec mean, arma::mat sigma, bool logd);
+#endif
 Rcpp::List dm_ppmx_ct(int iter, int burn, int thin, int nobs, arma::vec treatments, int PPMx, int ncon,
                       int ncat, arma::vec catvec, double alpha, arma::mat grid, arma::cube Vwm,
                       int cohesion, int CC, int reuse, int consim, int similarity, int calibration,
@@ -150,6 +155,7 @@ int ref_shim_linalg(const double *A, int n, const double *X, int m, double *inv_
   }
 }
 
+#ifndef REFDRV_SHIM_ONLY
 /* ---- src/utils_ct.cpp, function by function ---------------------------------------------------- */
 double ref_dinvgamma(double y, double a, double b, int lg) { return dinvgamma(y, a, b, lg); }
 double ref_dN_IG(double mu, double s2, double mu0, double k0, double a0, double b0, int lg) {
@@ -172,6 +178,7 @@ double ref_calculate_gamma(const double *eta, int D, int ncols, const double *Z,
 double ref_dmvnrm_log(const double *x, const double *mean, const double *sigma, int n) {
   return dmvnrm(mk_mat(x, 1, n), arma::rowvec(mk_mat(mean, 1, n)), mk_mat(sigma, n, n), true)(0);
 }
+#endif /* REFDRV_SHIM_ONLY */
 /* ---- src/dm_ppmx_ct.cpp:10-1471, the whole run -------------------------------------------------
  * Inputs are the 42 arguments in the reference's order, matrices column-major (Armadillo).  Vwm is
  * the dense cube (vr x vc x G).  Outputs are the 18 list elements, flattened column-major; fields

@@ -20,6 +20,7 @@ from cases import build_case
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(_ROOT, "oracle", "_ref", "libref.so")
+SHIM_SO = os.path.join(_ROOT, "oracle", "_ref", "libshim.so")   # the CUDA library's Rcpp shim, same driver
 REF_SRC = "/root/reference/src"
 
 RETURN_NAMES = ("eta", "beta", "sigma_ngg", "kappa_ngg", "eta_acc", "beta_acc", "cl_lab", "num_treat", "pi",
@@ -137,17 +138,35 @@ def reference_available() -> bool:
     return os.path.exists(REF_SO) or os.path.isdir(REF_SRC)
 
 
+class SeedTape:
+    """Two uniforms that make the Rcpp shim draw exactly `seed` as its Philox key
+    (seed = floor(u1 2^32) << 32 | floor(u2 2^32), treatppmx_shim.cpp:seed_from_r_rng)."""
+
+    def __init__(self, seed: int):
+        hi, lo = (seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF
+        self.kind = np.array([1.0, 1.0])
+        self.val = np.array([(hi + 0.5) / 4294967296.0, (lo + 0.5) / 4294967296.0])
+        self.aux = np.zeros(2)
+
+    def __len__(self):
+        return 2
+
+
 class RefLib:
-    def __init__(self):
-        if os.path.isdir(REF_SRC):
+    def __init__(self, so: str = REF_SO):
+        """so = REF_SO: the reference's own sources; so = SHIM_SO: the CUDA library's Rcpp shim behind
+        the same driver (make -C oracle shim), i.e. the reference's C++ signatures over the CUDA path."""
+        if so == REF_SO and os.path.isdir(REF_SRC):
             subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
-        self.L = C.CDLL(REF_SO)
+        if so == SHIM_SO and not os.path.exists(so):
+            subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "shim"], stdout=subprocess.DEVNULL)
+        self.L = C.CDLL(so)
         L, d, i = self.L, C.c_double, C.c_int
         dp = C.POINTER(C.c_double)
         L.ref_last_error.restype = C.c_char_p
         L.ref_tape_pos.restype = C.c_long
         L.ref_tape_set.argtypes = [dp, dp, dp, C.c_long]
-        for name, args in (("ref_dinvgamma", [d, d, d, i]), ("ref_dN_IG", [d, d, d, d, d, d, i]),
+        for name, args in () if so == SHIM_SO else (("ref_dinvgamma", [d, d, d, i]), ("ref_dN_IG", [d, d, d, d, d, d, i]),
                            ("ref_gsimconNN", [d, d, d, d, d, i, i, i]),
                            ("ref_gsimconNNIG", [d, d, d, d, d, d, i, i, i]), ("ref_gsimcatDM", [dp, dp, i, i, i]),
                            ("ref_calculate_gamma", [dp, i, i, dp, i, i, dp, i, i, i, i]),
@@ -176,6 +195,27 @@ class RefLib:
 
     def tape_pos(self) -> int:
         return self.L.ref_tape_pos()
+
+    def prior_ppmx_core(self, iter, burn, thin, nobs, PPMx, ncon, ncat, alpha, sigma, Vwm, cohesion, CC, consim,
+                        similarity, calibration, coardegree, xcon, similparam, curr_cluster, card_cluster,
+                        ncluster_curr, tape) -> dict:
+        """prior_ppmx_core(21 arguments) -> {"nclu": [nout], "njout": [nobs, nout]}"""
+        f = lambda x: np.require(np.asarray(x, dtype=np.float64), requirements=["F", "A", "O"])
+        V, xc, sp, cc, card = f(Vwm), f(np.ravel(xcon)), f(similparam), f(curr_cluster), f(card_cluster)
+        nout = (iter - burn) // thin
+        nclu, njout = np.zeros(nout), np.zeros((nobs, nout), order="F")
+        if isinstance(tape, int):
+            self.rng_free(tape)
+        else:
+            self.set_tape(tape.kind, tape.val, tape.aux)
+        i, d = C.c_int, C.c_double
+        rc = self.L.ref_prior_ppmx_core(i(iter), i(burn), i(thin), i(nobs), i(PPMx), i(ncon), i(ncat), d(alpha), d(sigma),
+                                        self._p(V), i(V.shape[0]), i(V.shape[1]), i(cohesion), i(CC), i(consim),
+                                        i(similarity), i(calibration), i(coardegree), self._p(xc), self._p(sp),
+                                        self._p(cc), self._p(card), i(ncluster_curr), self._p(nclu), self._p(njout))
+        if rc != 0:
+            raise RuntimeError(f"prior_ppmx_core failed: {self.err()}")
+        return {"nclu": nclu, "njout": njout}
 
     def dm_ppmx_ct(self, args: dict, tape, outputs: bool = True) -> dict:
         """The reference's dm_ppmx_ct(42 arguments) -> its 18-element list, with `tape` as R's RNG

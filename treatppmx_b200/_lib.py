@@ -20,7 +20,7 @@ SYMBOLS = [
     "tppmx_batch_last_timing", "tppmx_batch_predict",
     "tppmx_batch_accumulate", "tppmx_batch_summaries", "tppmx_batch_summaries_device",
     "tppmx_batch_reset_summaries", "tppmx_batch_update", "tppmx_batch_run", "tppmx_batch_get_acceptance",
-    "tppmx_dm_ppmx_ct", "tppmx_batch_npc", "tppmx_set_interrupt_flag",
+    "tppmx_dm_ppmx_ct", "tppmx_prior_ppmx_core", "tppmx_batch_npc", "tppmx_set_interrupt_flag",
 ]
 
 _lib = None
@@ -72,6 +72,7 @@ def load():
     L.tppmx_batch_run.argtypes = [vp, u64, i32, i32, i32, i32, i32, i32]
     L.tppmx_batch_get_acceptance.argtypes = [vp, i32, c_ip, c_ip]
     L.tppmx_dm_ppmx_ct.argtypes = [vp, vp, vp]
+    L.tppmx_prior_ppmx_core.argtypes = [vp, vp, vp]
     L.tppmx_batch_npc.argtypes = [vp, c_ip, c_ip, c_ip]
     L.tppmx_set_interrupt_flag.argtypes = [vp, c_ip, i32]
     _lib = L

@@ -1661,3 +1661,90 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
   tppmx_batch_destroy(B);
   return rc;
 }
+
+// ---- drop-in for prior_ppmx_core (reference src/prior_ppmx.cpp:9-466) --------------------------------
+// saved iteration ll of every chain: nclu(ll) = nclu_curr, njout.col(ll) = nj_curr (:455-459)
+__global__ void prior_save_kernel(DevBatch b, int ll, int nout, double *nclu_tr, double *nj_tr) {
+  const int chain = blockIdx.x;
+  const int K = b.nclu[(size_t)chain * b.T];
+  if (threadIdx.x == 0) nclu_tr[(size_t)chain * nout + ll] = (double)K;
+  const int *nj = b.nj + (size_t)chain * st_nj(b);
+  for (int j = threadIdx.x; j < b.nobs; j += blockDim.x)
+    nj_tr[((size_t)chain * nout + ll) * b.nobs + j] = (j < K && j < b.kcap) ? (double)nj[j] : 0.0;
+}
+
+extern "C" int tppmx_prior_ppmx_core(tppmx_ctx *ctx, const tppmx_prior_args *a, tppmx_prior_out *o) {
+  if (!ctx || ctx->closed) return TPPMX_ERR_ARG;
+  if (!a || !o) return fail(ctx, TPPMX_ERR_ARG, "null argument");
+  if (a->iter < 1 || a->burn < 0 || a->thin < 1 || a->burn > a->iter || a->nobs < 1 || a->n_chains < 1)
+    return fail(ctx, TPPMX_ERR_ARG, "iter/burn/thin/nobs/n_chains");
+  if (a->ncat != 0) return fail(ctx, TPPMX_ERR_ARG, "prior_ppmx_core has no categorical covariates (R/prior_ppmx.R:114)");
+  if (!a->similparam || !a->curr_cluster || (a->ncon > 0 && !a->xcon)) return fail(ctx, TPPMX_ERR_ARG, "null input array");
+  if (a->cohesion == 2 && !a->Vwm) return fail(ctx, TPPMX_ERR_ARG, "cohesion 2 needs Vwm");
+  const int nobs = a->nobs, P = a->ncon, nout = (a->iter - a->burn) / a->thin, nc = a->n_chains;
+
+  tppmx_model M;
+  memset(&M, 0, sizeof(M));
+  M.PPMx = a->PPMx; M.cohesion = a->cohesion; M.similarity = a->similarity; M.consim = a->consim;
+  M.calibration = a->calibration; M.coardegree = a->coardegree; M.reuse = 1; M.CC = a->CC;
+  M.nolik = 1; M.noprog = 1; M.alpha = a->alpha;
+  for (int k = 0; k < 7; k++) M.similparam[k] = a->similparam[k];
+  tppmx_dims dm;
+  memset(&dm, 0, sizeof(dm));
+  dm.nobs = nobs; dm.T = 1; dm.D = 1; dm.Q = 0; dm.P = P; dm.npred = 0; dm.G = 1; dm.ntmax = nobs; dm.kcap = 0;
+
+  // the two rows of V that are read (:239), on the log scale, in the compact layout of tppmx_shared.logV
+  std::vector<double> logV((size_t)2 * nobs, -INFINITY), grid = {a->sigma, 0.0};
+  if (a->cohesion == 2)
+    for (int r = 0; r < 2; r++) {
+      const int row = nobs - 2 + r;
+      if (row < 0 || row >= a->Vwm_rows) continue;
+      for (int K = 1; K <= nobs && K <= a->Vwm_cols; K++)
+        logV[(size_t)r * nobs + (K - 1)] = log(a->Vwm[row + (size_t)a->Vwm_rows * (K - 1)]);
+    }
+  std::vector<int32_t> treat(nobs, 0), lab(nobs), xcat(nobs, 0), catvec(1, 0);
+  std::vector<double> y(nobs, 1.0);
+  int K0 = 0;
+  for (int i = 0; i < nobs; i++) {
+    lab[i] = (int32_t)a->curr_cluster[i];
+    if (lab[i] > K0) K0 = lab[i];
+  }
+  if (a->ncluster_curr != K0) return fail(ctx, TPPMX_ERR_ARG, "ncluster_curr does not match curr_cluster");
+  tppmx_shared sh = {catvec.data(), grid.data(), a->cohesion == 2 ? logV.data() : nullptr};
+  tppmx_dataset ds = {treat.data(), y.data(), nullptr, a->xcon, xcat.data(), nullptr, nullptr, nullptr};
+
+  tppmx_batch *B = nullptr;
+  std::vector<int32_t> cds(nc, 0);
+  RC(tppmx_batch_create(ctx, &M, &dm, &sh, 1, &ds, nc, cds.data(), nullptr, &B));
+  int32_t ncl = K0;
+  int rc = tppmx_batch_init(B, a->seed, lab.data(), &ncl, nullptr);
+  double *d_nclu = nullptr, *d_nj = nullptr;
+  const size_t n1 = (size_t)nc * (nout > 0 ? nout : 1), n2 = n1 * nobs;
+  if (!rc && (cudaMalloc(&d_nclu, sizeof(double) * n1) != cudaSuccess || cudaMalloc(&d_nj, sizeof(double) * n2) != cudaSuccess))
+    rc = fail(ctx, TPPMX_ERR_NOMEM, "trace buffers");
+  int launches = 0, ll = 0;
+  for (int l = 0; l < a->iter && !rc; l++) {
+    if (ctx->interrupt && l > 0 && l % ctx->check_every == 0) {
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "prior_ppmx_core: kernel failure");
+      if (!rc && *ctx->interrupt) rc = fail(ctx, TPPMX_ERR_INTERRUPTED, "interrupted");
+      if (rc) break;
+    }
+    rc = sweep_launch(B, a->seed, l, 1, false, &launches);
+    if (!rc && (l > a->burn - 1) && ((l + 1) % a->thin == 0) && ll < nout) {  // :455
+      prior_save_kernel<<<nc, 128, 0, ctx->stream>>>(B->d, ll, nout, d_nclu, d_nj);
+      ll++;
+    }
+  }
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "prior_ppmx_core: kernel failure");
+  if (!rc) rc = check_status(B);
+  if (!rc && nout > 0) {
+    cudaError_t e = cudaSuccess;
+    if (o->nclu) e = cpy_sync(ctx->stream, o->nclu, d_nclu, sizeof(double) * n1, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && o->njout) e = cpy_sync(ctx->stream, o->njout, d_nj, sizeof(double) * n2, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, std::string("prior_ppmx_core: ") + cudaGetErrorString(e));
+  }
+  if (d_nclu) cudaFree(d_nclu);
+  if (d_nj) cudaFree(d_nj);
+  tppmx_batch_destroy(B);
+  return rc;
+}
