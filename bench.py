@@ -63,6 +63,42 @@ def build_workload(args, rank: int):
                 beta0=beta0, chain_ds=chain_ds, chain_id=chain_id, n_a=ex["n_a"])
 
 
+def host_cores() -> dict:
+    """What the CPU arm can actually use: the affinity mask of this process and the cgroup CPU quota
+    (cpu.max), not os.cpu_count() -- a 32-thread box with a 16-core quota gives 16 cores of work."""
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    usable = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return {"cpu_count": os.cpu_count() or 1, "affinity": aff, "cgroup_quota_cores": quota, "threads_used": usable}
+
+
+def profile_record(kind: str, key: str):
+    """ncu-derived constants of the dominant kernel (profiles/kernel_metrics.json), keyed by workload
+    shape: they describe a capture of THAT shape with the same command and are null for any other."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "kernel_metrics.json")))
+        return rec.get(kind, {}).get(key)
+    except Exception:
+        return None
+
+
+def shape_key(dims, nchains: int, sweeps: int) -> str:
+    return f"n{dims.nobs}_T{dims.T}_P{dims.P}_chains{nchains}_sweeps{sweeps}"
+
+
 def algorithmic_bytes_per_realloc(dims, CC: int, Kbar: float) -> float:
     """compulsory fp64 state traffic of one Gibbs step."""
     P, Q, D, ncat, C = dims.P, dims.Q, dims.D, dims.ncat, dims.maxC
@@ -230,7 +266,8 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     w = build_workload(args, 0)
-    ncores = os.cpu_count() or 1
+    hc = host_cores()
+    ncores = hc["threads_used"]
     # each step is a bounded sample: ~ (target) seconds of all-core work
     total_budget = 60.0 * args.cpu_scale
     per_step = max(1.0 * min(args.cpu_scale, 1.0), total_budget / max(args.steps + args.warmup, 1))
@@ -247,7 +284,7 @@ def run_reference(args, rank: int, world: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, w),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "host": hc,
                          "sample": desc + f", {len(rates)} timed steps; sweep phase only, which the reference does not expose on its "
                          "own (dm_ppmx_ct is its one entry point): the port of that phase is timed here, the reference's "
                          "own code in full_iteration.reference_*"},
@@ -314,6 +351,92 @@ def e2e_bytes(w, lab, ncl, pi):
     return int(h2d), int(d2h)
 
 
+def extra_config_legs(ctx, args) -> dict:
+    """Short legs on the other BASELINE configs (N = 1), so that they are measured by the driver's own
+    run and not only by the builder: config 1 (ppmxct() on the bundled simupats data, one chain, the
+    reference's own dm_ppmx_ct timed beside it), config 4 (n = 20 000, P = 50, NGG, 1024 chains) and
+    config 5's per-GPU shape (1024 chains, 10 000 new patients, predictive + co-clustering every
+    iteration).  Each is a parity-tested shape (tests/test_simupats.py, tests/test_gpu_large_n.py)."""
+    import argparse as _ap
+    from treatppmx_b200.engine import Batch
+    out = {}
+    # ---- config 1
+    try:
+        import refrun
+        from cases import build_case
+        from treatppmx_b200.ppmxct import dm_ppmx_ct
+        iters, burn, thin = 1100, 100, 1
+        case = build_case("simupats_ngg")
+        model, dims, shared, dsets, labels, nclu, betas = case
+        a1, logV = refrun.reference_args_of(model, dims, shared, dsets[0], labels, nclu, betas[0], iters, burn, thin, False)
+        dm_ppmx_ct(ctx, **dict(a1, iter=30, burn=10), seed=1, logV_compact=logV)   # warm
+        t0 = time.perf_counter()
+        o = dm_ppmx_ct(ctx, **a1, seed=3, logV_compact=logV)
+        dt = time.perf_counter() - t0
+        leg = {"workload": "ppmxct() on the bundled simupats data (genmech recipe; 124 patients, 2 arms, P=10, 28 new patients), "
+                           "ONE chain, iter 1100 / burn 100 / thin 1, default switches, NGG cohesion with the in-repo V table; "
+                           "through the drop-in tppmx_dm_ppmx_ct, host buffers in, all 18 outputs out",
+               "ms_per_iteration": 1e3 * dt / iters, "seconds": dt, "mean_clusters_per_arm": float(o["nclus"].mean()),
+               "reallocations_per_sec": dims.nobs * iters / dt}
+        if args.cpu_baseline and os.path.exists(refrun.REF_SO):
+            ad, _ = refrun.reference_args_of(model, dims, shared, dsets[0], labels, nclu, betas[0], iters, burn, thin, True)
+            t0 = time.perf_counter()
+            refrun.RefLib().dm_ppmx_ct(ad, 5)
+            dr = time.perf_counter() - t0
+            leg["reference_ms_per_iteration"] = 1e3 * dr / iters
+            leg["reference_kind"] = "reference (its own dm_ppmx_ct, oracle/_ref, one host thread; R's RNG replaced by a free-running generator)"
+        out["config1"] = leg
+    except Exception as e:   # a leg never takes the headline down with it
+        out["config1"] = {"error": repr(e)}
+    # ---- config 4 and config 5 shape
+    for name, kw, mode in (
+            ("config4", dict(datasets=1, chains_per_dataset=1024, n=20000, npred=0, P=50, Q=2, T=3, cohesion=2, kcap=128, mixture=8), "sweep"),
+            ("config5_shape_1gpu", dict(datasets=256, chains_per_dataset=4, n=152, npred=10000, P=10, Q=2, T=3, cohesion=2, kcap=0, mixture=0), "full")):
+        try:
+            a = _ap.Namespace(**kw)
+            t0 = time.perf_counter()
+            w = build_workload(a, 0)
+            b = Batch(ctx, w["model"], w["dims"], w["shared"], w["dsets"], chain_dataset=w["chain_ds"], chain_id=w["chain_id"])
+            b.init(7, w["labels"], w["nclu"], w["beta0"])
+            setup_s = time.perf_counter() - t0
+            nch, d = int(w["chain_ds"].size), w["dims"]
+            if mode == "sweep":
+                b.run(7, 0, 2)              # two full iterations: leaves the initial partition behind
+                b.sweep(7, 2, 1)
+                ms = []
+                for r in range(3):
+                    b.sweep(7, 3 + r, 1)
+                    ms.append(b.last_timing()[0])
+                impl, hand = b.last_sweep_info()
+                _, ncl = b.get_partitions()
+                med = float(np.median(ms))
+                Kb = float(ncl.mean())
+                B = algorithmic_bytes_per_realloc(d, w["model"].CC, Kb)
+                out[name] = {"workload": f"n={d.nobs} T={d.T} P={d.P} NGG, compact V table, kcap={d.kcap}, {nch} chains on one dataset; "
+                                         "3 timed launches of one sweep after 2 full iterations + 1 sweep",
+                             "reallocations_per_sec": nch * d.nobs / (med * 1e-3), "ms_per_sweep": med,
+                             "mean_clusters_per_arm": Kb, "max_clusters_per_arm": int(ncl.max()),
+                             "sweep_kernel": impl, "handovers_last_sweep": hand, "bytes_per_reallocation": B,
+                             "algorithmic_GBps": nch * d.nobs * B / (med * 1e-3) / 1e9, "setup_s": setup_s}
+            else:
+                b.run(7, 0, 20)
+                b.reset_summaries()
+                b.run(7, 20, 10, burn=0, thin=1, psm=True, predictive=True)
+                ms, nl = b.last_timing()
+                b.predict(7, 31, want=())
+                pms = b.last_timing()[0]
+                out[name] = {"workload": f"n={d.nobs} T={d.T} P={d.P} NGG, {nch} chains over {len(w['dsets'])} replicate datasets, "
+                                         f"{d.npred} new patients; 10 full iterations with the predictive step and the co-clustering "
+                                         "counts on every iteration, after 20 burn-in iterations",
+                             "gibbs_iterations_per_sec": nch * 10 / (ms * 1e-3), "ms_per_iteration_all_chains": ms / 10,
+                             "launches_per_iteration": nl / 10, "predictive_ms": pms,
+                             "new_patient_arm_scores_per_s": nch * d.npred * d.T / (pms * 1e-3), "setup_s": setup_s}
+            b.close()
+        except Exception as e:
+            out[name] = {"error": repr(e)}
+    return out
+
+
 def run_native(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
@@ -369,6 +492,20 @@ def run_native(args, rank: int, world: int, local_rank: int):
     t_wall = time.perf_counter() - t_wall0
 
     dev_ms = float(sum(ms_steps))
+    # sustained leg: ONE launch of the persistent sweep kernel sized to run for >= args.sustained_s
+    # seconds (the burst `value` above is steps x ~2.5 ms): what a minutes-long simulation study sees
+    sustained = None
+    if args.sustained_s > 0:
+        per_sweep_ms = dev_ms / (args.steps * args.sweeps)
+        nsus = max(args.sweeps, int(args.sustained_s * 1e3 / per_sweep_ms) + 1)
+        t0s = time.perf_counter()
+        batch.sweep(seed, it, nsus)
+        sus_ms, _ = batch.last_timing()
+        sus_wall = time.perf_counter() - t0s
+        it += nsus
+        sustained = {"value": nchains * dims.nobs * nsus / (sus_ms * 1e-3), "unit": UNIT, "seconds": sus_ms * 1e-3,
+                     "sweeps": nsus, "launches": 1, "wall_s": sus_wall,
+                     "what": "one launch of the sweep kernel, device-timed (CUDA events on the launching stream)"}
     lab, ncl = batch.get_partitions()
     Kbar = float(ncl.mean())
     Kmax = int(ncl.max())
@@ -471,14 +608,15 @@ def run_native(args, rank: int, world: int, local_rank: int):
     e2e_pipe_s = (time.perf_counter() - t0) / (ninfl * pipe_reps)
     for c in ctxs[1:]:
         c.close()
-    e2e_s = min(e2e_serial_s, e2e_pipe_s)
+    e2e_s = e2e_pipe_s   # the headline e2e is the pipelined mode, stated in e2e.mode; serial is reported beside it
 
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
 
     # reduce over ranks: max time, sum work
     full_ms = (nchains * 1e3 / full["gibbs_iterations_per_sec"]) if full else 0.0   # ms per iteration of all chains
-    t = torch.tensor([dev_ms, e2e_s, Kbar, full_ms, e2e_serial_s], dtype=torch.float64, device="cuda")
+    sus_s = sustained["seconds"] if sustained else 0.0
+    t = torch.tensor([dev_ms, e2e_s, Kbar, full_ms, e2e_serial_s, sus_s], dtype=torch.float64, device="cuda")
     by_rank = None
     if world > 1:
         allt = [torch.zeros_like(t) for _ in range(world)]
@@ -490,6 +628,9 @@ def run_native(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms_max, e2e_s_max, Kbar_all = float(tmax[0]), float(tmax[1]), float(tsum[2]) / world
         e2e_serial_max = float(tmax[4])
+        if sustained:
+            sustained["seconds"] = float(tmax[5])
+            sustained["value"] = world * nchains * dims.nobs * sustained["sweeps"] / float(tmax[5])
         if full:  # max over ranks, like every multi-GPU time
             full["ms_per_iteration_all_chains"] = float(tmax[3])
             full["gibbs_iterations_per_sec"] = nchains * 1e3 / float(tmax[3])
@@ -510,11 +651,15 @@ def run_native(args, rank: int, world: int, local_rank: int):
         B = algorithmic_bytes_per_realloc(dims, model.CC, Kbar_all)
         # per GPU: the dominant kernel is sweep_kernel, one launch per step
         achieved = (nchains * dims.nobs * args.sweeps * B) / (dev_ms_max / args.steps * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("sweep_kernel_bytes_per_launch")
-        except Exception:
-            pass
+        key = shape_key(dims, nchains, args.sweeps)
+        prof = profile_record("sweep", key)   # ncu capture of THIS shape (same command), or None
+        traffic = prof.get("dram_bytes_per_launch") if prof else None
+        issue = None
+        if prof:
+            issue = {"warp_instructions_per_reallocation": prof["warp_instructions_per_launch"] / (nchains * dims.nobs * args.sweeps),
+                     "issue_active_pct": prof.get("issue_active_pct"), "fp64_pipe_pct": prof.get("fp64_pipe_pct"),
+                     "warps_active_pct": prof.get("warps_active_pct"), "kernel": prof.get("kernel"),
+                     "source": prof.get("source")}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
@@ -529,13 +674,17 @@ def run_native(args, rank: int, world: int, local_rank: int):
             "summary_gather": gather,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": (prof.get("source") if prof else f"no ncu capture of shape {key} committed -> null"),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "bytes_per_reallocation": B,
                          "note": "cluster state is staged on chip; the sweep is bound by fp64 issue + sequential-step latency, not HBM (DESIGN.md)"},
+            "issue": issue,
+            "sustained": sustained,
             "e2e": {"value": world * nchains * dims.nobs * args.sweeps / e2e_s_max, "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s_max * 1e3,
                     "mode": f"{ninfl} batches in flight ({ninfl} host threads, one context each): copies and host staging of "
                             "one batch overlap the kernels of the other; every step copies its inputs in and results out",
+                    "value_is": "pipelined",
                     "serial_value": world * nchains * dims.nobs * args.sweeps / e2e_serial_max,
                     "serial_ms_per_step": e2e_serial_max * 1e3},
             "gpu_launches": launches,
@@ -545,11 +694,15 @@ def run_native(args, rank: int, world: int, local_rank: int):
             "clocks": clocks,
             "by_rank": by_rank,
         }
+        if args.extra_configs and world == 1:
+            batch.close()
+            out["extra"] = {"configs": extra_config_legs(ctx, args)}
         if args.cpu_baseline and world == 1:
-            ncores = os.cpu_count() or 1
+            hc = host_cores()
+            ncores = hc["threads_used"]
             r, desc, dt, _ = cpu_oracle_rate(w, ncores, 12.0)
             r1, desc1, dt1, _ = cpu_oracle_rate(w, 1, 4.0)
-            out["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": ncores, "kind": "port",
+            out["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": ncores, "kind": "port", "host": hc,
                                    "sample": desc + f" ({dt:.1f} s)", "single_core_value": r1}
             if full is not None:
                 fr, fdesc = cpu_oracle_full_rate(w, ncores, 6.0)
@@ -607,6 +760,9 @@ def main():
     ap.add_argument("--e2e-inflight", type=int, default=3, help="batches in flight of the e2e measurement (host threads)")
     ap.add_argument("--cpu-scale", type=float, default=1.0, help="scales the time budgets of the CPU legs (tests use a small value)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the sustained leg (one long launch); 0 = off")
+    ap.add_argument("--no-extra-configs", dest="extra_configs", action="store_false",
+                    help="skip the short BASELINE config-1 / config-4 / config-5-shape legs (N = 1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

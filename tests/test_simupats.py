@@ -44,8 +44,8 @@ def test_fixture_shapes_are_config1():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["simupats_ngg", "simupats_dp"])
 def test_config1_posterior_agrees_with_oracle_chains(name):
-    """North-star level 3 on the real data set: chains of the CUDA drop-in (seeds 1..4) against chains
-    of the CPU oracle (seeds 11..14), ppmxct()'s default length (iter 1100, burn 100): number of
+    """North-star level 3 on the real data set: chains of the CUDA drop-in (seeds 1..8) against chains
+    of the CPU oracle (seeds 11..18), ppmxct()'s default length (iter 1100, burn 100): number of
     clusters, predictive response probabilities of the 28 new patients and their chosen arm agree
     within Monte-Carlo error (two-sample z-scores over the independent chains)."""
     from treatppmx_b200.engine import Context
@@ -55,9 +55,9 @@ def test_config1_posterior_agrees_with_oracle_chains(name):
     model, dims, shared, dsets, labels, nclu, betas = case
     args, logV = refrun.reference_args_of(model, dims, shared, dsets[0], labels, nclu, betas[0], iters, burn, thin, False)
     ctx = Context(0)
-    dev = [dm_ppmx_ct(ctx, **args, seed=s, logV_compact=logV) for s in (1, 2, 3, 4)]
+    dev = [dm_ppmx_ct(ctx, **args, seed=s, logV_compact=logV) for s in range(1, 9)]
     ctx.close()
-    ora = [refrun.oracle_run(case, iters, burn, thin, s) for s in (11, 12, 13, 14)]
+    ora = [refrun.oracle_run(case, iters, burn, thin, s) for s in range(11, 19)]
 
     def stats(runs, f):
         v = np.array([f(r) for r in runs])
@@ -70,9 +70,14 @@ def test_config1_posterior_agrees_with_oracle_chains(name):
         md, sd = stats(dev, f)
         mo, so = stats(ora, f)
         z = (md - mo) / np.sqrt(sd ** 2 + so ** 2 + 1e-12)
-        assert np.abs(z).max() < 6.0 and np.sqrt((z ** 2).mean()) < 2.0, (what, np.abs(z).max())
-    ud = np.mean([np.einsum("pdt,d->pt", r["pipred"].mean(3), util_w) for r in dev], 0)
-    uo = np.mean([np.einsum("pdt,d->pt", r["pipred"].mean(3), util_w) for r in ora], 0)
-    clear = np.abs(uo[:, 0] - uo[:, 1]) > 6.0       # utility gap well above Monte-Carlo noise
+        assert np.abs(z).max() < 6.5 and np.sqrt((z ** 2).mean()) < 1.8, (what, np.abs(z).max())
+    # treatment choice: identical wherever the utility gap between the arms is clear of the Monte-Carlo
+    # noise of either set of chains (gap of each chain -> mean and standard error over the chains)
+    gap = lambda r: np.einsum("pdt,d->pt", r["pipred"].mean(3), util_w) @ np.array([1.0, -1.0])
+    gd, sd = stats(dev, gap)
+    go, so = stats(ora, gap)
+    clear = np.abs(go) > 5.0 * (sd + so)
     assert clear.sum() >= 5
-    assert (ud.argmax(1)[clear] == uo.argmax(1)[clear]).all()
+    assert (np.sign(gd[clear]) == np.sign(go[clear])).all()
+    z = (gd - go) / np.sqrt(sd ** 2 + so ** 2 + 1e-12)
+    assert np.abs(z).max() < 6.5
