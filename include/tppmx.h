@@ -352,6 +352,18 @@ typedef struct tppmx_ppmxct_out { /* names of the returned list, :1453-1471 */
 
 int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *in, tppmx_ppmxct_out *out);
 
+/* Point-estimate partition per replicate dataset and arm from the co-clustering matrix of the last
+ * tppmx_batch_summaries[_device] call: what users compute next with mcclust.ext::minVI /
+ * minbinder.ext (imported by the package, R/treatppmx.R:30-31; un-vendored, so the published
+ * algorithm is restated -- Wade & Ghahramani 2018, Bayesian Analysis 13(2) section 4, method "avg" / "comp"):
+ * hierarchical clustering of 1 - psm (linkage 0 = average, 1 = complete), every cut with
+ * k = 1..max_k clusters (max_k = 0 => ceiling(n_t / 8), the package's default) scored with the loss
+ * (0 = Binder sum_{i<j} |1{c_i = c_j} - psm_ij|, 1 = lower bound of the variation of information),
+ * the best cut returned.  labels_out [n_datasets][T x ntmax col-major] 1-based in order of first
+ * appearance (0 beyond the arm), k_out / loss_out [n_datasets][T] (may be NULL).  n_t <= 144. */
+int tppmx_batch_point_estimate(tppmx_batch *b, int32_t loss, int32_t linkage, int32_t max_k,
+                               int32_t *labels_out, int32_t *k_out, double *loss_out);
+
 /* ---- drop-in for the package's second sampler ------------------------------------------------
  * tppmx_prior_ppmx_core runs what prior_ppmx_core() runs (reference src/prior_ppmx.cpp:9-466;
  * .Call entry _treatppmx_prior_ppmx_core, src/RcppExports.cpp:189; R wrapper R/prior_ppmx.R:32-132):
@@ -410,6 +422,46 @@ int tppmx_batch_reset_summaries(tppmx_batch *b);
  * equal to the observed outcome.  trtsgn (assigned arm) and outcome (observed category) are
  * [n_datasets][npred], 0-based; npc_out is [n_datasets]. */
 int tppmx_batch_npc(tppmx_batch *b, const int32_t *trtsgn, const int32_t *outcome, int32_t *npc_out);
+
+/* ---- one process, several GPUs (tppmx_create(ctx**, device_ids[], ndev)) ----------
+ * The reference has no parallelism at all; its workload (a simulation study over replicate data
+ * sets, R/gendata.R:198-216) is embarrassingly parallel.  tppmx_multi_run_study shards the replicate
+ * datasets, each with all of its chains, over the devices in contiguous blocks (one host thread and
+ * one context per device, no data-path collective), runs n_iter full iterations per chain with the
+ * summaries accumulated on the saved iterations, and gathers the per-dataset posterior summaries with
+ * NCCL over NVLink (ncclCommInitAll; grouped ncclSend / ncclRecv into device 0) before one copy to
+ * the caller.  Chain c of dataset d uses Philox stream d * chains_per_dataset + c, so the results do
+ * not depend on the number of devices.  NCCL is loaded at run time and only when ndev > 1. */
+typedef struct tppmx_multi tppmx_multi;
+typedef struct tppmx_study {
+  const tppmx_model *model;
+  const tppmx_dims *dims;
+  const tppmx_shared *shared;
+  int32_t n_datasets;
+  const tppmx_dataset *datasets;   /* [n_datasets]                                              */
+  int32_t chains_per_dataset;
+  const int32_t *init_labels;      /* [n_datasets][T x ntmax col-major], as tppmx_batch_init      */
+  const int32_t *init_nclu;        /* [n_datasets][T]                                            */
+  const double *initbeta;          /* [Q*D]                                                      */
+  uint64_t seed;
+  int32_t n_iter, burn, thin;      /* saved iterations: (l > burn-1) && (l+1) % thin == 0         */
+  int32_t do_psm, do_pred;
+  const double *util_w;            /* [D] utility weights (NULL = zeros)                         */
+} tppmx_study;
+typedef struct tppmx_study_out {   /* host buffers (any may be NULL), layouts of tppmx_batch_summaries */
+  double *psm;                     /* [n_datasets][T][ntmax][ntmax]                              */
+  double *pi_mean;                 /* [n_datasets][npred x D x T col-major]                      */
+  double *utility;                 /* [n_datasets][T][npred]                                     */
+  int32_t *best_arm;               /* [n_datasets][npred]                                        */
+  double ms_run;                   /* device time of the chains, max over the devices            */
+  double ms_gather;                /* device time of the NCCL gather (0 on one device)           */
+  int32_t n_devices, used_nccl;
+} tppmx_study_out;
+int tppmx_multi_create(tppmx_multi **m, const int32_t *device_ids, int32_t ndev); /* device_ids NULL = 0..ndev-1 */
+int tppmx_multi_destroy(tppmx_multi *m);
+int tppmx_multi_device_count(const tppmx_multi *m);
+const char *tppmx_multi_last_error(const tppmx_multi *m);
+int tppmx_multi_run_study(tppmx_multi *m, const tppmx_study *in, tppmx_study_out *out);
 
 #ifdef __cplusplus
 }

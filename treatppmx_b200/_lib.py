@@ -21,6 +21,9 @@ SYMBOLS = [
     "tppmx_batch_accumulate", "tppmx_batch_summaries", "tppmx_batch_summaries_device",
     "tppmx_batch_reset_summaries", "tppmx_batch_update", "tppmx_batch_run", "tppmx_batch_get_acceptance",
     "tppmx_dm_ppmx_ct", "tppmx_prior_ppmx_core", "tppmx_batch_npc", "tppmx_set_interrupt_flag",
+    "tppmx_batch_point_estimate",
+    "tppmx_multi_create", "tppmx_multi_destroy", "tppmx_multi_device_count", "tppmx_multi_last_error",
+    "tppmx_multi_run_study",
 ]
 
 _lib = None
@@ -73,6 +76,13 @@ def load():
     L.tppmx_batch_get_acceptance.argtypes = [vp, i32, c_ip, c_ip]
     L.tppmx_dm_ppmx_ct.argtypes = [vp, vp, vp]
     L.tppmx_prior_ppmx_core.argtypes = [vp, vp, vp]
+    L.tppmx_batch_point_estimate.argtypes = [vp, i32, i32, i32, c_ip, c_ip, c_dp]
+    L.tppmx_multi_create.argtypes = [C.POINTER(vp), c_ip, i32]
+    L.tppmx_multi_destroy.argtypes = [vp]
+    L.tppmx_multi_device_count.argtypes = [vp]
+    L.tppmx_multi_last_error.argtypes = [vp]
+    L.tppmx_multi_last_error.restype = C.c_char_p
+    L.tppmx_multi_run_study.argtypes = [vp, vp, vp]
     L.tppmx_batch_npc.argtypes = [vp, c_ip, c_ip, c_ip]
     L.tppmx_set_interrupt_flag.argtypes = [vp, c_ip, i32]
     _lib = L

@@ -1511,6 +1511,42 @@ extern "C" int tppmx_batch_npc(tppmx_batch *b, const int32_t *trtsgn, const int3
   return TPPMX_OK;
 }
 
+extern "C" int tppmx_batch_point_estimate(tppmx_batch *b, int32_t loss, int32_t linkage, int32_t max_k, int32_t *labels_out,
+                                          int32_t *k_out, double *loss_out) {
+  if (!b || !labels_out) return TPPMX_ERR_ARG;
+  tppmx_ctx *ctx = b->ctx;
+  const DevBatch &d = b->d;
+  if (loss < 0 || loss > 1 || linkage < 0 || linkage > 1 || max_k < 0) return fail(ctx, TPPMX_ERR_ARG, "loss 0|1, linkage 0|1, max_k >= 0");
+  if (!b->psm_cnt) return fail(ctx, TPPMX_ERR_CAPACITY, "co-clustering counts were not reserved (ntmax too large)");
+  if (d.ntmax > TPPMX_PE_MAXN) return fail(ctx, TPPMX_ERR_CAPACITY, "point estimate: arms of more than TPPMX_PE_MAXN patients are not supported");
+  CK(ctx, cudaSetDevice(ctx->device));
+  const int nth = 256;
+  const size_t nu = (size_t)d.n_datasets * d.T, smem = point_estimate_smem(d.ntmax, nth);
+  int *dl = nullptr, *dk = nullptr;
+  double *dls = nullptr;
+  CK(ctx, cudaMalloc(&dl, sizeof(int) * nu * d.ntmax));
+  cudaError_t e = cudaMalloc(&dk, sizeof(int) * nu);
+  if (e == cudaSuccess) e = cudaMalloc(&dls, sizeof(double) * nu);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(point_estimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    point_estimate_kernel<<<dim3(d.n_datasets, d.T), nth, smem, ctx->stream>>>(d, b->psm_mean, loss, linkage, max_k, dl, dk, dls);
+    e = cudaGetLastError();
+  }
+  std::vector<int> hl(nu * d.ntmax);
+  if (e == cudaSuccess) e = cpy_sync(ctx->stream, hl.data(), dl, sizeof(int) * hl.size(), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && k_out) e = cpy_sync(ctx->stream, k_out, dk, sizeof(int) * nu, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && loss_out) e = cpy_sync(ctx->stream, loss_out, dls, sizeof(double) * nu, cudaMemcpyDeviceToHost);
+  cudaFree(dl);
+  if (dk) cudaFree(dk);
+  if (dls) cudaFree(dls);
+  if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("point_estimate: ") + cudaGetErrorString(e));
+  for (int ds = 0; ds < d.n_datasets; ds++)   // [ds][T x ntmax col-major], the layout of cl_lab / tppmx_state.labels
+    for (int t = 0; t < d.T; t++)
+      for (int it = 0; it < d.ntmax; it++)
+        labels_out[(size_t)ds * d.T * d.ntmax + t + (size_t)d.T * it] = hl[((size_t)ds * d.T + t) * d.ntmax + it];
+  return TPPMX_OK;
+}
+
 // ---- drop-in for dm_ppmx_ct (reference src/dm_ppmx_ct.cpp:10-1472), one chain -----------------------
 extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppmx_ppmxct_out *o) {
   if (!ctx || ctx->closed) return TPPMX_ERR_ARG;

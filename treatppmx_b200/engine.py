@@ -224,6 +224,19 @@ class Batch:
                                                   out.ctypes.data_as(c_ip)))
         return out
 
+    def point_estimate(self, loss: str = "VI", linkage: str = "average", max_k: int = 0):
+        """Point-estimate partition per (dataset, arm) from the co-clustering matrix of the last
+        summaries() call (minVI / minbinder.ext, method "avg" | "comp"): labels [nd, T, ntmax] 1-based
+        (0 beyond the arm), k [nd, T], loss [nd, T]."""
+        nd, d = len(self.datasets), self.dims
+        lab = np.zeros((nd, d.ntmax, d.T), dtype=np.int32)      # C-order == col-major T x ntmax per dataset
+        k = np.zeros((nd, d.T), dtype=np.int32)
+        ls = np.zeros((nd, d.T))
+        self.ctx.check(self.ctx.L.tppmx_batch_point_estimate(
+            self.h, {"binder": 0, "VI": 1}[loss], {"average": 0, "complete": 1}[linkage], max_k,
+            lab.ctypes.data_as(c_ip), k.ctypes.data_as(c_ip), ls.ctypes.data_as(c_dp)))
+        return lab.transpose(0, 2, 1), k, ls
+
     def summaries_device(self, util_w=None):
         """The same arrays left on the device as DeviceArray views (C-order shapes as in summaries(),
         pi_mean as [nd, T, D, npred])."""

@@ -31,7 +31,9 @@ def gather_summaries(local: dict, n_datasets_total: int, group=None, dst=None):
     local: name -> torch tensor whose leading dimension is the rank's number of datasets (CUDA
     tensors for nccl, CPU tensors for gloo; all ranks pass the same names / trailing shapes).
     Returns name -> tensor with leading dimension n_datasets_total, in dataset order.
-    Shards are padded to the largest shard so one all_gather_into_tensor per array suffices."""
+    Equal shards (the usual case: datasets divisible by ranks) are gathered STRAIGHT into the result
+    tensor -- no padding, no concatenation copy; unequal shards are padded to the largest one and
+    trimmed afterwards."""
     import torch
     import torch.distributed as dist
 
@@ -41,8 +43,14 @@ def gather_summaries(local: dict, n_datasets_total: int, group=None, dst=None):
         return {k: v.clone() for k, v in local.items()}
     sizes = [shard_range(n_datasets_total, world, r) for r in range(world)]
     nmax = max(hi - lo for lo, hi in sizes)
+    equal = all(hi - lo == nmax for lo, hi in sizes)
     for name in sorted(local):
         t = local[name].contiguous()
+        if equal:
+            res = torch.empty((n_datasets_total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(res, t, group=group)
+            out[name] = res
+            continue
         pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         pad[: t.shape[0]] = t
         buf = torch.empty((world * nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
@@ -58,3 +66,70 @@ def device_summaries_as_torch(batch, util_w=None):
 
     dev = torch.device("cuda", batch.ctx.device)
     return {k: torch.as_tensor(v, device=dev) for k, v in batch.summaries_device(util_w).items()}
+
+
+# ---- one process, several devices: the in-library entry (include/tppmx.h, tppmx_multi_*) -----------
+def run_study_multi(model, dims, shared, datasets, chains_per_dataset: int, init_labels, init_nclu, initbeta,
+                    seed: int, n_iter: int, burn: int = 0, thin: int = 1, util_w=None, device_ids=None,
+                    psm: bool = True, pred: bool = True) -> dict:
+    """tppmx_multi_run_study: replicate datasets (with all their chains) sharded over `device_ids`
+    (None = device 0 only) inside ONE process, summaries gathered with NCCL inside the library.
+    Returns psm [nd, T, ntmax, ntmax], pi_mean [nd, npred, D, T], utility [nd, T, npred], best_arm
+    [nd, npred] and the timing / device info of the call."""
+    import ctypes as C
+
+    from . import _lib
+    from ._abi import MAXD, Dataset, Dims, Model, Shared, c_dp, c_ip
+
+    class Study(C.Structure):
+        _fields_ = [("model", C.POINTER(Model)), ("dims", C.POINTER(Dims)), ("shared", C.POINTER(Shared)),
+                    ("n_datasets", C.c_int32), ("datasets", C.POINTER(Dataset)), ("chains_per_dataset", C.c_int32),
+                    ("init_labels", c_ip), ("init_nclu", c_ip), ("initbeta", c_dp), ("seed", C.c_uint64),
+                    ("n_iter", C.c_int32), ("burn", C.c_int32), ("thin", C.c_int32), ("do_psm", C.c_int32),
+                    ("do_pred", C.c_int32), ("util_w", c_dp)]
+
+    class StudyOut(C.Structure):
+        _fields_ = [("psm", c_dp), ("pi_mean", c_dp), ("utility", c_dp), ("best_arm", c_ip), ("ms_run", C.c_double),
+                    ("ms_gather", C.c_double), ("n_devices", C.c_int32), ("used_nccl", C.c_int32)]
+
+    L = _lib.load()
+    ids = np.ascontiguousarray([0] if device_ids is None else list(device_ids), dtype=np.int32)
+    h = C.c_void_p()
+    rc = L.tppmx_multi_create(C.byref(h), ids.ctypes.data_as(c_ip), len(ids))
+    if rc != 0:
+        raise _lib.TppmxError(rc, f"tppmx_multi_create failed for devices {ids.tolist()}")
+    try:
+        nd, T, nt, D, npred = len(datasets), dims.T, dims.ntmax, dims.D, dims.npred
+        il = np.asarray(init_labels, dtype=np.int32)
+        if il.ndim == 2:
+            il = np.broadcast_to(il, (nd, T, nt))
+        il = np.ascontiguousarray(np.stack([np.asfortranarray(a).ravel(order="F") for a in il]))
+        ic = np.asarray(init_nclu, dtype=np.int32)
+        ic = np.ascontiguousarray(np.broadcast_to(ic, (nd, T)) if ic.ndim == 1 else ic)
+        ib = np.ascontiguousarray(initbeta, dtype=np.float64)
+        uw = np.ascontiguousarray(np.concatenate([np.asarray(util_w if util_w is not None else [], float), np.zeros(MAXD)])[:MAXD])
+        arr = (Dataset * nd)(*[d.cstruct() for d in datasets])
+        sh = shared.cstruct()
+        st = Study()
+        st.model, st.dims, st.shared = C.pointer(model), C.pointer(dims), C.pointer(sh)
+        st.n_datasets, st.datasets, st.chains_per_dataset = nd, arr, chains_per_dataset
+        st.init_labels, st.init_nclu, st.initbeta = il.ctypes.data_as(c_ip), ic.ctypes.data_as(c_ip), ib.ctypes.data_as(c_dp)
+        st.seed, st.n_iter, st.burn, st.thin, st.do_psm, st.do_pred = seed, n_iter, burn, thin, int(psm), int(pred and npred > 0)
+        st.util_w = uw.ctypes.data_as(c_dp)
+        o = StudyOut()
+        res = {}
+        if psm:
+            res["psm"] = np.zeros((nd, T, nt, nt))
+            o.psm = res["psm"].ctypes.data_as(c_dp)
+        if pred and npred > 0:
+            pim, res["utility"], res["best_arm"] = np.zeros((nd, T, D, npred)), np.zeros((nd, T, npred)), np.zeros((nd, npred), np.int32)
+            o.pi_mean, o.utility, o.best_arm = pim.ctypes.data_as(c_dp), res["utility"].ctypes.data_as(c_dp), res["best_arm"].ctypes.data_as(c_ip)
+        rc = L.tppmx_multi_run_study(h, C.byref(st), C.byref(o))
+        if rc != 0:
+            raise _lib.TppmxError(rc, L.tppmx_multi_last_error(h).decode())
+        if pred and npred > 0:
+            res["pi_mean"] = pim.transpose(0, 3, 2, 1)
+        res["info"] = dict(ms_run=o.ms_run, ms_gather=o.ms_gather, n_devices=o.n_devices, used_nccl=bool(o.used_nccl))
+        return res
+    finally:
+        L.tppmx_multi_destroy(h)
