@@ -110,3 +110,26 @@ def test_empty_arm_is_rejected_cleanly(ctx):
     b = Batch(ctx, model, dims, shared, [ds], chain_dataset=[0])
     with pytest.raises(_lib.TppmxError):
         b.init(3, labels, nclu, beta0)
+
+
+def test_set_state_rejects_out_of_range_indices():
+    """labels index eta / sumx / nj with label - 1 and idxs indexes the V table on the device: a bad
+    state is refused on the host instead of reading out of bounds."""
+    from treatppmx_b200 import _lib
+    from treatppmx_b200.engine import Batch, Context
+    model, dims, shared, dsets, labels, nclu, betas = build_case("default_ngg")
+    ctx = Context(0)
+    b = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0])
+    b.init(1, labels, nclu, betas[0])
+    good = b.get_state(0)
+    for field, idx, val in (("labels", (0, 3), 99), ("labels", (1, 0), 0), ("idxs", (0,), dims.G), ("idxs", (0,), -1),
+                            ("nj", (0, 1), -2)):
+        st = good.copy()
+        getattr(st, field)[idx] = val
+        with pytest.raises(_lib.TppmxError) as ei:
+            b.set_state(0, st)
+        assert ei.value.code == 1, field
+    b.set_state(0, good)          # and the untouched state still goes through
+    b.sweep(1, 0, 2)
+    b.close()
+    ctx.close()

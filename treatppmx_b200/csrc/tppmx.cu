@@ -499,9 +499,13 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
       }
     }
     if (pass == 1) {
-      CK(ctx, cudaMemcpyAsync(b->ar.dbase, b->ar.hbase, b->up_used, cudaMemcpyHostToDevice, ctx->stream));
-      CK(ctx, cudaMemsetAsync(b->ar.dbase + b->up_need, 0, b->st_used, ctx->stream));
-      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaError_t ce = cudaMemcpyAsync(b->ar.dbase, b->ar.hbase, b->up_used, cudaMemcpyHostToDevice, ctx->stream);
+      if (ce == cudaSuccess) ce = cudaMemsetAsync(b->ar.dbase + b->up_need, 0, b->st_used, ctx->stream);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+      if (ce != cudaSuccess) {
+        rc = fail(ctx, TPPMX_ERR_CUDA, std::string("batch upload: ") + cudaGetErrorString(ce));
+        goto bad;
+      }
     }
   }
   *out = b;
@@ -723,6 +727,28 @@ extern "C" int tppmx_batch_set_state(tppmx_batch *b, int32_t chain, const tppmx_
   if (s->nclu)
     for (int t = 0; t < T; t++)
       if (s->nclu[t] < 0 || s->nclu[t] > ks) return fail(b->ctx, TPPMX_ERR_CAPACITY, "nclu exceeds kcap");
+  // the kernels index eta / sumx / nj with label-1 and logV / lgtab with idxs: validate before the upload
+  const int ds_of_chain = b->chain_ds[chain];
+  if (s->labels) {
+    std::vector<int> kcur(T, 0);
+    if (s->nclu) {
+      for (int t = 0; t < T; t++) kcur[t] = s->nclu[t];
+    } else {
+      CK(b->ctx, cpy_sync(b->ctx->stream, kcur.data(), d.nclu + (size_t)chain * T, sizeof(int) * T, cudaMemcpyDeviceToHost));
+    }
+    for (int t = 0; t < T; t++) {
+      const int na = b->arm_n[(size_t)ds_of_chain * T + t];
+      for (int it = 0; it < na; it++) {
+        const int v = s->labels[t + (size_t)T * it];
+        if (v < 1 || v > kcur[t]) return fail(b->ctx, TPPMX_ERR_ARG, "set_state: label outside 1..nclu[t]");
+      }
+    }
+  }
+  if (s->nj)
+    for (int t = 0; t < T; t++)
+      for (int j = 0; j < ks; j++)
+        if (s->nj[t + (size_t)T * j] < 0) return fail(b->ctx, TPPMX_ERR_ARG, "set_state: negative cluster size");
+  if (s->idxs && (s->idxs[0] < 0 || s->idxs[0] >= d.G)) return fail(b->ctx, TPPMX_ERR_ARG, "set_state: idxs outside 0..G-1");
   if (s->labels) {
     std::vector<int> h(st_labels(d));
     for (int t = 0; t < T; t++)
@@ -1207,6 +1233,18 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
   // beside the update kernel / the JJ-ss gamma draws; the next sweep waits for them.
   bool side_pending = false;
   int interrupted_at = -1;
+  // every error exit below leaves through this: nothing of the batch may still run on the side streams,
+  // and hs_pending must not survive (get_state / update of a later call would not join it)
+  struct SideGuard {
+    tppmx_ctx *c;
+    bool armed = true;
+    ~SideGuard() {
+      if (!armed) return;
+      cudaStreamSynchronize(c->side);
+      cudaStreamSynchronize(c->hs);
+      c->hs_pending = false;
+    }
+  } guard{ctx};
   for (int l = iter0; l < iter0 + n_iter; l++) {
     if (side_pending) {
       CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
@@ -1249,6 +1287,7 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
   }
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
+  guard.armed = false;   // the main stream has joined both side streams
   float ms = 0;
   CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   b->last_ms = ms;
@@ -1558,6 +1597,8 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
     return fail(ctx, TPPMX_ERR_ARG, "null input array");
   const int nobs = a->nobs, T = a->A, D = a->D, Q = a->Q, P = a->ncon, ncat = a->ncat, npred = a->npred, G = a->G;
   const int ntm = a->ntmax, nout = (a->iter - a->burn) / a->thin;
+  if (npred > 0 && ((Q > 0 && !a->zpred) || (P > 0 && !a->xconp) || (ncat > 0 && !a->xcatp)))
+    return fail(ctx, TPPMX_ERR_ARG, "npred > 0 but zpred / xconp / xcatp is null");
   if (T < 1 || T > TPPMX_MAXT || D < 1 || D > TPPMX_MAXD || ntm < 1 || G < 1) return fail(ctx, TPPMX_ERR_ARG, "dims out of range");
 
   tppmx_model M;
