@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import oracle_binding as ob
+from cases import build_case
 from treatppmx_b200 import _lib, datagen
 from treatppmx_b200._abi import HostDataset, default_model
 
