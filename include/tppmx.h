@@ -229,7 +229,8 @@ int tppmx_batch_sweep(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_sw
  *   prob_out [T][ntmax][stride] (row = position in the arm; entries 0..K+CC-1 are filled)
  *   K_out    [T][ntmax]         (-1: the step was not run by the fast kernel -- hand-over -- or
  *                                lies beyond the arm)
- * stride >= min(kcap, 32) + CC.  Fails when the model is not eligible for the fast kernel. */
+ * stride >= staged cluster capacity + CC (min(kcap, 32), or min(kcap, 256) for long arms; min(kcap, 256)
+ * + CC always suffices).  Fails when the model is not eligible for the fast kernel. */
 int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t chain,
                             int32_t stride, double *prob_out, int32_t *K_out);
 
@@ -246,8 +247,9 @@ int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t
 enum {
   TPPMX_OPT_SWEEP_IMPL = 1,
   TPPMX_OPT_LANES_PER_UNIT = 2,
-  TPPMX_OPT_FAST_STAGED_CLUSTERS = 3 /* clusters per arm the fast kernel stages on chip (1..32,
-                                        default min(kcap,32)); set before the first sweep */
+  TPPMX_OPT_FAST_STAGED_CLUSTERS = 3 /* clusters per arm the fast kernel stages on chip: 1..32, default
+                                        min(kcap,32); long arms (thousands of patients) 1..256, default
+                                        min(kcap,256); set before the first sweep */
 };
 enum { TPPMX_INFO_LAST_SWEEP_IMPL = 1, TPPMX_INFO_LAST_HANDOVERS = 2 };
 int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value);

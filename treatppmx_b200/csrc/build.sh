@@ -6,7 +6,7 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2 -I"${HERE}/../../include")
-UNITS=(tppmx sweep_fast_lpu8 sweep_fast_lpu16 sweep_fast_lpu32 multi)
+UNITS=(tppmx sweep_fast_lpu8 sweep_fast_lpu16 sweep_fast_lpu32 sweep_big multi)
 
 build_variant() {  # $1 = output .so, $2 = object dir, rest = extra flags
   local out="$1" odir="$2"; shift 2

@@ -755,10 +755,7 @@ static cudaError_t fast_launch5(const DevBatch &d, const FastArgs &fa, size_t sm
 template <int LPU, int XR, int DR, bool NOLIK>
 static cudaError_t fast_launch4(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  if (fa.big) {  // big-arm mode exists for one unit per warp only (sweep_launch picks LPU = 32 for it)
-    if constexpr (LPU == 32) return fast_launch5<LPU, XR, DR, NOLIK, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
-    return cudaErrorInvalidConfiguration;
-  }
+  if (fa.big) return cudaErrorInvalidConfiguration;  // long arms run sweep_big_kernel (sweep_big.cuh)
   return fast_launch5<LPU, XR, DR, NOLIK, false>(d, fa, smem, seed, iter0, n_sweeps, stream);
 }
 template <int LPU, int XR>

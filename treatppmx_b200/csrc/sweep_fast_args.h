@@ -52,4 +52,16 @@ cudaError_t fast_launch_lpu8(const DevBatch &d, const FastArgs &fa, size_t smem,
 cudaError_t fast_launch_lpu16(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0, int n_sweeps, cudaStream_t stream);
 cudaError_t fast_launch_lpu32(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0, int n_sweeps, cudaStream_t stream);
 
+// Long arms (fa.big): sweep_big_kernel (sweep_big.cuh), one CTA of nth = 128 | 256 threads per (chain, arm),
+// up to TPPMX_BIG_KSMAX staged clusters.
+#define TPPMX_BIG_KSMAX 256
+cudaError_t big_launch(const DevBatch &d, const FastArgs &fa, int nth, size_t smem, uint64_t seed, int iter0, int n_sweeps, cudaStream_t stream);
+__host__ __device__ inline int big_kstr(int KS) { return (KS + 1) | 1; }
+// bytes of dynamic shared memory of one CTA of the long-arm kernel
+__host__ __device__ inline size_t big_smem_bytes(int P, int KS, int CC, int D, int nth) {
+  const size_t dbl = (size_t)P * big_kstr(KS) + (size_t)(KS + CC) * D + 2 * fast_pp(P) + 2 * (nth / 32);
+  const size_t in = (size_t)KS + 2 * (KS + CC) + (nth / 32) + 8;
+  return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
+}
+
 }  // namespace tppmx

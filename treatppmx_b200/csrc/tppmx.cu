@@ -955,7 +955,7 @@ extern "C" int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value
     b->opt_lpu = value;
     return TPPMX_OK;
   }
-  if (opt == TPPMX_OPT_FAST_STAGED_CLUSTERS && value >= 0 && value <= TPPMX_FAST_KSMAX && !b->fast_ready) {
+  if (opt == TPPMX_OPT_FAST_STAGED_CLUSTERS && value >= 0 && value <= TPPMX_BIG_KSMAX && !b->fast_ready) {
     b->opt_ks = value;
     return TPPMX_OK;
   }
@@ -977,12 +977,25 @@ static bool fast_eligible(const tppmx_batch *b, int lpu) {
   return m.PPMx == 1 && m.consim == 1 && m.similarity == 1 && (m.calibration == 0 || m.calibration == 2) &&
          d.ncat == 0 && m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
 }
+// arms too long for the small-arm kernel's shared-memory label / order / cohesion tables (thousands of
+// patients, BASELINE config 4) run the long-arm kernel (sweep_big.cuh): one CTA per (chain, arm)
+static bool big_arms(const DevBatch &d) {
+  const size_t ks = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX, ntp = (d.ntmax + 3) & ~3;
+  return fast_tab_bytes(d.ntmax, 0) + 2 * fast_unit_bytes(d.P, (int)ks, (int)ntp, d.CC, d.D, 0) > 48 * 1024;
+}
+// staged cluster capacity of the long-arm kernel: min(kcap, 256), lowered until one CTA fits an SM
+static int big_ks(const DevBatch &d, int opt_ks) {
+  int ks = d.kcap < TPPMX_BIG_KSMAX ? d.kcap : TPPMX_BIG_KSMAX;
+  if (opt_ks > 0 && opt_ks < ks) ks = opt_ks;
+  while (ks > 8 && big_smem_bytes(d.P, ks, d.CC, d.D, ks <= 128 ? 128 : 256) > 200 * 1024) ks -= 8;
+  return ks;
+}
 
 // scratch of the fast sweep kernel, sized for the largest staged capacity (part of the arena)
 static int fast_reserve(tppmx_batch *b) {
   const DevBatch &d = b->d;
   FastArgs &fa = b->fa;
-  const size_t KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
+  const size_t KS = big_arms(d) ? (size_t)big_ks(d, 0) : (d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX);
   const size_t ntp = (d.ntmax + 3) & ~3, units = (size_t)d.n_chains * d.T;
   RC(dev_alloc(b, &fa.lik, units * (KS + d.CC) * ntp + ntp + 8));
   RC(dev_alloc(b, &fa.uq, units * 2 * (ntp + 1) + 8));
@@ -1012,18 +1025,22 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
   FastArgs &fa = b->fa;
   if (!fa.lik) return fail(b->ctx, TPPMX_ERR_ARG, "fast sweep scratch was not reserved for this batch");
   if (!b->fast_ready) {
-    fa.KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
-    if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
+    fa.big = big_arms(d) ? 1 : 0;
+    if (fa.big) {
+      fa.KS = big_ks(d, b->opt_ks);
+    } else {
+      fa.KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
+      if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
+    }
     fa.ntp = (d.ntmax + 3) & ~3;
     fa.ncol = fa.KS + d.CC;
     fa.n_units = d.n_chains * d.T;
-    // arms too long for shared-memory label / order / cohesion tables run in "big" mode
-    fa.big = (fast_tab_bytes(d.ntmax, 0) + 2 * fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D, 0) > 48 * 1024) ? 1 : 0;
-    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D, fa.big);
-    fa.tab_bytes = (int)fast_tab_bytes(d.ntmax, fa.big);
+    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D, 0);
+    fa.tab_bytes = (int)fast_tab_bytes(d.ntmax, 0);
     b->fast_ready = true;
   }
-  *smem_out = (size_t)fa.tab_bytes + (size_t)(32 / lpu) * fa.unit_bytes;
+  if (fa.big) *smem_out = big_smem_bytes(d.P, fa.KS, d.CC, d.D, fa.KS <= 128 ? 128 : 256);
+  else *smem_out = (size_t)fa.tab_bytes + (size_t)(32 / lpu) * fa.unit_bytes;
   return TPPMX_OK;
 }
 
@@ -1036,13 +1053,9 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   // lanes per (chain, arm): 16 (two units per warp) for the package's shapes, where an arm holds
   // ~4-10 clusters; long arms (config 4) hold tens of clusters -> one unit per warp
   int lpu = b->opt_lpu;
-  {
-    const DevBatch &dd = b->d;
-    const size_t ks = dd.kcap < TPPMX_FAST_KSMAX ? dd.kcap : TPPMX_FAST_KSMAX, ntp = (dd.ntmax + 3) & ~3;
-    const bool big = fast_tab_bytes(dd.ntmax, 0) + 2 * fast_unit_bytes(dd.P, (int)ks, (int)ntp, dd.CC, dd.D, 0) > 48 * 1024;
-    if (big) lpu = 32;  // the big-arm instantiations exist for one unit per warp only
-    else if (!lpu) lpu = 16;
-  }
+  const bool big = big_arms(b->d);
+  if (big) lpu = 32;  // long arms: one CTA per (chain, arm), P <= 128 covariate owners
+  else if (!lpu) lpu = 16;
   size_t smem = 0;
   bool use_fast = b->opt_impl != 1 && fast_eligible(b, lpu) && b->fa.lik;
   if (use_fast) {
@@ -1052,7 +1065,8 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   if (b->opt_impl == 2 && !use_fast) return fail(ctx, TPPMX_ERR_ARG, "model/shape not eligible for the fast sweep kernel");
   if (use_fast) {
     CK(ctx, cudaMemsetAsync(b->fa.bail_count, 0, sizeof(int), ctx->stream));
-    cudaError_t e = lpu == 8    ? fast_launch_lpu8(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
+    cudaError_t e = b->fa.big ? big_launch(b->d, b->fa, b->fa.KS <= 128 ? 128 : 256, smem, seed, iter0, n_sweeps, ctx->stream)
+                    : lpu == 8  ? fast_launch_lpu8(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
                     : lpu == 32 ? fast_launch_lpu32(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
                                 : fast_launch_lpu16(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("sweep_fast_kernel: ") + cudaGetErrorString(e));
@@ -1104,8 +1118,8 @@ extern "C" int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t it
   tppmx_ctx *ctx = b->ctx;
   const DevBatch &d = b->d;
   if (chain < 0 || chain >= d.n_chains) return fail(ctx, TPPMX_ERR_ARG, "chain out of range");
-  const int ksmax = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
-  if (stride < ksmax + d.CC) return fail(ctx, TPPMX_ERR_ARG, "stride must be >= min(kcap, 32) + CC");
+  const int ksmax = big_arms(d) ? big_ks(d, b->opt_ks) : (d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX);
+  if (stride < ksmax + d.CC) return fail(ctx, TPPMX_ERR_ARG, "stride must be >= the staged cluster capacity + CC");
   if (b->opt_impl == 1 || !b->fa.lik) return fail(ctx, TPPMX_ERR_ARG, "the probe exists for the fast sweep kernel only");
   CK(ctx, cudaSetDevice(ctx->device));
   const int T = d.T, ntp = (d.ntmax + 3) & ~3;

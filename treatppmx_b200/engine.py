@@ -146,7 +146,7 @@ class Batch:
         (prob [T, ntmax, W], K [T, ntmax]) of `chain` -- each step's normalised allocation
         probabilities and occupied-cluster count (-1 where the fast kernel did not run the step)."""
         d = self.dims
-        W = min(d.kcap if d.kcap > 0 else d.ntmax, 32) + self.model.CC
+        W = min(d.kcap if d.kcap > 0 else d.ntmax, 256) + self.model.CC   # >= the staged capacity of either kernel
         prob = np.zeros((d.T, d.ntmax, W))
         K = np.zeros((d.T, d.ntmax), dtype=np.int32)
         self.ctx.check(self.ctx.L.tppmx_batch_sweep_probe(self.h, seed, iter_, chain, W, prob.ctypes.data_as(c_dp),
