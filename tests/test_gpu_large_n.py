@@ -106,16 +106,22 @@ def test_config4_full_size_lockstep_with_oracle():
     ctx.close()
 
 
-def test_big_arms_more_than_32_clusters_lockstep():
+@pytest.mark.parametrize("staged", [0, 24])
+def test_big_arms_more_than_32_clusters_lockstep(staged):
     """Big-arm mode (n_t in the thousands) driven ABOVE 32 clusters per arm: a tighter within-cluster
     variance (similparam v = 0.3) takes K_t from 5 to ~70-80 within two sweeps (the K_t = 50-300
     regime SURVEY section 7.3 expects at config 4).  Whole iterations through tppmx_batch_run in lock-step
-    with the oracle: labels / counts / K bit-identical while K crosses 32 mid-sweep and stays above."""
+    with the oracle: labels / counts / K bit-identical while K crosses 32 mid-sweep and stays above.
+    staged = 0: the long-arm kernel picks its staged capacity per launch from the largest K seen so far
+    (the jump from 5 to ~70 clusters inside one sweep outgrows the first choice: hand-over, then a larger
+    capacity); staged = 24: a fixed small capacity, hand-over in every sweep."""
     from treatppmx_b200.engine import Batch, Context
     model, dims, shared, dsets, labels, nclu, beta0 = _case(
         n=4500, P=50, T=3, kcap=200, similparam=(0.0, 10.0, 0.3, 1.0, 2.0, 0.0, 0.1))
     ctx = Context(0)
     b = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0, 0])
+    if staged:   # a fixed small staged capacity: every unit outgrows it mid-sweep and is finished by the generic kernel
+        b.set_sweep_impl("fast", staged_clusters=staged)
     b.init(5, labels, nclu, beta0)
     pb = ob.Problem(model, dims, shared, dsets[0])
     sts = [pb.init_state(5, c, labels, nclu, beta0) for c in range(2)]

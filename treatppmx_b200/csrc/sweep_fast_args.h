@@ -33,6 +33,10 @@ struct FastArgs {
   double *probe;    // [probe_nunits][ntp][probe_stride], nullptr = production instantiation
   int *probe_k;     // [probe_nunits][ntp], -1 = step not visited by the fast kernel (hand-over)
   int probe_stride, probe_unit0, probe_nunits;
+  // long-arm kernel (sweep_big.cuh): the staged capacity KS is chosen per launch, the likelihood table
+  // keeps the stride of the largest one; kmax_dev receives the largest K any unit reached
+  size_t lik_unit_stride;  // doubles per unit of `lik`
+  int *kmax_dev;
 };
 
 __host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }
@@ -57,10 +61,12 @@ cudaError_t fast_launch_lpu32(const DevBatch &d, const FastArgs &fa, size_t smem
 #define TPPMX_BIG_KSMAX 256
 cudaError_t big_launch(const DevBatch &d, const FastArgs &fa, int nth, size_t smem, uint64_t seed, int iter0, int n_sweeps, cudaStream_t stream);
 __host__ __device__ inline int big_kstr(int KS) { return (KS + 1) | 1; }
-// bytes of dynamic shared memory of one CTA of the long-arm kernel
+// bytes of dynamic shared memory of one CTA of the long-arm kernel (layout: sweep_big.cuh)
 __host__ __device__ inline size_t big_smem_bytes(int P, int KS, int CC, int D, int nth) {
-  const size_t dbl = (size_t)P * big_kstr(KS) + (size_t)(KS + CC) * D + 2 * fast_pp(P) + 2 * (nth / 32);
-  const size_t in = (size_t)KS + 2 * (KS + CC) + (nth / 32) + 8;
+  (void)nth;
+  const size_t NC = (size_t)KS + CC, NO = 16;
+  const size_t dbl = (size_t)P * big_kstr(KS) + NC * D + 2 * fast_pp(P) + 2 * NC + NC + NC + (KS + 1) + 4 + NO + 4;
+  const size_t in = (size_t)KS + 2 * NC + 8 + 2 + 4 + 2;
   return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
 }
 

@@ -107,6 +107,9 @@ struct tppmx_batch {
   UpdArgs ua{};
   bool fast_ready = false;
   int last_impl = 0, last_handovers = 0;
+  // long-arm kernel: staged capacity per launch from the largest K seen (pinned read-back, no sync)
+  int big_ksmax = 0, big_nth = 0, kmax_hint = 0;
+  int *kmax_host = nullptr;  // pinned
 };
 
 #define CK(ctx, call)                                                                      \
@@ -241,6 +244,7 @@ static T *dev_stage(tppmx_batch *b, const T **p, size_t n, int *rc) {
   return h;
 }
 static bool fast_eligible(const tppmx_batch *b, int lpu);
+static bool big_arms(const DevBatch &d);
 static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc,
                           cudaStream_t st = nullptr);
 // one thread per new patient of an (chain, arm) block: no more threads than patients
@@ -482,6 +486,8 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
       TRY(dev_alloc(b, &b->pred_c, (size_t)n_chains * npred * T));
     }
     if (fast_eligible(b, 32)) TRY(fast_reserve(b));
+    if (pass == 1 && big_arms(d) && !b->kmax_host && cudaHostAlloc((void **)&b->kmax_host, sizeof(int), cudaHostAllocDefault) == cudaSuccess)
+      *b->kmax_host = 0;
     {  // posterior summaries; the co-clustering counts are skipped beyond 2 GiB (large-n config)
       const size_t npsm = (size_t)n_datasets * T * d.ntmax * d.ntmax;
       TRY(dev_alloc(b, &b->psm_n, (size_t)n_datasets));
@@ -535,6 +541,7 @@ extern "C" int tppmx_batch_destroy(tppmx_batch *b) {
   }
   cudaEventDestroy(b->ev0);
   cudaEventDestroy(b->ev1);
+  if (b->kmax_host) cudaFreeHost(b->kmax_host);
   tppmx_ctx *c = b->ctx;
   delete b;
   if (--c->live_batches == 0 && c->closed) ctx_release(c);
@@ -668,11 +675,14 @@ extern "C" int tppmx_batch_init(tppmx_batch *b, uint64_t seed, const int32_t *in
   CK(ctx, cudaSetDevice(ctx->device));
   const DevBatch &d = b->d;
   const int nd = d.n_datasets, T = d.T, nt = d.ntmax;
+  b->kmax_hint = 0;
+  if (b->kmax_host) *b->kmax_host = 0;
   std::vector<int> lab((size_t)nd * T * nt), ncl((size_t)nd * T);
   for (int ds = 0; ds < nd; ds++)
     for (int t = 0; t < T; t++) {
       const int K = init_nclu[(size_t)ds * T + t];
       if (K < 1 || K > d.kcap) return fail(ctx, TPPMX_ERR_ARG, "init_nclu out of range (1..kcap)");
+      if (K > b->kmax_hint) b->kmax_hint = K;
       ncl[(size_t)ds * T + t] = K;
       const int na = b->arm_n[(size_t)ds * T + t];
       for (int it = 0; it < nt; it++) {
@@ -983,11 +993,11 @@ static bool big_arms(const DevBatch &d) {
   const size_t ks = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX, ntp = (d.ntmax + 3) & ~3;
   return fast_tab_bytes(d.ntmax, 0) + 2 * fast_unit_bytes(d.P, (int)ks, (int)ntp, d.CC, d.D, 0) > 48 * 1024;
 }
-// staged cluster capacity of the long-arm kernel: min(kcap, 256), lowered until one CTA fits an SM
+// largest staged cluster capacity of the long-arm kernel: min(kcap, 256), lowered until one CTA fits an SM
 static int big_ks(const DevBatch &d, int opt_ks) {
   int ks = d.kcap < TPPMX_BIG_KSMAX ? d.kcap : TPPMX_BIG_KSMAX;
   if (opt_ks > 0 && opt_ks < ks) ks = opt_ks;
-  while (ks > 8 && big_smem_bytes(d.P, ks, d.CC, d.D, ks <= 128 ? 128 : 256) > 200 * 1024) ks -= 8;
+  while (ks > 8 && big_smem_bytes(d.P, ks, d.CC, d.D, 0) > 200 * 1024) ks -= 8;
   return ks;
 }
 
@@ -1002,6 +1012,8 @@ static int fast_reserve(tppmx_batch *b) {
   RC(dev_alloc(b, &fa.resume_l, units));
   RC(dev_alloc(b, &fa.resume_it, units));
   RC(dev_alloc(b, &fa.bail_count, 1));
+  RC(dev_alloc(b, &fa.kmax_dev, 1));
+  fa.lik_unit_stride = (KS + d.CC) * ntp;
   RC(dev_alloc(b, &fa.logng, units * (ntp + 1)));
   RC(dev_alloc(b, &fa.patpad, units * (ntp + 1)));
   {  // the three tables over n of sweep_fast.cuh, for arms too long to keep them in shared memory
@@ -1027,7 +1039,8 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
   if (!b->fast_ready) {
     fa.big = big_arms(d) ? 1 : 0;
     if (fa.big) {
-      fa.KS = big_ks(d, b->opt_ks);
+      b->big_ksmax = big_ks(d, 0);
+      fa.KS = b->big_ksmax;
     } else {
       fa.KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
       if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
@@ -1039,8 +1052,29 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     fa.tab_bytes = (int)fast_tab_bytes(d.ntmax, 0);
     b->fast_ready = true;
   }
-  if (fa.big) *smem_out = big_smem_bytes(d.P, fa.KS, d.CC, d.D, fa.KS <= 128 ? 128 : 256);
-  else *smem_out = (size_t)fa.tab_bytes + (size_t)(32 / lpu) * fa.unit_bytes;
+  if (fa.big) {
+    // staged capacity of THIS launch: room for 1.5 x the largest K any unit has reached so far (read back
+    // from the previous launch without a sync; the initial partition before that), so that the shared-
+    // memory footprint -- and with it the number of resident units -- follows the partition.  A unit that
+    // outgrows it hands over to the generic kernel, so the choice affects speed only.
+    int hint = b->kmax_hint;
+    if (b->kmax_host && *(volatile int *)b->kmax_host > 0) hint = *(volatile int *)b->kmax_host;
+    int ks = b->big_ksmax;
+    if (b->opt_ks > 0) ks = b->opt_ks < ks ? b->opt_ks : ks;
+    else if (hint > 0) {
+      int want = hint + hint / 2 + 16;
+      want = (want + 15) & ~15;
+      if (want < 32) want = 32;
+      if (want < ks) ks = want;
+    }
+    fa.KS = ks;
+    fa.ncol = ks + d.CC;
+    // threads per unit: one warp when the units outnumber what the SMs can hold anyway, else a wider CTA
+    b->big_nth = fa.n_units >= 8 * 148 ? 32 : (ks <= 128 ? 128 : 256);
+    *smem_out = big_smem_bytes(d.P, ks, d.CC, d.D, b->big_nth);
+  } else {
+    *smem_out = (size_t)fa.tab_bytes + (size_t)(32 / lpu) * fa.unit_bytes;
+  }
   return TPPMX_OK;
 }
 
@@ -1065,12 +1099,15 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   if (b->opt_impl == 2 && !use_fast) return fail(ctx, TPPMX_ERR_ARG, "model/shape not eligible for the fast sweep kernel");
   if (use_fast) {
     CK(ctx, cudaMemsetAsync(b->fa.bail_count, 0, sizeof(int), ctx->stream));
-    cudaError_t e = b->fa.big ? big_launch(b->d, b->fa, b->fa.KS <= 128 ? 128 : 256, smem, seed, iter0, n_sweeps, ctx->stream)
+    if (b->fa.big) CK(ctx, cudaMemsetAsync(b->fa.kmax_dev, 0, sizeof(int), ctx->stream));
+    cudaError_t e = b->fa.big ? big_launch(b->d, b->fa, b->big_nth, smem, seed, iter0, n_sweeps, ctx->stream)
                     : lpu == 8  ? fast_launch_lpu8(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
                     : lpu == 32 ? fast_launch_lpu32(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
                                 : fast_launch_lpu16(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("sweep_fast_kernel: ") + cudaGetErrorString(e));
     (*launches)++;
+    if (b->fa.big && b->kmax_host)
+      CK(ctx, cudaMemcpyAsync(b->kmax_host, b->fa.kmax_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     int nb = 1;
     if (sync_handover) {
       CK(ctx, cudaMemcpyAsync(&nb, b->fa.bail_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
