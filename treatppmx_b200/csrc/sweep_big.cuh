@@ -52,13 +52,13 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int unit = blockIdx.x;
   const int P = b.P, D = b.D, Q = b.Q, CC = b.CC, KS = fa.KS, ntp = fa.ntp, kcap = b.kcap;
-  const int kstr = big_kstr(KS), Pp = fast_pp(P), NC = KS + CC;
+  const int pstr = big_pstr(P), Pp = fast_pp(P), NC = KS + CC;
   const SimConst s = make_simconst(b);
 
   // ---- shared memory (big_smem_bytes)
-  double *T = reinterpret_cast<double *>(smem_raw);  // [P][kstr], column KS = the empty cluster (t = c0)
-  double *E = T + (size_t)P * kstr;                  // [NC][D] exp(eta) by likelihood column
-  double *XS = E + (size_t)NC * D;                   // [2][Pp] covariate row of the current / next patient
+  double *T = reinterpret_cast<double *>(smem_raw);  // [KS + 1][pstr] cluster-major rows, row KS = the empty cluster (t = c0)
+  double *E = T + (size_t)(KS + 1) * pstr;           // [NC][D] exp(eta) by likelihood column
+  double *XS = E + (((size_t)NC * D + 1) & ~(size_t)1);  // [2][Pp] covariate row of the current / next patient (16-byte aligned)
   double *s_lik = XS + 2 * Pp;                       // [2][NC] likelihood entries of the current / next patient
   double *s_w = s_lik + 2 * NC;                      // [NC] log-weights, then partial sums of e
   double *s_tY = s_w + NC;                           // [NC] t_Y of every candidate (the arrival value of a_j)
@@ -105,6 +105,7 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
 
   // ---- stage what lives on chip for the whole launch
   for (int j = tid; j < KS; j += NTH) s_nj[j] = g_nj[j];
+  for (int e = tid; e < 2 * Pp; e += NTH) XS[e] = 0.0;  // the pad entry of an odd P stays zero
   for (int it = tid; it <= ntp; it += NTH) patp[it] = (it < nt) ? g_pat[it] : 0;
   int nfree;
   {
@@ -126,14 +127,14 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
   auto colmap = [&](int j, int Kcur) -> int { return (j < Kcur) ? s_col[j] : s_col[KS + (j - Kcur)]; };
   // a_j = sum_p t_jp^2 from the staged matrix (two accumulators, fixed order)
   auto a_of = [&](int col) -> double {
+    const double *tc = T + (size_t)col * pstr;
     double a0 = 0.0, a1 = 0.0;
     int p = 0;
     for (; p + 1 < P; p += 2) {
-      const double t0 = T[p * kstr + col], t1 = T[(p + 1) * kstr + col];
-      a0 = fma(t0, t0, a0);
-      a1 = fma(t1, t1, a1);
+      a0 = fma(tc[p], tc[p], a0);
+      a1 = fma(tc[p + 1], tc[p + 1], a1);
     }
-    if (p < P) a0 = fma(T[p * kstr + col], T[p * kstr + col], a0);
+    if (p < P) a0 = fma(tc[p], tc[p], a0);
     return a0 + a1;
   };
 
@@ -171,9 +172,9 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
     for (int mm = tid; mm < CC; mm += NTH)  // :351-360 auxiliary eta ~ N(0, I)
       rng_normals(rng, l, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, D, g_etae + mm, CC);
     // t = sumx / v2 + m0 / s20 from the exact statistics (drift of the rank-one updates ends here)
-    for (int e = tid; e < P * kstr; e += NTH) {
-      const int p = e / kstr, j = e - p * kstr;
-      T[e] = fma((j < K) ? g_sumx[(size_t)p * kcap + j] : 0.0, iv2, c0);
+    for (int e = tid; e < (KS + 1) * pstr; e += NTH) {
+      const int j = e / pstr, p = e - j * pstr;
+      T[e] = (p < P) ? fma((j < K) ? g_sumx[(size_t)p * kcap + j] : 0.0, iv2, c0) : 0.0;   // padding: t = 0 against x = 0
     }
     __syncthreads();
     for (int j = tid; j <= KS; j += NTH) s_a[j] = (j < K || j == KS) ? a_of(j) : 0.0;
@@ -310,7 +311,7 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
               t = g_sumx2[e1];
               g_sumx2[e1] = g_sumx2[e2];
               g_sumx2[e2] = t;
-              T[p * kstr + iaux - 1] = fma(g_sumx[e1], iv2, c0);
+              T[(iaux - 1) * pstr + p] = fma(g_sumx[e1], iv2, c0);
             }
           }
         }
@@ -344,7 +345,7 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
           const int p = tid + r * NTH;
           vR1[r] = vR2[r] = vA1[r] = vA2[r] = 0.0;
           if (p < P) {
-            T[p * kstr + zi] = fma(-iv2, xv[r], T[p * kstr + zi]);
+            T[zi * pstr + p] = fma(-iv2, xv[r], T[zi * pstr + p]);
             if (pend_c >= 0) {
               const size_t eA = (size_t)p * kcap + pend_c;
               vA1[r] = g_sumx[eA];
@@ -370,14 +371,29 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
         const bool actj = j < ntot, occj = j < K;
         const int col = occj ? j : KS;
         double b0 = 0.0, b1 = 0.0;
-        {
-          const double *tc = T + col;
-          int p = 0;
-          for (; p + 1 < P; p += 2) {
-            b0 = fma(tc[p * kstr], xs[p], b0);
-            b1 = fma(tc[(p + 1) * kstr], xs[p + 1], b1);
+        {  // b_j = sum_p t_jp x_p: 128-bit loads (row stride 2 x odd doubles: conflict free, 16-byte aligned),
+           // eight covariates per trip with the loads issued ahead of the fused multiply-adds
+          const double2 *tc = reinterpret_cast<const double2 *>(T + (size_t)col * pstr);
+          const double2 *xc = reinterpret_cast<const double2 *>(xs);
+          const int np2 = Pp >> 1;  // pairs; the pad entry of xs / t is zero
+          int q = 0;
+          for (; q + 4 <= np2; q += 4) {
+            const double2 t0 = tc[q], t1 = tc[q + 1], t2 = tc[q + 2], t3 = tc[q + 3];
+            const double2 x0 = xc[q], x1 = xc[q + 1], x2 = xc[q + 2], x3 = xc[q + 3];
+            b0 = fma(t0.x, x0.x, b0);
+            b1 = fma(t0.y, x0.y, b1);
+            b0 = fma(t1.x, x1.x, b0);
+            b1 = fma(t1.y, x1.y, b1);
+            b0 = fma(t2.x, x2.x, b0);
+            b1 = fma(t2.y, x2.y, b1);
+            b0 = fma(t3.x, x3.x, b0);
+            b1 = fma(t3.y, x3.y, b1);
           }
-          if (p < P) b0 = fma(tc[p * kstr], xs[p], b0);
+          for (; q < np2; q++) {
+            const double2 t0 = tc[q], x0 = xc[q];
+            b0 = fma(t0.x, x0.x, b0);
+            b1 = fma(t0.y, x0.y, b1);
+          }
         }
         const double incr = iv2 * (2.0 * (b0 + b1) + iv2 * qx);
         int n = occj ? s_nj[j] : 0;
@@ -481,7 +497,7 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
         for (int r = 0; r < XR; r++) {
           const int p = tid + r * NTH;
           if (p < P) {
-            T[p * kstr + lab - 1] = fma(iv2, xv[r], T[p * kstr + lab - 1]);
+            T[(lab - 1) * pstr + p] = fma(iv2, xv[r], T[(lab - 1) * pstr + p]);
             if (!single) {  // retire the reads issued at the top of the step
               const size_t eR = (size_t)p * kcap + zi;
               if (pend_c >= 0) {
@@ -554,7 +570,7 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
             const double v1 = __dadd_rn(g_sumx[e], xv[r]);
             g_sumx[e] = v1;
             g_sumx2[e] = __dadd_rn(g_sumx2[e], __dmul_rn(xv[r], xv[r]));
-            T[p * kstr + lab - 1] = fma(v1, iv2, c0);
+            T[(lab - 1) * pstr + p] = fma(v1, iv2, c0);
           }
         }
         __syncthreads();

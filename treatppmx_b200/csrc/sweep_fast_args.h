@@ -60,12 +60,14 @@ cudaError_t fast_launch_lpu32(const DevBatch &d, const FastArgs &fa, size_t smem
 // up to TPPMX_BIG_KSMAX staged clusters.
 #define TPPMX_BIG_KSMAX 256
 cudaError_t big_launch(const DevBatch &d, const FastArgs &fa, int nth, size_t smem, uint64_t seed, int iter0, int n_sweeps, cudaStream_t stream);
-__host__ __device__ inline int big_kstr(int KS) { return (KS + 1) | 1; }
+// row stride (doubles) of the long-arm kernel's t matrix [cluster][covariate]: even (16-byte aligned rows for
+// 128-bit loads) with an odd half (rows of consecutive clusters start in different 16-byte bank groups)
+__host__ __device__ inline int big_pstr(int P) { const int h = (P + 1) >> 1; return 2 * (h | 1); }
 // bytes of dynamic shared memory of one CTA of the long-arm kernel (layout: sweep_big.cuh)
 __host__ __device__ inline size_t big_smem_bytes(int P, int KS, int CC, int D, int nth) {
   (void)nth;
   const size_t NC = (size_t)KS + CC, NO = 16;
-  const size_t dbl = (size_t)P * big_kstr(KS) + NC * D + 2 * fast_pp(P) + 2 * NC + NC + NC + (KS + 1) + 4 + NO + 4;
+  const size_t dbl = (size_t)(KS + 1) * big_pstr(P) + ((NC * D + 1) & ~(size_t)1) + 2 * fast_pp(P) + 2 * NC + NC + NC + (KS + 1) + 4 + NO + 4;
   const size_t in = (size_t)KS + 2 * NC + 8 + 2 + 4 + 2;
   return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
 }

@@ -1053,7 +1053,7 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     b->fast_ready = true;
   }
   if (fa.big) {
-    // staged capacity of THIS launch: room for 1.5 x the largest K any unit has reached so far (read back
+    // staged capacity of THIS launch: room for 1.25 x + 8 the largest K any unit has reached so far (read back
     // from the previous launch without a sync; the initial partition before that), so that the shared-
     // memory footprint -- and with it the number of resident units -- follows the partition.  A unit that
     // outgrows it hands over to the generic kernel, so the choice affects speed only.
@@ -1062,9 +1062,9 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     int ks = b->big_ksmax;
     if (b->opt_ks > 0) ks = b->opt_ks < ks ? b->opt_ks : ks;
     else if (hint > 0) {
-      int want = hint + hint / 2 + 16;
-      want = (want + 15) & ~15;
-      if (want < 32) want = 32;
+      int want = hint + hint / 4 + 8;
+      want = (want + 7) & ~7;
+      if (want < 16) want = 16;
       if (want < ks) ks = want;
     }
     fa.KS = ks;
