@@ -247,9 +247,11 @@ int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t
 enum {
   TPPMX_OPT_SWEEP_IMPL = 1,
   TPPMX_OPT_LANES_PER_UNIT = 2,
-  TPPMX_OPT_FAST_STAGED_CLUSTERS = 3 /* clusters per arm the fast kernel stages on chip: 1..32, default
+  TPPMX_OPT_FAST_STAGED_CLUSTERS = 3, /* clusters per arm the fast kernel stages on chip: 1..32, default
                                         min(kcap,32); long arms (thousands of patients) 1..256, default
                                         min(kcap,256); set before the first sweep */
+  TPPMX_OPT_BIG_THREADS = 4          /* long arms: threads per (chain, arm) of the long-arm kernel, 32 | 128 | 256;
+                                        0 = automatic (32 when the units outnumber what the SMs hold) */
 };
 enum { TPPMX_INFO_LAST_SWEEP_IMPL = 1, TPPMX_INFO_LAST_HANDOVERS = 2 };
 int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value);

@@ -23,6 +23,7 @@ ap.add_argument("--full-burn", type=int, default=30, help="full iterations befor
 ap.add_argument("--lpu", type=int, default=0)
 ap.add_argument("--impl", default="auto")
 ap.add_argument("--staged", type=int, default=0)
+ap.add_argument("--big-threads", type=int, default=0)
 ap.add_argument("--datasets", type=int, default=256)
 ap.add_argument("--chains-per-dataset", type=int, default=4)
 ap.add_argument("--n", type=int, default=152)
@@ -40,7 +41,7 @@ w = bench.build_workload(a, 0)
 w["model"].similparam[2] = a.v
 ctx = Context(0)
 b = Batch(ctx, w["model"], w["dims"], w["shared"], w["dsets"], chain_dataset=w["chain_ds"], chain_id=w["chain_id"])
-b.set_sweep_impl(a.impl, a.lpu, a.staged)
+b.set_sweep_impl(a.impl, a.lpu, a.staged, a.big_threads)
 b.init(1, w["labels"], w["nclu"], w["beta0"])
 it = 0
 if a.full_burn:

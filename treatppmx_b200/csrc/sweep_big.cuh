@@ -96,6 +96,15 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
   double *lognp = fa.logng + (size_t)unit * (ntp + 1);
   const double2 *tab2 = reinterpret_cast<const double2 *>(fa.tabg);
 
+  // second stage of a long-arm sweep: only the units the first stage (sweep_fast_kernel, <= 32 clusters) handed
+  // over, from their exact (sweep, patient) position; the other units are complete
+  int l_begin = iter0, it_begin = 0;
+  if (fa.resume_mode) {
+    const int rl = fa.resume_l[unit];
+    if (rl < 0) return;  // CTA-uniform
+    l_begin = rl;
+    it_begin = fa.resume_it[unit];
+  }
   int K = b.nclu[(size_t)chain * b.T + tt];
   int Kpeak = K;
   const double sigma = b.sigma[(size_t)chain * b.T + tt];
@@ -161,16 +170,18 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
     pend_c = -1;
   };
 
-  for (int l = iter0; l < iter0 + n_sweeps && live; l++) {
-    if (K > KS) {
+  for (int l = l_begin; l < iter0 + n_sweeps && live; l++) {
+    const int itb = (l == l_begin) ? it_begin : 0;  // a resumed sweep starts mid-arm
+    if (K > KS || (itb > 0 && K >= KS)) {
       bail_l = l;
-      bail_it = 0;
+      bail_it = itb;
       live = false;
       break;
     }
     // =========================== parallel pre-pass of the sweep ===========================
-    for (int mm = tid; mm < CC; mm += NTH)  // :351-360 auxiliary eta ~ N(0, I)
-      rng_normals(rng, l, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, D, g_etae + mm, CC);
+    if (!(fa.resume_mode && l == l_begin && itb > 0))  // a sweep resumed mid-arm keeps its (partly refreshed) auxiliary eta
+      for (int mm = tid; mm < CC; mm += NTH)           // :351-360 auxiliary eta ~ N(0, I)
+        rng_normals(rng, l, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, D, g_etae + mm, CC);
     // t = sumx / v2 + m0 / s20 from the exact statistics (drift of the rank-one updates ends here)
     for (int e = tid; e < (KS + 1) * pstr; e += NTH) {
       const int j = e / pstr, p = e - j * pstr;
@@ -227,19 +238,22 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
     // =========================== sequential reallocation steps ===========================
     double dV = dV_of(K);
     // operands of step 0 (synchronously), patient indices of steps 0..1
-    if (tid == 0) {
-      s_pat[0] = patp[0];
-      s_pat[1] = patp[1];
-      s_uq[0] = uq[0];
-      s_uq[1] = uq[uqs];
-      s_lab[0] = labp[0];
+    {
+      const int cb = itb & 1;
+      if (tid == 0) {
+        s_pat[itb & 3] = patp[itb];
+        s_pat[(itb + 1) & 3] = patp[itb + 1];
+        s_uq[2 * cb] = uq[itb];
+        s_uq[2 * cb + 1] = uq[uqs + itb];
+        s_lab[cb] = labp[itb];
+      }
+      for (int p = tid; p < P; p += NTH) XS[cb * Pp + p] = g_x[(size_t)patp[itb] * P + p];
+      for (int j = tid; j < K + CC; j += NTH) s_lik[cb * NC + j] = NOLIK ? 0.0 : lik[(size_t)colmap(j, K) * ntp + itb];
     }
-    for (int p = tid; p < P; p += NTH) XS[p] = g_x[(size_t)patp[0] * P + p];
-    for (int j = tid; j < K + CC; j += NTH) s_lik[j] = NOLIK ? 0.0 : lik[(size_t)colmap(j, K) * ntp];
     bool resync = false;  // the candidates' likelihood entries of the NEXT step must be re-read (structural change)
     __syncthreads();
 
-    for (int it = 0; it < nt; it++) {
+    for (int it = itb; it < nt; it++) {
       if (K >= KS) {  // a birth could overflow the staged capacity: hand the unit over (state is consistent)
         bail_l = l;
         bail_it = it;

@@ -711,6 +711,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       fa.resume_l[unit] = bail_l;
       fa.resume_it[unit] = bail_it;
       if (bail_l >= 0) atomicAdd(fa.bail_count, 1);
+      if (BIG && fa.kmax_dev) atomicMax(fa.kmax_dev, K);  // long arms: the next launch sizes its staging from it
     }
   }
   __syncwarp();
@@ -755,7 +756,11 @@ static cudaError_t fast_launch5(const DevBatch &d, const FastArgs &fa, size_t sm
 template <int LPU, int XR, int DR, bool NOLIK>
 static cudaError_t fast_launch4(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  if (fa.big) return cudaErrorInvalidConfiguration;  // long arms run sweep_big_kernel (sweep_big.cuh)
+  if (fa.big) {  // long arms, first stage (<= 32 clusters per arm): one unit per warp only; units that outgrow it
+                 // are finished by sweep_big_kernel (sweep_big.cuh) from the exact position
+    if constexpr (LPU == 32) return fast_launch5<LPU, XR, DR, NOLIK, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
+    return cudaErrorInvalidConfiguration;
+  }
   return fast_launch5<LPU, XR, DR, NOLIK, false>(d, fa, smem, seed, iter0, n_sweeps, stream);
 }
 template <int LPU, int XR>

@@ -37,6 +37,7 @@ struct FastArgs {
   // keeps the stride of the largest one; kmax_dev receives the largest K any unit reached
   size_t lik_unit_stride;  // doubles per unit of `lik`
   int *kmax_dev;
+  int resume_mode;         // 1: run only the units with resume_l >= 0, from (resume_l, resume_it) (second stage)
 };
 
 __host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }

@@ -108,7 +108,8 @@ struct tppmx_batch {
   bool fast_ready = false;
   int last_impl = 0, last_handovers = 0;
   // long-arm kernel: staged capacity per launch from the largest K seen (pinned read-back, no sync)
-  int big_ksmax = 0, big_nth = 0, kmax_hint = 0;
+  int big_ksmax = 0, big_nth = 0, kmax_hint = 0, opt_big_nth = 0, big_hint = 0;
+  bool big_two_stage = false;
   int *kmax_host = nullptr;  // pinned
 };
 
@@ -969,6 +970,10 @@ extern "C" int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value
     b->opt_ks = value;
     return TPPMX_OK;
   }
+  if (opt == TPPMX_OPT_BIG_THREADS && (value == 0 || value == 128 || value == 256)) {
+    b->opt_big_nth = value;
+    return TPPMX_OK;
+  }
   return fail(b->ctx, TPPMX_ERR_ARG, "unknown option or value");
 }
 
@@ -1053,24 +1058,29 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     b->fast_ready = true;
   }
   if (fa.big) {
-    // staged capacity of THIS launch: room for 1.25 x + 8 the largest K any unit has reached so far (read back
-    // from the previous launch without a sync; the initial partition before that), so that the shared-
-    // memory footprint -- and with it the number of resident units -- follows the partition.  A unit that
-    // outgrows it hands over to the generic kernel, so the choice affects speed only.
+    // staged capacity of THIS launch of the long-arm kernel: room for 1.25 x + 8 the largest K any unit has
+    // reached so far (read back from the previous launch without a sync; the initial partition before
+    // that), so that the shared-memory footprint -- and with it the number of resident units -- follows the
+    // partition.  A unit that outgrows it hands over to the generic kernel: the choice affects speed only.
     int hint = b->kmax_hint;
     if (b->kmax_host && *(volatile int *)b->kmax_host > 0) hint = *(volatile int *)b->kmax_host;
+    b->big_hint = hint;
+    // two stages while the partitions are small (K + 4 <= 32 everywhere): the one-warp-per-unit kernel
+    // (sweep_fast_kernel, big-arm mode, 8 units resident per SM) runs every unit, and only the units that reach
+    // 32 clusters are finished by the CTA-per-unit kernel; larger partitions go to the latter directly
+    b->big_two_stage = b->opt_ks == 0 && hint > 0 && hint + 4 <= TPPMX_FAST_KSMAX && d.P <= 128;
     int ks = b->big_ksmax;
     if (b->opt_ks > 0) ks = b->opt_ks < ks ? b->opt_ks : ks;
     else if (hint > 0) {
       int want = hint + hint / 4 + 8;
+      if (b->big_two_stage && want < 64) want = 64;  // second stage: units that have just outgrown 32 clusters
       want = (want + 7) & ~7;
       if (want < 16) want = 16;
       if (want < ks) ks = want;
     }
     fa.KS = ks;
     fa.ncol = ks + d.CC;
-    // threads per unit: one warp when the units outnumber what the SMs can hold anyway, else a wider CTA
-    b->big_nth = fa.n_units >= 8 * 148 ? 32 : (ks <= 128 ? 128 : 256);
+    b->big_nth = b->opt_big_nth ? b->opt_big_nth : (ks <= 128 ? 128 : 256);
     *smem_out = big_smem_bytes(d.P, ks, d.CC, d.D, b->big_nth);
   } else {
     *smem_out = (size_t)fa.tab_bytes + (size_t)(32 / lpu) * fa.unit_bytes;
@@ -1099,11 +1109,29 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   if (b->opt_impl == 2 && !use_fast) return fail(ctx, TPPMX_ERR_ARG, "model/shape not eligible for the fast sweep kernel");
   if (use_fast) {
     CK(ctx, cudaMemsetAsync(b->fa.bail_count, 0, sizeof(int), ctx->stream));
-    if (b->fa.big) CK(ctx, cudaMemsetAsync(b->fa.kmax_dev, 0, sizeof(int), ctx->stream));
-    cudaError_t e = b->fa.big ? big_launch(b->d, b->fa, b->big_nth, smem, seed, iter0, n_sweeps, ctx->stream)
-                    : lpu == 8  ? fast_launch_lpu8(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
-                    : lpu == 32 ? fast_launch_lpu32(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
-                                : fast_launch_lpu16(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream);
+    cudaError_t e;
+    if (b->fa.big) {
+      CK(ctx, cudaMemsetAsync(b->fa.kmax_dev, 0, sizeof(int), ctx->stream));
+      FastArgs f2 = b->fa;
+      f2.resume_mode = 0;
+      e = cudaSuccess;
+      if (b->big_two_stage) {  // first stage: every unit, up to 32 clusters, one warp per unit
+        FastArgs f1 = b->fa;
+        f1.KS = b->d.kcap < TPPMX_FAST_KSMAX ? b->d.kcap : TPPMX_FAST_KSMAX;
+        f1.ncol = f1.KS + b->d.CC;
+        f1.unit_bytes = (int)fast_unit_bytes(b->d.P, f1.KS, f1.ntp, b->d.CC, b->d.D, 1);
+        f1.tab_bytes = (int)fast_tab_bytes(b->d.ntmax, 1);
+        e = fast_launch_lpu32(b->d, f1, (size_t)f1.tab_bytes + f1.unit_bytes, seed, iter0, n_sweeps, ctx->stream);
+        (*launches)++;
+        CK(ctx, cudaMemsetAsync(b->fa.bail_count, 0, sizeof(int), ctx->stream));  // its hand-overs are resumed next
+        f2.resume_mode = 1;
+      }
+      if (e == cudaSuccess) e = big_launch(b->d, f2, b->big_nth, smem, seed, iter0, n_sweeps, ctx->stream);
+    } else {
+      e = lpu == 8    ? fast_launch_lpu8(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
+          : lpu == 32 ? fast_launch_lpu32(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream)
+                      : fast_launch_lpu16(b->d, b->fa, smem, seed, iter0, n_sweeps, ctx->stream);
+    }
     if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("sweep_fast_kernel: ") + cudaGetErrorString(e));
     (*launches)++;
     if (b->fa.big && b->kmax_host)

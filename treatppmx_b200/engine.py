@@ -156,11 +156,13 @@ class Batch:
     # kernel selection (include/tppmx.h: TPPMX_OPT_*, TPPMX_INFO_*)
     IMPL = {"auto": 0, "generic": 1, "fast": 2}
 
-    def set_sweep_impl(self, impl: str = "auto", lanes_per_unit: int = 0, staged_clusters: int = 0):
+    def set_sweep_impl(self, impl: str = "auto", lanes_per_unit: int = 0, staged_clusters: int = 0, big_threads: int = 0):
         self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 1, self.IMPL[impl]))
         self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 2, lanes_per_unit))
         if staged_clusters:
             self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 3, staged_clusters))
+        if big_threads:
+            self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 4, big_threads))
 
     def last_sweep_info(self):
         """(kernel used by the last sweep: 'generic'|'fast', units handed over to generic)"""
