@@ -1764,7 +1764,10 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
       if (rc) break;
     }
     rc = sweep_launch(B, a->seed, l, 1, false, &launches);
-    if (!rc) rc = update_launch(B, a->seed, l, &launches);
+    // the horseshoe update (a ~100 us serial chain that nothing reads before the NEXT iteration's beta step and
+    // no output saves) runs on the context's third stream beside the gamma draws, the in-sample fit and the
+    // predictive step: for ONE chain it was half of the iteration's latency
+    if (!rc) rc = update_launch(B, a->seed, l, &launches, nullptr, true);
     if (rc) break;
     sumtotclu_kernel<<<1, 32, 0, ctx->stream>>>(d, tr);
     if ((l > (a->burn - 1)) && ((l + 1) % a->thin == 0) && ll < nout) {  // :1060
@@ -1774,6 +1777,7 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
       ll++;
     }
   }
+  if (!rc) rc = hs_join(ctx);
   if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: kernel failure");
   if (!rc) {
     cudaError_t e = cudaGetLastError();
