@@ -49,7 +49,7 @@ __device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int nt
   U.sumx = d; d += (size_t)P * TPPMX_FAST_KSTR;
   U.sumx2 = d; d += (size_t)P * TPPMX_FAST_KSTR;
   U.logn = d; d += big ? 0 : ntp + 1;
-  U.xs = d; d += 2 * fast_pp(P);
+  U.xs = d; d += 4 * fast_pp(P);  // ring of four covariate rows (patients it-1 .. it+2)
   U.wsc = d; d += KS + CC;
   U.E = d; d += (size_t)(KS + CC) * D;
   int *q = reinterpret_cast<int *>(d);
@@ -82,12 +82,20 @@ constexpr unsigned TPPMX_FULL = 0xffffffffu;
 // cluster birth, > LPU candidates) are entered warp-uniformly through __any_sync.
 // maximum over the unit's lanes: one redux.sync on an order-preserving integer image of the
 // float instead of log2(LPU) shuffle + max levels (the step's dependent chain is what bounds it)
-__device__ __forceinline__ float unit_maxf(float v, unsigned unit_mask) {
+template <int LPU>
+__device__ __forceinline__ float unit_maxf(float v, int sub) {
   int i = __float_as_int(v);
   i ^= (i >> 31) & 0x7fffffff;
-  i = __reduce_max_sync(unit_mask, i);
-  i ^= (i >> 31) & 0x7fffffff;
-  return __int_as_float(i);
+  // one full-mask redux per unit of the warp (a redux over a partial mask is serialised per distinct
+  // mask behind a WARPSYNC.EXCLUSIVE loop; with the full mask the 32 / LPU reductions pipeline)
+  int r = i;
+#pragma unroll
+  for (int s = 0; s < 32 / LPU; s++) {
+    const int m = __reduce_max_sync(TPPMX_FULL, (sub == s) ? i : (int)0x80000000);
+    if (sub == s) r = m;
+  }
+  r ^= (r >> 31) & 0x7fffffff;
+  return __int_as_float(r);
 }
 template <int LPU>
 __device__ __forceinline__ double unit_sum(double v) {
@@ -221,7 +229,8 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
 #ifndef TPPMX_FAST_MINB
 #define TPPMX_FAST_MINB 12
 #endif
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
+// PC: compile-time number of covariates (0: run-time b.P)
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0>
 __global__ void __launch_bounds__(32, TPPMX_FAST_MINB)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -229,11 +238,10 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   extern __shared__ __align__(16) char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPU, ul = lane % LPU;
-  const unsigned unit_mask = (LPU == 32) ? TPPMX_FULL : (((1u << (LPU & 31)) - 1u) << (sub * LPU));
   const int unit_raw = blockIdx.x * UPW + sub;
   const bool valid = unit_raw < fa.n_units;
   const int unit = valid ? unit_raw : 0;  // lanes of a missing unit shadow unit 0 read-only
-  const int P = b.P, D = b.D, Q = b.Q, CC = b.CC, KS = fa.KS, ntp = fa.ntp, kcap = b.kcap;
+  const int P = PC > 0 ? PC : b.P, D = b.D, Q = b.Q, CC = b.CC, KS = fa.KS, ntp = fa.ntp, kcap = b.kcap;
   const int Pp = fast_pp(P);
   const SimConst s = make_simconst(b);
 
@@ -267,7 +275,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const double *g_x = b.x + (size_t)ds * b.nobs * P;
   double *lik = fa.lik + (size_t)unit * fa.ncol * ntp;
   const int uqs = ntp + 1;
-  double *uq = fa.uq + (size_t)unit * 2 * uqs;
+  double *uq = fa.uq + (size_t)unit * 3 * uqs;  // rows: uniform, sum_p x^2, x_{it-1} . x_it
   double *g_ez = b.zb + (size_t)chain * b.nobs * D;   // here: exp(beta'z) (scratch, rebuilt per sweep)
   double *g_ljj = b.ljj + (size_t)chain * b.nobs * D;
   const double *beta = b.beta + (size_t)chain * Q * D;
@@ -358,12 +366,17 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         for (int it = ul; it < nt; it += LPU) {
           const int i = patp[it];
           const double *xi = g_x + (size_t)i * P;
-          double qx = 0.0;
-          for (int p = 0; p < P; p++) qx = fma(xi[p], xi[p], qx);
+          const double *xm = g_x + (size_t)patp[it > 0 ? it - 1 : 0] * P;  // the patient one step earlier
+          double qx = 0.0, gx = 0.0;
+          for (int p = 0; p < P; p++) {
+            qx = fma(xi[p], xi[p], qx);
+            gx = fma(xi[p], xm[p], gx);
+          }
           double uu, u1;
           rng_u2(rng, l, TPPMX_SITE_ALLOC_U, tt, (uint32_t)i, 0, uu, u1);
           uq[it] = uu;
           uq[uqs + it] = qx;
+          uq[2 * uqs + it] = gx;
           if (!NOLIK) {
             const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
             const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
@@ -395,12 +408,17 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         for (int it = ul; it < nt; it += LPU) {
           const int i = patp[it];
           const double *xi = g_x + (size_t)i * P;
-          double qx = 0.0;
-          for (int p = 0; p < P; p++) qx = fma(xi[p], xi[p], qx);
+          const double *xm = g_x + (size_t)patp[it > 0 ? it - 1 : 0] * P;  // the patient one step earlier
+          double qx = 0.0, gx = 0.0;
+          for (int p = 0; p < P; p++) {
+            qx = fma(xi[p], xi[p], qx);
+            gx = fma(xi[p], xm[p], gx);
+          }
           double uu, u1;
           rng_u2(rng, l, TPPMX_SITE_ALLOC_U, tt, (uint32_t)i, 0, uu, u1);
           uq[it] = uu;
           uq[uqs + it] = qx;
+          uq[2 * uqs + it] = gx;
           if (!NOLIK) {
             const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
             const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
@@ -437,6 +455,16 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     }
 
     // =========================== sequential reallocation steps ===========================
+    // The step is software-pipelined so that only  draw -> score -> softmax -> draw  is a dependent chain:
+    //  * a_j = sum_p t_jp^2 and b_j = sum_p t_jp x_p of patient it+1 are formed during step it, from the
+    //    statistics as they stand after the removal of patient it (they do not depend on step it's draw);
+    //    the one cluster the draw then changes is corrected in closed form on its own lane,
+    //        b += iv2 (x_it . x_it+1),   a += iv2 (2 b_it + iv2 q_it)  [= t_Y of the draw's score],
+    //    and so is the next patient's own cluster (b -= iv2 q, a -= iv2 (2 b + iv2 q)); x_it . x_it+1 and
+    //    q = sum_p x^2 come from the pre-pass.  Every a, b is re-formed from the exact statistics at
+    //    every step, so nothing drifts;
+    //  * the exact statistics' read-modify-writes (arrival of patient it-1, removal of patient it) are
+    //    merged at the top of step it, off the chain; cluster sizes are carried in the lanes' registers.
     // more candidates than lanes in some unit of the warp?  Changes only with the number of
     // clusters, so the per-step vote is skipped while it cannot be true.
     bool anymulti = __any_sync(TPPMX_FULL, live && K + CC > LPU);
@@ -445,16 +473,64 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     bool act0 = ul < K + CC;
     const double *likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
     double likv = 0.0, uu = uq[0], qx = uq[uqs];
-    {  // operands of step 0
-      const int i0 = patp[0];
+    {  // covariate rows of patients 0 and 1 -> ring slots 0 and 1
+      const int i0 = patp[0], i1 = patp[1];
 #pragma unroll
       for (int r = 0; r < XR; r++) {
         const int p = ul + r * LPU;
-        if (p < P) U.xs[p] = g_x[(size_t)i0 * P + p];
+        if (p < P) {
+          U.xs[p] = g_x[(size_t)i0 * P + p];
+          U.xs[Pp + p] = g_x[(size_t)i1 * P + p];
+        }
       }
       if (!NOLIK) likv = likp[0];
     }
     __syncwarp();
+    // a, b of this lane's cluster (lanes >= K: the empty cluster, column 32) against the staged statistics
+    auto dots = [&](const double *xv, double &a, double &bb) {
+      const double *sx = U.sumx + ((ul < K) ? ul : TPPMX_FAST_KSMAX);
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      if constexpr (PC > 0) {  // compile-time P: straight-line code the scheduler can interleave with the draw's chain
+#pragma unroll
+        for (int p = 0; p + 1 < PC; p += 2) {
+          const double t0 = fma(sx[p * KSTR], iv2, c0), t1 = fma(sx[(p + 1) * KSTR], iv2, c0);
+          a0 = fma(t0, t0, a0);
+          a1 = fma(t1, t1, a1);
+          b0 = fma(t0, xv[p], b0);
+          b1 = fma(t1, xv[p + 1], b1);
+        }
+        if constexpr (PC & 1) {
+          const double t0 = fma(sx[(PC - 1) * KSTR], iv2, c0);
+          a0 = fma(t0, t0, a0);
+          b0 = fma(t0, xv[PC - 1], b0);
+        }
+      } else {
+        int p = 0;
+        for (; p + 1 < P; p += 2) {
+          const double t0 = fma(sx[p * KSTR], iv2, c0), t1 = fma(sx[(p + 1) * KSTR], iv2, c0);
+          a0 = fma(t0, t0, a0);
+          a1 = fma(t1, t1, a1);
+          b0 = fma(t0, xv[p], b0);
+          b1 = fma(t1, xv[p + 1], b1);
+        }
+        if (p < P) {
+          const double t0 = fma(sx[p * KSTR], iv2, c0);
+          a0 = fma(t0, t0, a0);
+          b0 = fma(t0, xv[p], b0);
+        }
+      }
+      a = a0 + a1;
+      bb = b0 + b1;
+    };
+    int myn = (ul < K) ? U.nj[ul] : 0;  // size of this lane's cluster (0: auxiliary / none)
+    int nzi = U.nj[labcur - 1];         // size of the current patient's cluster
+    int pend = 0;                       // label whose statistics still miss patient it-1 (0: none)
+    double a_c, b_c;
+    dots(U.xs, a_c, b_c);
+    if (ul == labcur - 1) {  // patient 0 leaves its own cluster
+      b_c = fma(-iv2, qx, b_c);
+      a_c = fma(-iv2, fma(iv2, qx, 2.0 * b_c), a_c);
+    }
 
     for (int it = 0; it < nt_w; it++) {
       bool on = live && it < nt;
@@ -464,30 +540,63 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         live = false;
         on = false;
       }
-      const double *xs = U.xs + (it & 1) * Pp;
-      // ---- prefetch the operands of step it+1 (addresses do not depend on this step; the
-      //      arrays are padded so the last step may read one entry past the arm)
+      const double *xs = U.xs + (it & 3) * Pp;          // x of patient it
+      const double *xs_n = U.xs + ((it + 1) & 3) * Pp;  // x of patient it+1 (staged during step it-1)
+      // ---- prefetch: covariate row of patient it+2, scalars of patient it+1 (addresses do not depend
+      //      on this step; the arrays are padded so the last steps may read past the arm)
       double xr_n[XR], lik_n = 0.0;
       {
-        const double *xrow = g_x + (size_t)patp[it + 1] * P;
+        const double *xrow = g_x + (size_t)patp[min(it + 2, ntp)] * P;
 #pragma unroll
         for (int r = 0; r < XR; r++) {
           const int p = ul + r * LPU;
           xr_n[r] = (p < P) ? xrow[p] : 0.0;
         }
       }
-      const double uu_n = uq[it + 1], qx_n = uq[uqs + it + 1];
-      const int lab_n = labp[it + 1];  // label of the next patient (re-read after a relabelling)
+      const double uu_n = uq[it + 1], qx_n = uq[uqs + it + 1], g_n = uq[2 * uqs + it + 1];
+      int lab_n = labp[it + 1];  // label of the next patient (re-read after a relabelling)
       if (!NOLIK) lik_n = likp[it + 1];
       bool structural = false;
 
-      // ---- :368-457 take the patient out of its cluster
+      // ---- :368-457 take the patient out of its cluster; :820-856 of the previous step (deferred).
+      //      Branch-free: a missing arrival / removal adds 0.0 to the column of the other one, and lanes
+      //      beyond P repeat the last covariate's (identical) read-modify-write.
       const int zi = on ? labcur - 1 : 0;
       TPPMX_ASSERT(zi >= 0 && zi < KS && (!on || zi < K), 1);
-      const int nzi = U.nj[zi];
       TPPMX_ASSERT(!on || nzi >= 1, 2);
       TPPMX_ASSERT(it + 1 <= ntp, 3);
       const bool single = on && nzi <= 1;
+      {
+        const bool add = pend != 0;        // cluster pend-1 receives patient it-1
+        const bool rem = on && !single;    // cluster zi loses patient it
+        const int ca = add ? pend - 1 : zi;
+        const double *xm = U.xs + ((it + 3) & 3) * Pp;
+#pragma unroll
+        for (int r = 0; r < XR; r++) {
+          if (r * LPU >= P) break;  // warp-uniform
+          int p = ul + r * LPU;
+          p = p < P ? p : P - 1;
+          double *pa1 = U.sumx + p * KSTR + ca, *pa2 = U.sumx2 + p * KSTR + ca;
+          double *pr1 = U.sumx + p * KSTR + zi, *pr2 = U.sumx2 + p * KSTR + zi;
+          const double sa1 = *pa1, sa2 = *pa2, sr1 = *pr1, sr2 = *pr2;  // all loads before the stores
+          const double xa = add ? xm[p] : 0.0, xr = rem ? xs[p] : 0.0;
+          const double na1 = __dadd_rn(sa1, xa), na2 = __dadd_rn(sa2, __dmul_rn(xa, xa));
+          const bool same = ca == zi;  // remove from what the arrival left
+          const double nr1 = __dsub_rn(same ? na1 : sr1, xr), nr2 = __dsub_rn(same ? na2 : sr2, __dmul_rn(xr, xr));
+          *pa1 = na1;
+          *pa2 = na2;
+          *pr1 = nr1;
+          *pr2 = nr2;
+        }
+        if (ul == 0) {
+          const int na = U.nj[ca] + (add ? 1 : 0);
+          U.nj[ca] = na;
+          const int nr = ((ca == zi) ? na : U.nj[zi]) - (rem ? 1 : 0);
+          U.nj[zi] = nr;
+        }
+        myn -= (rem && ul == zi) ? 1 : 0;
+      }
+      pend = 0;
       __syncwarp();
       if (__any_sync(TPPMX_FULL, single)) {  // singleton (:384-457), rare
         const int iaux = zi + 1, Kc = K;
@@ -536,59 +645,57 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           structural = true;
         }
         anymulti = __any_sync(TPPMX_FULL, live && K + CC > LPU);
-      }
-      if (on && !single) {
-        if (ul == 0) U.nj[zi] = nzi - 1;
-#pragma unroll
-        for (int r = 0; r < XR; r++) {
-          const int p = ul + r * LPU;
-          if (p < P) {  // both loads before either store: the two arrays may alias for all the
-                        // compiler knows, and a load queued behind a store doubles the latency
-            const double xv = xs[p], s1 = U.sumx[p * KSTR + zi], s2 = U.sumx2[p * KSTR + zi];
-            U.sumx[p * KSTR + zi] = __dsub_rn(s1, xv);
-            U.sumx2[p * KSTR + zi] = __dsub_rn(s2, __dmul_rn(xv, xv));
+        __syncwarp();
+        // the lanes of a unit whose partition changed re-form their a, b, n from the statistics
+        lab_n = labp[it + 1];
+        double ar, br;
+        dots(xs, ar, br);
+        if (single) {
+          a_c = ar;
+          b_c = br;
+          myn = (ul < K) ? U.nj[ul] : 0;
+          act0 = ul < K + CC;
+          likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
+          TPPMX_ASSERT(!act0 || (colmap(ul, K) >= 0 && colmap(ul, K) < fa.ncol), 6);
+          TPPMX_ASSERT(nfree >= 0 && nfree <= fa.ncol, 7);
+          if (!NOLIK) {
+            likv = likp[it];
+            lik_n = likp[it + 1];
           }
         }
-      }
-      __syncwarp();
-      if (structural) {
-        act0 = ul < K + CC;
-        likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
-        TPPMX_ASSERT(!act0 || (colmap(ul, K) >= 0 && colmap(ul, K) < fa.ncol), 6);
-        TPPMX_ASSERT(nfree >= 0 && nfree <= fa.ncol, 7);
-        if (!NOLIK) likv = likp[it];
       }
 
       // ---- :460-814 score the K occupied + CC auxiliary clusters, normalise, draw
       const int ntot = K + CC;
       int newci;
+      const double t1 = fma(iv2, qx, 2.0 * b_c);
+      double w, wmax;
       {
-        const bool occ = ul < K;
-        const int n = occ ? U.nj[ul] : 0;
-        const double *sx = U.sumx + (occ ? ul : TPPMX_FAST_KSMAX);  // column 32: the empty cluster
-        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-        int p = 0;
-        for (; p + 1 < P; p += 2) {
-          const double t0 = fma(sx[p * KSTR], iv2, c0), t1 = fma(sx[(p + 1) * KSTR], iv2, c0);
-          a0 = fma(t0, t0, a0);
-          a1 = fma(t1, t1, a1);
-          b0 = fma(t0, xs[p], b0);
-          b1 = fma(t1, xs[p + 1], b1);
-        }
-        if (p < P) {
-          const double t0 = fma(sx[p * KSTR], iv2, c0);
-          a0 = fma(t0, t0, a0);
-          b0 = fma(t0, xs[p], b0);
-        }
-        const double a = a0 + a1, bb = b0 + b1;
-        const double tY = a + iv2 * (2.0 * bb + iv2 * qx);
+        const int n = myn;
+        const double tY = fma(iv2, t1, a_c);
         const double2 t01 = tab2[2 * n], t23 = tab2[2 * n + 1];  // (dA, HN), (HY, -)
-        const double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a);
-        const double w = act0 ? dV + lognp[n] + simscale * d + likv : -INFINITY;
+        const double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a_c);
+        const double wv = dV + lognp[n] + simscale * d + likv;
+        w = act0 ? wv : -INFINITY;
         // the shift only has to be common to the unit's lanes and close to the maximum: the
         // float-rounded maximum costs a quarter of the shuffles of an fp64 max
-        const double wmax = (double)unit_maxf((float)w, unit_mask);
-        const double e0 = act0 ? fast_exp(w - wmax) : 0.0;
+        wmax = (double)unit_maxf<LPU>((float)w, sub);
+      }
+      // ---- a, b of patient it+1 against the statistics without patient it: independent of this step's
+      //      draw; placed here so that the scheduler interleaves it with the exp / scan chain below.
+      //      The next patient's own cluster is corrected for its removal.
+      const int zn = (it + 1 < nt) ? lab_n - 1 : 0;
+      double a_n, b_n;
+      dots(xs_n, a_n, b_n);
+      {
+        const double bs = fma(-iv2, qx_n, b_n);
+        const double as = fma(-iv2, fma(iv2, qx_n, 2.0 * bs), a_n);
+        b_n = (ul == zn) ? bs : b_n;
+        a_n = (ul == zn) ? as : a_n;
+      }
+      const int nj_n = U.nj[zn];  // size of the next patient's cluster before this step's arrival
+      {
+        const double e0 = fast_exp(w - wmax);  // 0 for w = -inf
         const double cum = unit_incl_scan<LPU>(e0, ul);
         const double den = __shfl_sync(TPPMX_FULL, cum, LPU - 1, LPU);
         // uu < cumsum(e)/den  <=>  uu*den < cumsum(e)   (:805-814)
@@ -615,15 +722,12 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         if (multi) newci = r;
       }
 
-      // ---- :820-856 assign, update sufficient statistics
+      // ---- :820-856 assign; the statistics receive the patient at the top of the next step
       TPPMX_ASSERT(!on || (newci >= 1 && newci <= K + CC), 4);
       const bool born = on && newci > K;
       TPPMX_ASSERT(!born || (nfree >= 1 && K + 1 <= KS), 5);
       int lab = newci;
-      if (on && !born && ul == 0) {
-        labp[it] = lab;
-        U.nj[lab - 1] += 1;
-      }
+      if (on && !born && ul == 0) labp[it] = lab;
       if (__any_sync(TPPMX_FULL, born)) {  // a new cluster takes the auxiliary eta (:829-845), rare
         int m = 0, newcol = 0, i = 0;
         if (born) {
@@ -637,7 +741,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         if (born) {
           if (ul == 0) {
             labp[it] = lab;
-            U.nj[lab - 1] = 1;
+            U.nj[lab - 1] = 0;  // the arrival is counted with the statistics, at the top of the next step
             U.col[lab - 1] = U.col[KS + m];
             U.col[KS + m] = newcol;
           }
@@ -662,34 +766,54 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
         anymulti = __any_sync(TPPMX_FULL, live && K + CC > LPU);
       }
-      if (on) {
-#pragma unroll
-        for (int r = 0; r < XR; r++) {
-          const int p = ul + r * LPU;
-          if (p < P) {
-            const double xv = xs[p], s1 = U.sumx[p * KSTR + lab - 1], s2 = U.sumx2[p * KSTR + lab - 1];
-            U.sumx[p * KSTR + lab - 1] = __dadd_rn(s1, xv);
-            U.sumx2[p * KSTR + lab - 1] = __dadd_rn(s2, __dmul_rn(xv, xv));
-          }
-        }
+      // ---- the lane of the cluster that receives patient it: its size, and a, b of patient it+1
+      //      (a lane >= the old K held the empty cluster's values: a birth needs nothing else)
+      {
+        const bool mine = on && ul == lab - 1;
+        const double bq = fma(iv2, g_n, b_n);
+        const double aq = fma(iv2, t1 - ((ul == zn) ? 2.0 * iv2 * g_n : 0.0), a_n);
+        myn += mine ? 1 : 0;
+        b_n = mine ? bq : b_n;
+        a_n = mine ? aq : a_n;
       }
-      // ---- stage the operands of the next step
+      pend = on ? lab : 0;
+      nzi = nj_n + ((on && lab - 1 == zn) ? 1 : 0);
+      // ---- stage the covariate row of patient it+2, rotate the operands
 #pragma unroll
       for (int r = 0; r < XR; r++) {
         const int p = ul + r * LPU;
-        if (p < P) U.xs[((it + 1) & 1) * Pp + p] = xr_n[r];
+        if (p < P) U.xs[((it + 2) & 3) * Pp + p] = xr_n[r];
       }
       uu = uu_n;
       qx = qx_n;
       likv = lik_n;
-      __syncwarp();
       labcur = lab_n;
+      a_c = a_n;
+      b_c = b_n;
+      __syncwarp();
       if (structural) {
         act0 = ul < K + CC;
         likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
         if (!NOLIK) likv = likp[it + 1];
-        labcur = labp[it + 1];
       }
+    }
+    // ---- the statistics still miss the last patient of the arm
+    {
+      const int ca = pend - 1;
+      const double *xm = U.xs + ((nt_w + 3) & 3) * Pp;
+      if (ca >= 0) {
+#pragma unroll
+        for (int r = 0; r < XR; r++) {
+          const int p = ul + r * LPU;
+          if (p < P) {
+            const double xv = xm[p], s1 = U.sumx[p * KSTR + ca], s2 = U.sumx2[p * KSTR + ca];
+            U.sumx[p * KSTR + ca] = __dadd_rn(s1, xv);
+            U.sumx2[p * KSTR + ca] = __dadd_rn(s2, __dmul_rn(xv, xv));
+          }
+        }
+        if (ul == 0) U.nj[ca] += 1;
+      }
+      __syncwarp();
     }
   }
 
@@ -734,15 +858,24 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
 }
 
 // ---- launch: instantiation picked from the batch shape (one translation unit per LPU) ----------
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
-static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC>
+static cudaError_t fast_launch7(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
+}
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
+static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
+                                int n_sweeps, cudaStream_t stream) {
+  // the package's shape (genmech: 10 predictive covariates, D = 3 outcome categories, two units per warp) is
+  // compiled with P as a constant: its dot products unroll into straight-line code
+  if constexpr (LPU == 16 && XR == 1 && DR == 3 && !NOLIK && !BIG)
+    if (d.P == 10) return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 10>(d, fa, smem, seed, iter0, n_sweeps, stream);
+  return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 0>(d, fa, smem, seed, iter0, n_sweeps, stream);
 }
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG>
 static cudaError_t fast_launch5(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,

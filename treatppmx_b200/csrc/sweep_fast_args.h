@@ -15,7 +15,7 @@ namespace tppmx {
 
 struct FastArgs {
   double *lik;     // [units][ncol][ntp] (+ntp pad)  likelihood table (global, L2 resident)
-  double *uq;      // [units][2][ntp+1]    uniforms, sum_p x_ip^2
+  double *uq;      // [units][3][ntp+1]    uniforms, sum_p x_ip^2, x_{it-1} . x_it (the long-arm kernel uses two rows)
   int *resume_l;   // [units] sweep at which the unit handed over to the generic kernel, -1 = done
   int *resume_it;  // [units] patient position of the hand-over
   int *bail_count; // [1]
@@ -43,7 +43,7 @@ struct FastArgs {
 __host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }
 // bytes of shared memory of one unit
 __host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D, int big) {
-  size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (big ? 0 : (ntp + 1)) + 2 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
+  size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (big ? 0 : (ntp + 1)) + 4 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
   size_t in = (size_t)KS + 2 * (KS + CC) + (big ? 0 : 2 * (ntp + 1)) + 1;
   return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
 }

@@ -1013,7 +1013,7 @@ static int fast_reserve(tppmx_batch *b) {
   const size_t KS = big_arms(d) ? (size_t)big_ks(d, 0) : (d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX);
   const size_t ntp = (d.ntmax + 3) & ~3, units = (size_t)d.n_chains * d.T;
   RC(dev_alloc(b, &fa.lik, units * (KS + d.CC) * ntp + ntp + 8));
-  RC(dev_alloc(b, &fa.uq, units * 2 * (ntp + 1) + 8));
+  RC(dev_alloc(b, &fa.uq, units * 3 * (ntp + 1) + 8));
   RC(dev_alloc(b, &fa.resume_l, units));
   RC(dev_alloc(b, &fa.resume_it, units));
   RC(dev_alloc(b, &fa.bail_count, 1));
