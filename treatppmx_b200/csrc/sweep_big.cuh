@@ -599,7 +599,7 @@ sweep_big_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps
         if (!NOLIK)  // likelihood column of the refreshed auxiliary eta, remaining patients
           for (int it2 = it + 1 + tid; it2 < nt; it2 += NTH) {
             const int i2 = patp[it2];
-            lik[(size_t)newcol * ntp + it2] = fast_lik(E + newcol * D, g_ez + (size_t)i2 * D, g_ljj + (size_t)i2 * D, D);
+            lik[(size_t)newcol * ntp + it2] = fast_lik<DR>(E + newcol * D, g_ez + (size_t)i2 * D, g_ljj + (size_t)i2 * D, D);
           }
         K = lab;
         if (K > Kpeak) Kpeak = K;

@@ -121,8 +121,23 @@ __device__ __forceinline__ int warp_max_over_units(int v) {
 
 // L_i(eta) without its cluster-independent part (:570-576):
 //   sum_k [ gamma_k log JJ_ik - lgamma(gamma_k) ],  gamma_k = exp(eta_k) exp(zb_ik)
-// The only call site of the lgamma code (keeps the kernel's instruction footprint small).
-static __device__ __noinline__ double fast_lik(const double *E, const double *Z, const double *ljj, int D) {
+// D <= 3 (the package's case): the patient's exp(zb) / log JJ arrive in registers, so the caller can
+// fetch them one pair ahead.  The only call site of the lgamma code for D <= 3 (keeps the kernel's
+// instruction footprint small).  Missing categories: z = 1, l = 0 (their terms are skipped).
+static __device__ __noinline__ double fast_lik3(const double *E, int D, double z0, double z1, double z2, double j0,
+                                                double j1, double j2) {
+  const bool h1 = D > 1, h2 = D > 2;
+  const double g0 = E[0] * z0;
+  const double g1 = h1 ? E[1] * z1 : 1.0;
+  const double g2 = h2 ? E[2] * z2 : 1.0;
+  double l0, l1, l2;
+  lgamma_fast3(g0, g1, g2, l0, l1, l2);
+  double w = fma(g0, j0, -l0);
+  if (h1) w += fma(g1, j1, -l1);
+  if (h2) w += fma(g2, j2, -l2);
+  return w;
+}
+static __device__ __noinline__ double fast_lik_loop(const double *E, const double *Z, const double *ljj, int D) {
   double w = 0.0;
   // three outcome categories per trip: the three lgamma evaluations are independent straight-line
   // code, so their dependent fma chains interleave (fp64 latency hiding inside one warp)
@@ -138,6 +153,14 @@ static __device__ __noinline__ double fast_lik(const double *E, const double *Z,
     if (h2) w += fma(g2, ljj[k + 2], -l2);
   }
   return w;
+}
+// pointer form (cluster birth, D > 3)
+template <int DR>
+__device__ __forceinline__ double fast_lik(const double *E, const double *Z, const double *ljj, int D) {
+  if constexpr (DR == 3)
+    return fast_lik3(E, D, Z[0], D > 1 ? Z[1] : 1.0, D > 2 ? Z[2] : 1.0, ljj[0], D > 1 ? ljj[1] : 0.0, D > 2 ? ljj[2] : 0.0);
+  else
+    return fast_lik_loop(E, Z, ljj, D);
 }
 
 // Register version for the pre-pass: the patient's exp(zb) / log JJ stay in registers while the
@@ -404,30 +427,55 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       __syncwarp();
     } else {
       if (live) {
-        // phase A, per patient (one lane each): allocation uniform, sum_p x^2, exp(beta'z), log JJ
+        // phase A, per patient (one lane each): allocation uniform, sum_p x^2, x_{it-1} . x_it, exp(beta'z),
+        // log JJ.  Every global load of a patient is issued before the first use (the lane is alone on its
+        // dependent chain: a load inside the loop over categories costs a full L2 round trip each time).
         for (int it = ul; it < nt; it += LPU) {
           const int i = patp[it];
           const double *xi = g_x + (size_t)i * P;
           const double *xm = g_x + (size_t)patp[it > 0 ? it - 1 : 0] * P;  // the patient one step earlier
-          double qx = 0.0, gx = 0.0;
-          for (int p = 0; p < P; p++) {
-            qx = fma(xi[p], xi[p], qx);
-            gx = fma(xi[p], xm[p], gx);
+          const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
+          const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
+          double JJv[DR], acc[DR];
+#pragma unroll
+          for (int k = 0; k < DR; k++) {
+            JJv[k] = (!NOLIK && k < D) ? JJ[k] : 1.0;
+            acc[k] = 0.0;
           }
+          double qx = 0.0, gx = 0.0;
+          if constexpr (PC > 0) {
+#pragma unroll
+            for (int p = 0; p < PC; p++) {
+              const double xv = xi[p];
+              qx = fma(xv, xv, qx);
+              gx = fma(xv, xm[p], gx);
+            }
+          } else {
+            for (int p = 0; p < P; p++) {
+              const double xv = xi[p];
+              qx = fma(xv, xv, qx);
+              gx = fma(xv, xm[p], gx);
+            }
+          }
+          if (!NOLIK)
+            for (int q = 0; q < Q; q++) {
+              const double zq = zi[q];
+#pragma unroll
+              for (int k = 0; k < DR; k++)
+                if (k < D) acc[k] = fma(beta[k + q * D], zq, acc[k]);
+            }
           double uu, u1;
           rng_u2(rng, l, TPPMX_SITE_ALLOC_U, tt, (uint32_t)i, 0, uu, u1);
           uq[it] = uu;
           uq[uqs + it] = qx;
           uq[2 * uqs + it] = gx;
           if (!NOLIK) {
-            const double *zi = b.z + ((size_t)ds * b.nobs + i) * Q;
-            const double *JJ = b.JJ + ((size_t)chain * b.nobs + i) * D;
-            for (int k = 0; k < D; k++) {
-              double acc = 0.0;
-              for (int q = 0; q < Q; q++) acc += beta[k + q * D] * zi[q];
-              g_ez[(size_t)i * D + k] = fast_exp(acc);
-              g_ljj[(size_t)i * D + k] = fast_log(JJ[k]);
-            }
+#pragma unroll
+            for (int k = 0; k < DR; k++)
+              if (k < D) {
+                g_ez[(size_t)i * D + k] = fast_exp(acc[k]);
+                g_ljj[(size_t)i * D + k] = fast_log(JJv[k]);
+              }
           }
         }
       }
@@ -437,17 +485,52 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         // every lane carries the same number of likelihood terms whatever n_t and K are (a loop
         // over patients with an inner loop over clusters leaves 20-40 % of the lanes idle):
         // pair e -> (c, it) = (e / nt, e % nt), kept incrementally; consecutive lanes write
-        // consecutive rows of one table column
+        // consecutive rows of one table column.  D <= 3: the operands of the NEXT pair are fetched
+        // before the current pair's three lgamma evaluations.
         const int npair = (K + CC) * nt;
         int c = ul / nt, it = ul - c * nt;
-        for (int e = ul; e < npair; e += LPU) {
-          const int i = patp[it];
-          const int cl = colmap(c, K);
-          lik[(size_t)cl * ntp + it] = fast_lik(U.E + cl * D, g_ez + (size_t)i * D, g_ljj + (size_t)i * D, D);
-          it += LPU;
-          while (it >= nt) {
-            it -= nt;
-            c += 1;
+        if constexpr (DR == 3) {
+          const bool h1 = D > 1, h2 = D > 2;
+          double z0 = 1.0, z1 = 1.0, z2 = 1.0, j0 = 0.0, j1 = 0.0, j2 = 0.0;
+          int cl = 0;
+          if (ul < npair) {
+            const size_t o = (size_t)patp[it] * D;
+            cl = colmap(c, K);
+            z0 = g_ez[o];
+            j0 = g_ljj[o];
+            if (h1) { z1 = g_ez[o + 1]; j1 = g_ljj[o + 1]; }
+            if (h2) { z2 = g_ez[o + 2]; j2 = g_ljj[o + 2]; }
+          }
+          for (int e = ul; e < npair; e += LPU) {
+            int itn = it + LPU, cn = c;
+            while (itn >= nt) {
+              itn -= nt;
+              cn += 1;
+            }
+            double y0 = 1.0, y1 = 1.0, y2 = 1.0, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+            int cln = 0;
+            if (e + LPU < npair) {
+              const size_t o = (size_t)patp[itn] * D;
+              cln = colmap(cn, K);
+              y0 = g_ez[o];
+              m0 = g_ljj[o];
+              if (h1) { y1 = g_ez[o + 1]; m1 = g_ljj[o + 1]; }
+              if (h2) { y2 = g_ez[o + 2]; m2 = g_ljj[o + 2]; }
+            }
+            lik[(size_t)cl * ntp + it] = fast_lik3(U.E + cl * D, D, z0, z1, z2, j0, j1, j2);
+            it = itn; c = cn; cl = cln;
+            z0 = y0; z1 = y1; z2 = y2; j0 = m0; j1 = m1; j2 = m2;
+          }
+        } else {
+          for (int e = ul; e < npair; e += LPU) {
+            const int i = patp[it];
+            const int cl = colmap(c, K);
+            lik[(size_t)cl * ntp + it] = fast_lik<DR>(U.E + cl * D, g_ez + (size_t)i * D, g_ljj + (size_t)i * D, D);
+            it += LPU;
+            while (it >= nt) {
+              it -= nt;
+              c += 1;
+            }
           }
         }
       }
@@ -758,7 +841,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
             for (int it2 = it + 1 + ul; it2 < nt; it2 += LPU) {
               const int i2 = patp[it2];
               lik[(size_t)newcol * ntp + it2] =
-                  fast_lik(U.E + newcol * D, g_ez + (size_t)i2 * D, g_ljj + (size_t)i2 * D, D);
+                  fast_lik<DR>(U.E + newcol * D, g_ez + (size_t)i2 * D, g_ljj + (size_t)i2 * D, D);
             }
           K = lab;
           dV = dV_of(K);
