@@ -517,7 +517,18 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
               if (h1) { y1 = g_ez[o + 1]; m1 = g_ljj[o + 1]; }
               if (h2) { y2 = g_ez[o + 2]; m2 = g_ljj[o + 2]; }
             }
-            lik[(size_t)cl * ntp + it] = fast_lik3(U.E + cl * D, D, z0, z1, z2, j0, j1, j2);
+            {  // inlined (a call would wait for the loads in flight): sum_k gamma_k log JJ_k - lgamma(gamma_k)
+              const double *E = U.E + cl * D;
+              const double g0 = E[0] * z0;
+              const double g1 = h1 ? E[1] * z1 : 1.0;
+              const double g2 = h2 ? E[2] * z2 : 1.0;
+              double l0, l1, l2;
+              lgamma_fast3(g0, g1, g2, l0, l1, l2);
+              double w = fma(g0, j0, -l0);
+              if (h1) w += fma(g1, j1, -l1);
+              if (h2) w += fma(g2, j2, -l2);
+              lik[(size_t)cl * ntp + it] = w;
+            }
             it = itn; c = cn; cl = cln;
             z0 = y0; z1 = y1; z2 = y2; j0 = m0; j1 = m1; j2 = m2;
           }
