@@ -82,12 +82,15 @@ constexpr unsigned TPPMX_FULL = 0xffffffffu;
 // cluster birth, > LPU candidates) are entered warp-uniformly through __any_sync.
 // maximum over the unit's lanes: one redux.sync on an order-preserving integer image of the
 // float instead of log2(LPU) shuffle + max levels (the step's dependent chain is what bounds it)
+// A shift for the unit's softmax: the largest weight of the unit's lanes with its low mantissa word
+// cleared (within 2^-20 relative of the maximum, which is all the shift has to be: common to the lanes
+// and close to the maximum).  The high word of an fp64 orders like a sign-magnitude integer, so no
+// conversion is needed; one full-mask redux per unit of the warp (a redux over a partial mask is
+// serialised per distinct mask behind a WARPSYNC.EXCLUSIVE loop; with the full mask they pipeline).
 template <int LPU>
-__device__ __forceinline__ float unit_maxf(float v, int sub) {
-  int i = __float_as_int(v);
+__device__ __forceinline__ double unit_shift(double w, int sub) {
+  int i = __double2hiint(w);
   i ^= (i >> 31) & 0x7fffffff;
-  // one full-mask redux per unit of the warp (a redux over a partial mask is serialised per distinct
-  // mask behind a WARPSYNC.EXCLUSIVE loop; with the full mask the 32 / LPU reductions pipeline)
   int r = i;
 #pragma unroll
   for (int s = 0; s < 32 / LPU; s++) {
@@ -95,7 +98,7 @@ __device__ __forceinline__ float unit_maxf(float v, int sub) {
     if (sub == s) r = m;
   }
   r ^= (r >> 31) & 0x7fffffff;
-  return __int_as_float(r);
+  return __hiloint2double(r, 0);
 }
 template <int LPU>
 __device__ __forceinline__ double unit_sum(double v) {
@@ -650,7 +653,6 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       const double uu_n = uq[it + 1], qx_n = uq[uqs + it + 1], g_n = uq[2 * uqs + it + 1];
       int lab_n = labp[it + 1];  // label of the next patient (re-read after a relabelling)
       if (!NOLIK) lik_n = likp[it + 1];
-      bool structural = false;
 
       // ---- :368-457 take the patient out of its cluster; :820-856 of the previous step (deferred).
       //      Branch-free: a missing arrival / removal adds 0.0 to the column of the other one, and lanes
@@ -660,6 +662,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       TPPMX_ASSERT(!on || nzi >= 1, 2);
       TPPMX_ASSERT(it + 1 <= ntp, 3);
       const bool single = on && nzi <= 1;
+      // rows of the tables over n for this lane's cluster after the removal (issued before the statistics'
+      // read-modify-writes; re-read below if the partition changes)
+      const int n_sc = myn - ((on && !single && ul == zi) ? 1 : 0);
+      double2 t01 = tab2[2 * n_sc], t23 = tab2[2 * n_sc + 1];  // (dA, HN), (HY, -)
+      double lgn = lognp[n_sc];
       {
         const bool add = pend != 0;        // cluster pend-1 receives patient it-1
         const bool rem = on && !single;    // cluster zi loses patient it
@@ -682,17 +689,18 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           *pr1 = nr1;
           *pr2 = nr2;
         }
-        if (ul == 0) {
-          const int na = U.nj[ca] + (add ? 1 : 0);
-          U.nj[ca] = na;
-          const int nr = ((ca == zi) ? na : U.nj[zi]) - (rem ? 1 : 0);
-          U.nj[zi] = nr;
+        // cluster sizes: every lane keeps its cluster's size in a register (the arrival was counted when
+        // it was drawn) and stores it; clusters beyond the lanes (K > LPU, rare) are updated by lane 0
+        myn = n_sc;
+        if (ul < KS) U.nj[ul] = myn;
+        if (LPU < TPPMX_FAST_KSMAX && anymulti && ul == 0) {
+          if (add && ca >= LPU) U.nj[ca] += 1;
+          if (rem && zi >= LPU) U.nj[zi] -= 1;
         }
-        myn -= (rem && ul == zi) ? 1 : 0;
       }
       pend = 0;
       __syncwarp();
-      if (__any_sync(TPPMX_FULL, single)) {  // singleton (:384-457), rare
+      if (__builtin_expect(__any_sync(TPPMX_FULL, single), 0)) {  // singleton (:384-457), rare
         const int iaux = zi + 1, Kc = K;
         const bool swp = single && iaux < Kc;
         if (swp)  // swap with the last cluster
@@ -736,7 +744,6 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           }
           K = Kc - 1;
           dV = dV_of(K);
-          structural = true;
         }
         anymulti = __any_sync(TPPMX_FULL, live && K + CC > LPU);
         __syncwarp();
@@ -748,6 +755,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           a_c = ar;
           b_c = br;
           myn = (ul < K) ? U.nj[ul] : 0;
+          t01 = tab2[2 * myn];
+          t23 = tab2[2 * myn + 1];
+          lgn = lognp[myn];
           act0 = ul < K + CC;
           likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
           TPPMX_ASSERT(!act0 || (colmap(ul, K) >= 0 && colmap(ul, K) < fa.ncol), 6);
@@ -765,15 +775,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       const double t1 = fma(iv2, qx, 2.0 * b_c);
       double w, wmax;
       {
-        const int n = myn;
         const double tY = fma(iv2, t1, a_c);
-        const double2 t01 = tab2[2 * n], t23 = tab2[2 * n + 1];  // (dA, HN), (HY, -)
         const double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a_c);
-        const double wv = dV + lognp[n] + simscale * d + likv;
+        const double wv = dV + lgn + simscale * d + likv;
         w = act0 ? wv : -INFINITY;
-        // the shift only has to be common to the unit's lanes and close to the maximum: the
-        // float-rounded maximum costs a quarter of the shuffles of an fp64 max
-        wmax = (double)unit_maxf<LPU>((float)w, sub);
+        wmax = unit_shift<LPU>(w, sub);
       }
       // ---- a, b of patient it+1 against the statistics without patient it: independent of this step's
       //      draw; placed here so that the scheduler interleaves it with the exp / scan chain below.
@@ -805,7 +811,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
       }
       const bool multi = on && ntot > LPU;
-      if (anymulti && __any_sync(TPPMX_FULL, multi)) {
+      if (__builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
         double *prow = nullptr;
         if constexpr (PROBE) {
           const int pu = unit - fa.probe_unit0;
@@ -822,7 +828,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       TPPMX_ASSERT(!born || (nfree >= 1 && K + 1 <= KS), 5);
       int lab = newci;
       if (on && !born && ul == 0) labp[it] = lab;
-      if (__any_sync(TPPMX_FULL, born)) {  // a new cluster takes the auxiliary eta (:829-845), rare
+      if (__builtin_expect(__any_sync(TPPMX_FULL, born), 0)) {  // a new cluster takes the auxiliary eta (:829-845), rare
         int m = 0, newcol = 0, i = 0;
         if (born) {
           i = patp[it];
@@ -856,9 +862,14 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
             }
           K = lab;
           dV = dV_of(K);
-          structural = true;
         }
         anymulti = __any_sync(TPPMX_FULL, live && K + CC > LPU);
+        __syncwarp();
+        if (born) {  // lanes change roles: likelihood column of each lane, next patient's entry
+          act0 = ul < K + CC;
+          likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
+          if (!NOLIK) lik_n = likp[it + 1];
+        }
       }
       // ---- the lane of the cluster that receives patient it: its size, and a, b of patient it+1
       //      (a lane >= the old K held the empty cluster's values: a birth needs nothing else)
@@ -885,11 +896,6 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       a_c = a_n;
       b_c = b_n;
       __syncwarp();
-      if (structural) {
-        act0 = ul < K + CC;
-        likp = lik + (size_t)(act0 ? colmap(ul, K) : 0) * ntp;
-        if (!NOLIK) likv = likp[it + 1];
-      }
     }
     // ---- the statistics still miss the last patient of the arm
     {
