@@ -10,7 +10,12 @@ from treatppmx_b200.engine import Context
 from treatppmx_b200.ppmxct import dm_ppmx_ct
 
 iters, burn, thin = 1100, 100, 1
-for name in ("default_ngg", "dp_T3"):
+names = ("default_ngg", "dp_T3")
+if len(sys.argv) > 1:  # python scripts/single_chain.py CASE [ITERS]  (short runs for launch lists)
+    names = (sys.argv[1],)
+    if len(sys.argv) > 2:
+        iters = int(sys.argv[2]); burn = iters // 10
+for name in names:
     args, logV, case = refrun.reference_args(name, iters, burn, thin, False)
     ctx = Context(0)
     dm_ppmx_ct(ctx, **dict(args, iter=20, burn=10), seed=1, logV_compact=logV)  # warm
