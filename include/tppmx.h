@@ -250,10 +250,16 @@ enum {
   TPPMX_OPT_FAST_STAGED_CLUSTERS = 3, /* clusters per arm the fast kernel stages on chip: 1..32, default
                                         min(kcap,32); long arms (thousands of patients) 1..256, default
                                         min(kcap,256); set before the first sweep */
-  TPPMX_OPT_BIG_THREADS = 4          /* long arms: threads per (chain, arm) of the long-arm kernel, 32 | 128 | 256;
+  TPPMX_OPT_BIG_THREADS = 4,         /* long arms: threads per (chain, arm) of the long-arm kernel, 32 | 128 | 256;
                                         0 = automatic (32 when the units outnumber what the SMs hold) */
+  TPPMX_OPT_CHAIN_GROUPS = 5         /* tppmx_batch_run: the chains are split into this many contiguous groups,
+                                        each iterating on its own streams, so that the sweep of one group
+                                        overlaps the updates of another (chains are independent; results do not
+                                        depend on the grouping).  1..TPPMX_MAX_GROUPS, 0 = automatic (1: measured on
+                                        B200, two groups of 512 chains run no faster than one of 1024) */
 };
-enum { TPPMX_INFO_LAST_SWEEP_IMPL = 1, TPPMX_INFO_LAST_HANDOVERS = 2 };
+#define TPPMX_MAX_GROUPS 8
+enum { TPPMX_INFO_LAST_SWEEP_IMPL = 1, TPPMX_INFO_LAST_HANDOVERS = 2, TPPMX_INFO_LAST_CHAIN_GROUPS = 3 };
 int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value);
 int tppmx_batch_get_info(const tppmx_batch *b, int32_t what, int32_t *value);
 

@@ -74,6 +74,36 @@ def test_run_lockstep_with_oracle(ctx, name):
         _compare(b.get_state(c), st, dims, f"{name} chain {c} after {niter} iterations")
 
 
+@pytest.mark.parametrize("name,groups", [("default_ngg", 3), ("dp_T3", 2), ("nnig", 4)])
+def test_run_in_chain_groups_matches_oracle_and_one_group(ctx, name, groups):
+    """tppmx_batch_run with the chains split into groups on their own streams (TPPMX_OPT_CHAIN_GROUPS): chains are
+    independent, so every chain must end exactly where it does in one group -- and where the oracle does; the
+    per-dataset summaries (shared accumulators) must agree too."""
+    from treatppmx_b200.engine import Batch
+    model, dims, shared, dsets, labels, nclu, betas = build_case(name, n_datasets=2)
+    nchains, niter = 7, 24
+    cds = [c % 2 for c in range(nchains)]
+    outs = []
+    for g in (1, groups):
+        b = Batch(ctx, model, dims, shared, dsets, chain_dataset=cds)
+        b.init(29, labels, nclu, betas[0])
+        b.set_chain_groups(g)
+        b.run(29, 0, niter, burn=8, thin=2, psm=True, predictive=dims.npred > 0)
+        assert b.last_chain_groups() == g
+        outs.append(([b.get_state(c) for c in range(nchains)], b.summaries([1.0] * dims.D)))
+        b.close()
+    pbs = [ob.Problem(model, dims, shared, d) for d in dsets]
+    for c in range(nchains):
+        st = pbs[cds[c]].init_state(29, c, labels, nclu, betas[0])
+        pbs[cds[c]].iterate(st, 29, c, 0, niter)
+        _compare(outs[1][0][c], st, dims, f"{name} chain {c}, {groups} groups vs oracle")
+        _compare(outs[1][0][c], outs[0][0][c], dims, f"{name} chain {c}, {groups} groups vs one group")
+    s1, sg = outs[0][1], outs[1][1]
+    assert np.array_equal(s1["psm"], sg["psm"])
+    if dims.npred > 0:
+        np.testing.assert_allclose(sg["pi_mean"], s1["pi_mean"], rtol=1e-12, atol=1e-15)
+
+
 @pytest.mark.parametrize("over", [dict(hsp=0), dict(upd_hier=0), dict(noprog=1, hsp=0, upd_hier=0)],
                          ids=["hsp0", "upd_hier0", "noprog1-hsp0-upd_hier0"])
 def test_run_lockstep_with_the_update_switches_off(ctx, over):

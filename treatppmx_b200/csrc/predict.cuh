@@ -45,7 +45,8 @@ __device__ inline PredW pred_weight(const DevBatch &b, const SimConst &s, const 
 // one multinomial draw, outputs in the reference's layouts.
 __device__ inline void pred_emit(const DevBatch &b, const Rng &rng, const ArmView &A, int iter, int tt, int pp, int ds,
                                  int newci, int K, const double *beta, const double *Theta, const double *Sigma,
-                                 size_t obase, int chain, double *pipred, double *ypred, int *predclass) {
+                                 size_t obase, int chain, double *pipred, double *ypred, int *predclass,
+                                 double *pisum = nullptr) {
   const int D = b.D, npred = b.npred;
   double eta_pred[TPPMX_MAXD];
   if (newci <= K) {  // :1366-1370
@@ -75,20 +76,23 @@ __device__ inline void pred_emit(const DevBatch &b, const Rng &rng, const ArmVie
     sumrow += pi_row[k];
   }
   for (int k = 0; k < D; k++) pi_row[k] = pi_row[k] / sumrow;
-  double uy, uy1, cw = 0.0;  // :1381 rmultinom(1, pi)
-  rng_u2(rng, iter, TPPMX_SITE_PRED_Y, tt, (uint32_t)pp, 0, uy, uy1);
   int pick = D - 1;
-  for (int k = 0; k < D; k++) {
-    cw += pi_row[k];
-    if (uy < cw) {
-      pick = k;
-      break;
+  if (ypred) {  // :1381 rmultinom(1, pi); the draw has its own Philox block, so skipping it moves no other variate
+    double uy, uy1, cw = 0.0;
+    rng_u2(rng, iter, TPPMX_SITE_PRED_Y, tt, (uint32_t)pp, 0, uy, uy1);
+    for (int k = 0; k < D; k++) {
+      cw += pi_row[k];
+      if (uy < cw) {
+        pick = k;
+        break;
+      }
     }
   }
   for (int k = 0; k < D; k++) {
     const size_t o = obase + pp + (size_t)npred * (k + (size_t)D * tt);
     if (pipred) pipred[o] = pi_row[k];
     if (ypred) ypred[o] = (k == pick) ? 1.0 : 0.0;
+    if (pisum) atomicAdd(pisum + (size_t)ds * npred * D * b.T + (o - obase), pi_row[k]);  // summary.cuh
   }
   if (predclass) predclass[(size_t)chain * npred * b.T + pp + (size_t)npred * tt] = newci;
 }
@@ -96,8 +100,11 @@ __device__ inline void pred_emit(const DevBatch &b, const Rng &rng, const ArmVie
 // grid = (chains, T); threads stride over new patients
 __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed, int iter,
                                                       double *pipred, double *ypred,
-                                                      int *predclass) {
-  const int chain = blockIdx.x, tt = blockIdx.y;
+                                                      int *predclass, double *pisum) {
+  // block = (chain, arm): the arms of a chain (and the chains of a dataset) are adjacent blocks, so a dataset's new
+  // patients are read from DRAM once (as grid (chains, T) every arm made its own pass: 930 MB against 250 MB of inputs)
+  const int chain = blockIdx.x / b.T, tt = blockIdx.x % b.T;
+  const int pp_lo = 0, pp_hi = b.npred;
   const int ds = b.chain_ds[chain];
   const SimConst s = make_simconst(b);
   const Rng rng = make_rng(seed, b.chain_id[chain]);
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
   const size_t obase = (size_t)chain * npred * D * b.T;
   const int nc1 = b.ncat > 0 ? b.ncat : 1;
 
-  for (int pp = threadIdx.x; pp < npred; pp += blockDim.x) {
+  for (int pp = pp_lo + threadIdx.x; pp < pp_hi; pp += blockDim.x) {
     const double *x = b.xp + ((size_t)ds * npred + pp) * b.P;
     const int *xc_new = b.xcatp + ((size_t)ds * npred + pp) * nc1;
     // quirk 6: training row `pp` (requires pp < nobs when ncat > 0; checked on the host)
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
       }
     }
 
-    pred_emit(b, rng, A, iter, tt, pp, ds, newci, K, beta, Theta, Sigma, obase, chain, pipred, ypred, predclass);
+    pred_emit(b, rng, A, iter, tt, pp, ds, newci, K, beta, Theta, Sigma, obase, chain, pipred, ypred, predclass, pisum);
   }
 }
 
@@ -178,9 +185,10 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
 // dynamic smem: ((P + 3) * KP + P * nth + (KP + 1) * nth) doubles, KP = clusters staged (>= K).
 // kmin: arms with fewer occupied clusters were handled by predict_reg_kernel (block-uniform exit).
 __global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t seed, int iter, int KP, int kmin,
-                                                           double *pipred, double *ypred, int *predclass) {
+                                                           double *pipred, double *ypred, int *predclass, double *pisum) {
   extern __shared__ double psm[];
-  const int chain = blockIdx.x, tt = blockIdx.y, tid = threadIdx.x, nth = blockDim.x;
+  const int chain = blockIdx.x / b.T, tt = blockIdx.x % b.T, tid = threadIdx.x, nth = blockDim.x;
+  const int pp_lo = 0, pp_hi = b.npred;
   const int ds = b.chain_ds[chain];
   const SimConst s = make_simconst(b);
   const Rng rng = make_rng(seed, b.chain_id[chain]);
@@ -225,9 +233,9 @@ __global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t 
   const size_t obase = (size_t)chain * npred * D * b.T;
   __syncthreads();
 
-  for (int pp0 = 0; pp0 < npred; pp0 += nth) {
+  for (int pp0 = pp_lo; pp0 < pp_hi; pp0 += nth) {
     const int pp = pp0 + tid;
-    const bool on = pp < npred;
+    const bool on = pp < pp_hi;
     double qx = 0.0, sx = 0.0;
     if (on) {
       const double *x = b.xp + ((size_t)ds * npred + pp) * P;
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t 
           break;
         }
       }
-      pred_emit(b, rng, A, iter, tt, pp, ds, newci, K, beta, Theta, Sigma, obase, chain, pipred, ypred, predclass);
+      pred_emit(b, rng, A, iter, tt, pp, ds, newci, K, beta, Theta, Sigma, obase, chain, pipred, ypred, predclass, pisum);
     }
   }
 }
@@ -288,14 +296,15 @@ __global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t 
 #define TPPMX_PRED_KR 16
 template <int PR>
 __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_t seed, int iter, double *pipred,
-                                                          double *ypred, int *predclass) {
+                                                          double *ypred, int *predclass, double *pisum) {
   constexpr int KR = TPPMX_PRED_KR, DR = 3;
   __shared__ double ts[PR][KR];
   __shared__ double cs[3][KR];
   __shared__ double etas[DR][KR];
   __shared__ double Ls[DR * DR], Ths[DR], betas[DR * TPPMX_MAXQ];
   __shared__ double ws[KR][128];  // the thread's weights, column tid
-  const int chain = blockIdx.x, tt = blockIdx.y, tid = threadIdx.x, nth = blockDim.x;
+  const int chain = blockIdx.x / b.T, tt = blockIdx.x % b.T, tid = threadIdx.x, nth = blockDim.x;
+  const int pp_lo = 0, pp_hi = b.npred;
   const int ds = b.chain_ds[chain];
   const ArmView A = arm_view_global(b, chain, tt, ds);
   const int K = A.K;
@@ -346,8 +355,14 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
   const size_t obase = (size_t)chain * npred * D * b.T;
   __syncthreads();
 
-  for (int pp = tid; pp < npred; pp += nth) {
+  for (int pp = pp_lo + tid; pp < pp_hi; pp += nth) {
     double x[PR], qx = 0.0, sx = 0.0;
+    // the first prognostic covariates travel with the predictive ones (their loads would otherwise sit, one
+    // L2 round trip each, on the tail of the thread's dependent chain)
+    const double *zp = b.zpred + ((size_t)ds * npred + pp) * Q;
+    double zq[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) zq[q] = (q < Q) ? zp[q] : 0.0;
     {
       const double *xr = b.xp + ((size_t)ds * npred + pp) * P;
 #pragma unroll
@@ -409,8 +424,23 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
 #pragma unroll
       for (int k = 0; k < DR; k++) ep[k] = (k < D) ? etas[k][newci - 1] : 0.0;
     } else {
+      // the D <= 3 standard normals of rng_normals (block b -> normals 2b, 2b+1), with the branch-free log and
+      // sincospi (no large-argument path): most warps enter here for some lane, so the branch is on every
+      // warp's path (profiles/r2_predict_reg_*: a quarter of the kernel's instructions were these draws)
       double zn[4];
-      rng_normals(rng, iter, TPPMX_SITE_PRED_ETA, tt, (uint32_t)pp, D, zn, 1);
+      {
+        double u0, u1, sn, cs;
+        rng_u2(rng, iter, TPPMX_SITE_PRED_ETA, tt, (uint32_t)pp, 0, u0, u1);
+        const double r = sqrt(-2.0 * fast_log(u0));
+        sincospi(2.0 * u1, &sn, &cs);
+        zn[0] = r * cs;
+        zn[1] = r * sn;
+        zn[2] = 0.0;
+        if (D > 2) {
+          rng_u2(rng, iter, TPPMX_SITE_PRED_ETA, tt, (uint32_t)pp, 1, u0, u1);
+          zn[2] = sqrt(-2.0 * fast_log(u0)) * cospi(2.0 * u1);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < DR; k++) {
         double acc = (k < D) ? Ths[k] : 0.0;
@@ -418,39 +448,47 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
         ep[k] = acc;
       }
     }
-    const double *zp = b.zpred + ((size_t)ds * npred + pp) * Q;
     double pr[DR], sumrow = 0.0;
 #pragma unroll
     for (int k = 0; k < DR; k++) {
       pr[k] = 0.0;
       if (k < D) {
         double lg = ep[k];
-        for (int q = 0; q < Q; q++) lg += betas[k + q * D] * zp[q];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (q < Q) lg += betas[k + q * D] * zq[q];
+        for (int q = 4; q < Q; q++) lg += betas[k + q * D] * zp[q];
         pr[k] = fast_exp(lg);
         sumrow += pr[k];
       }
     }
     const double rs = fast_rcp(sumrow);
-    double uy, uy1, cwy = 0.0;
-    rng_u2(rng, iter, TPPMX_SITE_PRED_Y, tt, (uint32_t)pp, 0, uy, uy1);
-    int pick = D - 1;
-    bool got = false;
 #pragma unroll
-    for (int k = 0; k < DR; k++)
-      if (k < D) {
-        pr[k] *= rs;
-        cwy += pr[k];
-        if (!got && uy < cwy) {
-          pick = k;
-          got = true;
+    for (int k = 0; k < DR; k++) pr[k] *= rs;
+    int pick = D - 1;
+    if (ypred) {  // block-uniform; the outcome draw has its own Philox block (skipping it moves no other variate)
+      double uy, uy1, cwy = 0.0;
+      rng_u2(rng, iter, TPPMX_SITE_PRED_Y, tt, (uint32_t)pp, 0, uy, uy1);
+      bool got = false;
+#pragma unroll
+      for (int k = 0; k < DR; k++)
+        if (k < D) {
+          cwy += pr[k];
+          if (!got && uy < cwy) {
+            pick = k;
+            got = true;
+          }
         }
-      }
+    }
 #pragma unroll
     for (int k = 0; k < DR; k++)
       if (k < D) {
         const size_t o = obase + pp + (size_t)npred * (k + (size_t)D * tt);
         if (pipred) pipred[o] = pr[k];
         if (ypred) ypred[o] = (k == pick) ? 1.0 : 0.0;
+        // summary.cuh: posterior-predictive sums per replicate dataset, accumulated here (one RED.F64 per value)
+        // instead of a per-chain cube written out and read back by a second kernel
+        if (pisum) atomicAdd(pisum + (size_t)ds * npred * D * b.T + (o - obase), pr[k]);
       }
     if (predclass) predclass[(size_t)chain * npred * b.T + pp + (size_t)npred * tt] = newci;
   }

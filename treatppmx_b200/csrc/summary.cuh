@@ -24,13 +24,8 @@ __global__ void psm_accumulate_kernel(DevBatch b, int *psm) {
   }
 }
 
-// pisum[ds][(t*D+k)*npred + pp] += pipred[chain][...]   (pipred is the col-major npred x D x T cube)
-__global__ void pi_accumulate_kernel(DevBatch b, const double *pipred, double *pisum) {
-  const int chain = blockIdx.x;
-  const int ds = b.chain_ds[chain];
-  const size_t n1 = (size_t)b.npred * b.D * b.T;
-  for (size_t e = threadIdx.x; e < n1; e += blockDim.x) atomicAdd(pisum + (size_t)ds * n1 + e, pipred[(size_t)chain * n1 + e]);
-}
+// pisum[ds][(t*D+k)*npred + pp] += pipred of every chain of the dataset: added by the predictive kernels themselves
+// (predict.cuh, one RED.F64 per value) -- no per-chain cube is written out and read back.
 
 // grid = datasets: means, utilities, chosen arm
 __global__ void summarise_kernel(DevBatch b, const int *psm, const int *psm_n, const double *pisum,

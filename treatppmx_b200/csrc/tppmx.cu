@@ -4,8 +4,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -64,9 +66,19 @@ struct tppmx_ctx {
   // tppmx_set_interrupt_flag
   const volatile int32_t *interrupt = nullptr;
   int check_every = 64;
+  // chain groups of tppmx_batch_run (TPPMX_OPT_CHAIN_GROUPS): each group of chains runs its iterations on its
+  // own stream triple, so that the sweep of one group overlaps the updates of another -- chains are independent,
+  // and at BASELINE's 1024 chains every kernel of the iteration is latency-bound (2.6 warps per scheduler)
+  std::vector<tppmx_ctx *> lanes;
+  cudaEvent_t ev_go = nullptr, ev_done = nullptr;
+  bool side_pending = false;  // summaries of a saved iteration still running on `side`
 };
 static void ctx_release(tppmx_ctx *c) {
   cudaSetDevice(c->device);
+  for (tppmx_ctx *l : c->lanes) ctx_release(l);
+  c->lanes.clear();
+  if (c->ev_go) cudaEventDestroy(c->ev_go);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
   cudaStreamDestroy(c->stream);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_sweep) cudaEventDestroy(c->ev_sweep);
@@ -102,7 +114,8 @@ struct tppmx_batch {
   int last_launches;
   int scratch_chain;  // slot index n_chains
   // fast sweep kernel (sweep_fast.cuh)
-  int opt_impl = 0, opt_lpu = 0, opt_ks = 0;
+  int opt_impl = 0, opt_lpu = 0, opt_ks = 0, opt_groups = 0;
+  int last_groups = 1;
   FastArgs fa;
   UpdArgs ua{};
   bool fast_ready = false;
@@ -129,11 +142,7 @@ static int fail(tppmx_ctx *ctx, int code, const std::string &msg) {
 
 extern "C" int tppmx_version(void) { return TPPMX_VERSION; }
 
-extern "C" int tppmx_create(tppmx_ctx **out, int device) {
-  if (!out) return TPPMX_ERR_ARG;
-  *out = nullptr;
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return TPPMX_ERR_CUDA;
+static tppmx_ctx *ctx_new(int device) {
   tppmx_ctx *c = new tppmx_ctx();
   c->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -143,10 +152,22 @@ extern "C" int tppmx_create(tppmx_ctx **out, int device) {
       cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->hs, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_hs_go, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_hs_done, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&c->ev_hs_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
-    return TPPMX_ERR_CUDA;
+    return nullptr;
   }
+  return c;
+}
+
+extern "C" int tppmx_create(tppmx_ctx **out, int device) {
+  if (!out) return TPPMX_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return TPPMX_ERR_CUDA;
+  tppmx_ctx *c = ctx_new(device);
+  if (!c) return TPPMX_ERR_CUDA;
   *out = c;
   return TPPMX_OK;
 }
@@ -247,7 +268,7 @@ static T *dev_stage(tppmx_batch *b, const T **p, size_t n, int *rc) {
 static bool fast_eligible(const tppmx_batch *b, int lpu);
 static bool big_arms(const DevBatch &d);
 static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc,
-                          cudaStream_t st = nullptr);
+                          cudaStream_t st = nullptr, double *dsum = nullptr, int *launches = nullptr);
 // one thread per new patient of an (chain, arm) block: no more threads than patients
 static inline int predict_threads(const DevBatch &d) {
   const int t = ((d.npred + 31) / 32) * 32;
@@ -970,6 +991,10 @@ extern "C" int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value
     b->opt_ks = value;
     return TPPMX_OK;
   }
+  if (opt == TPPMX_OPT_CHAIN_GROUPS && value >= 0 && value <= TPPMX_MAX_GROUPS) {
+    b->opt_groups = value;
+    return TPPMX_OK;
+  }
   if (opt == TPPMX_OPT_BIG_THREADS && (value == 0 || value == 128 || value == 256)) {
     b->opt_big_nth = value;
     return TPPMX_OK;
@@ -981,6 +1006,7 @@ extern "C" int tppmx_batch_get_info(const tppmx_batch *b, int32_t what, int32_t 
   if (!b || !value) return TPPMX_ERR_ARG;
   if (what == TPPMX_INFO_LAST_SWEEP_IMPL) *value = b->last_impl;
   else if (what == TPPMX_INFO_LAST_HANDOVERS) *value = b->last_handovers;
+  else if (what == TPPMX_INFO_LAST_CHAIN_GROUPS) *value = b->last_groups;
   else return TPPMX_ERR_ARG;
   return TPPMX_OK;
 }
@@ -1016,8 +1042,8 @@ static int fast_reserve(tppmx_batch *b) {
   RC(dev_alloc(b, &fa.uq, units * 3 * (ntp + 1) + 8));
   RC(dev_alloc(b, &fa.resume_l, units));
   RC(dev_alloc(b, &fa.resume_it, units));
-  RC(dev_alloc(b, &fa.bail_count, 1));
-  RC(dev_alloc(b, &fa.kmax_dev, 1));
+  RC(dev_alloc(b, &fa.bail_count, TPPMX_MAX_GROUPS));  // one counter per chain group of tppmx_batch_run
+  RC(dev_alloc(b, &fa.kmax_dev, TPPMX_MAX_GROUPS));
   fa.lik_unit_stride = (KS + d.CC) * ntp;
   RC(dev_alloc(b, &fa.logng, units * (ntp + 1)));
   RC(dev_alloc(b, &fa.patpad, units * (ntp + 1)));
@@ -1230,6 +1256,9 @@ extern "C" int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t it
   return rc;
 }
 
+static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do_psm, int do_pred, int *launches,
+                             cudaStream_t st = nullptr);
+
 // ev_after_update (optional): recorded between the update kernel and the gamma draws, so that work
 // which only needs eta*, beta, (Theta,Sigma), (sigma,kappa) can start beside the draws
 // the main stream rejoins a horseshoe update still running on the third stream
@@ -1293,8 +1322,79 @@ extern "C" int tppmx_batch_update(tppmx_batch *b, uint64_t seed, int32_t iter) {
   return TPPMX_OK;
 }
 
-static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do_psm, int do_pred, int *launches,
-                             cudaStream_t st = nullptr);
+
+// chain-major arrays of a DevBatch moved to chain c (layout.h); datasets and tables are shared
+static void offset_chain_ptrs(DevBatch &d, const DevBatch &p, size_t c) {
+  const size_t T = p.T, D = p.D, Q = p.Q;
+  d.chain_ds += c; d.chain_id += c;
+  d.labels += c * st_labels(p); d.nj += c * st_nj(p); d.nclu += c * T; d.njc += c * st_njc(p);
+  d.idxs += c; d.status += c;
+  d.sumx += c * st_sumx(p); d.sumx2 += c * st_sumx(p); d.eta += c * st_eta(p); d.etae += c * st_etae(p);
+  d.JJ += c * st_pat(p); d.ss += c * p.nobs; d.lg += c * st_pat(p); d.beta += c * Q * D;
+  d.sigma += c * T; d.kappa += c * T; d.Theta += c * T * D; d.Sigma += c * T * D * D;
+  d.lambda += c * Q * D; d.tau += c; d.sigma_beta += c * Q * D;
+  d.zb += c * st_pat(p); d.ljj += c * st_pat(p); d.cpat += c * p.nobs; d.wbuf += c * st_wbuf(p);
+  d.eta_flag += c * T * p.kcap; d.beta_flag += c * Q * D;
+}
+
+// A view of chains [c0, c0 + nc) of a batch on the streams of `lane`: every per-chain array is chain-major
+// (layout.h), so the view is the same batch with offset pointers; datasets, tables and the per-dataset summary
+// accumulators (atomic adds) are shared.  g = group index (its own hand-over counter).
+static void batch_view(const tppmx_batch *b, tppmx_batch *v, tppmx_ctx *lane, int g, int c0, int nc) {
+  *v = *b;
+  v->ctx = lane;
+  const DevBatch &p = b->d;
+  const size_t c = (size_t)c0, T = p.T, D = p.D;
+  offset_chain_ptrs(v->d, p, c);
+  v->d.n_chains = nc;
+  UpdArgs &u = v->ua;
+  u.eta2 += c * T * 2 * D * p.kcap; u.pat2 += c * 3 * T * p.ntmax; u.os += c * T * p.G; u.acc += c * T * p.kcap;
+  FastArgs &f = v->fa;
+  if (f.lik) {
+    const size_t u0 = c * T, ntp = (p.ntmax + 3) & ~3;
+    f.lik += u0 * f.lik_unit_stride; f.uq += u0 * 3 * (ntp + 1);
+    f.resume_l += u0; f.resume_it += u0; f.logng += u0 * (ntp + 1); f.patpad += u0 * (ntp + 1);
+    f.bail_count += g; f.kmax_dev += g;
+  }
+  v->fast_ready = false;  // n_units follows the view
+  v->kmax_host = nullptr;
+}
+
+// one iteration (sweep, updates, and on a saved iteration the co-clustering counts / predictive step) of the
+// batch or chain-group view `b` on the streams of b->ctx
+static int run_iteration(tppmx_batch *b, uint64_t seed, int l, bool saved, int do_psm, int do_pred, int *launches) {
+  tppmx_ctx *ctx = b->ctx;
+  // Saved iterations: the co-clustering counts only need the partition (ready after the sweep) and
+  // the predictive step only needs what the update kernel writes, so they run on the side stream
+  // beside the update kernel / the JJ-ss gamma draws; the next sweep waits for them.
+  if (ctx->side_pending) {
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+    ctx->side_pending = false;
+  }
+  RC(sweep_launch(b, seed, l, 1, false, launches));
+  if (!saved) return update_launch(b, seed, l, launches, nullptr, true);
+  if (do_psm) {
+    CK(ctx, cudaEventRecord(ctx->ev_sweep, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_sweep, 0));
+    RC(accumulate_launch(b, seed, l, 1, 0, launches, ctx->side));
+  }
+  RC(update_launch(b, seed, l, launches, do_pred ? ctx->ev_upd : nullptr, true));
+  if (do_pred) {
+    CK(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_upd, 0));
+    RC(accumulate_launch(b, seed, l, 0, 1, launches, ctx->side));
+  }
+  CK(ctx, cudaEventRecord(ctx->ev_side, ctx->side));
+  ctx->side_pending = true;
+  return TPPMX_OK;
+}
+
+static int run_groups(const tppmx_batch *b) {
+  int g = b->opt_groups;
+  if (g == 0) g = 1;  // measured (profiles/r2_chain_groups.txt): at 1024 chains the kernels already fill the issue slots
+  if (b->fa.lik && big_arms(b->d)) g = 1;  // the long-arm kernels size their staging per batch
+  if (g > b->d.n_chains) g = b->d.n_chains;
+  return g < 1 ? 1 : g;
+}
 
 extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_iter, int32_t burn,
                                int32_t thin, int32_t do_psm, int32_t do_pred) {
@@ -1306,71 +1406,102 @@ extern "C" int tppmx_batch_run(tppmx_batch *b, uint64_t seed, int32_t iter0, int
   CK(ctx, cudaSetDevice(ctx->device));
   b->last_handovers = 0;
   int launches = 0;
+  // the chain groups: group 0 is the batch itself when there is only one
+  const int G = run_groups(b);
+  b->last_groups = G;
+  std::vector<tppmx_batch> views;
+  std::vector<tppmx_batch *> grp;
+  if (G > 1) {
+    while ((int)ctx->lanes.size() < G) {
+      tppmx_ctx *l = ctx_new(ctx->device);
+      if (!l) return fail(ctx, TPPMX_ERR_CUDA, "chain-group streams");
+      ctx->lanes.push_back(l);
+    }
+    views.resize(G);
+    for (int g = 0; g < G; g++) {
+      const int c0 = (int)((long long)d.n_chains * g / G), c1 = (int)((long long)d.n_chains * (g + 1) / G);
+      batch_view(b, &views[g], ctx->lanes[g], g, c0, c1 - c0);
+      ctx->lanes[g]->side_pending = false;
+      ctx->lanes[g]->hs_pending = false;
+      grp.push_back(&views[g]);
+    }
+  } else {
+    ctx->side_pending = false;
+    grp.push_back(b);
+  }
   CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
-  // Saved iterations: the co-clustering counts only need the partition (ready after the sweep) and
-  // the predictive step only needs what the update kernel writes, so they run on the side stream
-  // beside the update kernel / the JJ-ss gamma draws; the next sweep waits for them.
-  bool side_pending = false;
+  if (G > 1) {  // the groups start behind whatever the batch's own stream still holds
+    CK(ctx, cudaEventRecord(ctx->ev_go, ctx->stream));
+    for (tppmx_batch *v : grp) CK(ctx, cudaStreamWaitEvent(v->ctx->stream, ctx->ev_go, 0));
+  }
   int interrupted_at = -1;
+  const bool trace = getenv("TPPMX_TRACE") != nullptr;
+  const auto t_host0 = std::chrono::steady_clock::now();
   // every error exit below leaves through this: nothing of the batch may still run on the side streams,
   // and hs_pending must not survive (get_state / update of a later call would not join it)
   struct SideGuard {
     tppmx_ctx *c;
+    std::vector<tppmx_batch *> *grp;
     bool armed = true;
     ~SideGuard() {
       if (!armed) return;
-      cudaStreamSynchronize(c->side);
-      cudaStreamSynchronize(c->hs);
-      c->hs_pending = false;
+      for (tppmx_batch *v : *grp) {
+        tppmx_ctx *l = v->ctx;
+        cudaStreamSynchronize(l->side);
+        cudaStreamSynchronize(l->hs);
+        cudaStreamSynchronize(l->stream);
+        l->hs_pending = false;
+        l->side_pending = false;
+        if (l != c && !l->err.empty()) c->err = l->err;
+      }
     }
-  } guard{ctx};
+  } guard{ctx, &grp};
   for (int l = iter0; l < iter0 + n_iter; l++) {
-    if (side_pending) {
-      CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-      side_pending = false;
-    }
     if (ctx->interrupt && l > iter0 && (l - iter0) % ctx->check_every == 0) {  // tppmx_set_interrupt_flag
-      RC(hs_join(ctx));
-      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      for (tppmx_batch *v : grp) {
+        RC(hs_join(v->ctx));
+        CK(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+      }
       if (*ctx->interrupt) {
         interrupted_at = l - 1;
         break;
       }
     }
-    RC(sweep_launch(b, seed, l, 1, false, &launches));
     const bool saved = (do_psm || do_pred) && (l > burn - 1) && ((l + 1) % thin == 0);  // :1060
-    if (!saved) {
-      RC(update_launch(b, seed, l, &launches, nullptr, true));
-      continue;
-    }
-    if (do_psm) {
-      CK(ctx, cudaEventRecord(ctx->ev_sweep, ctx->stream));
-      CK(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_sweep, 0));
-      RC(accumulate_launch(b, seed, l, 1, 0, &launches, ctx->side));
-    }
-    RC(update_launch(b, seed, l, &launches, do_pred ? ctx->ev_upd : nullptr, true));
-    if (do_pred) {
-      CK(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_upd, 0));
-      RC(accumulate_launch(b, seed, l, 0, 1, &launches, ctx->side));
-    }
-    CK(ctx, cudaEventRecord(ctx->ev_side, ctx->side));
-    side_pending = true;
+    for (tppmx_batch *v : grp) RC(run_iteration(v, seed, l, saved, do_psm, do_pred, &launches));
   }
-  if (side_pending) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-  RC(hs_join(ctx));
+  for (tppmx_batch *v : grp) {  // every group's main stream rejoins its side streams, the batch's stream the groups
+    tppmx_ctx *lc = v->ctx;
+    if (lc->side_pending) {
+      CK(lc, cudaStreamWaitEvent(lc->stream, lc->ev_side, 0));
+      lc->side_pending = false;
+    }
+    RC(hs_join(lc));
+    if (lc != ctx) {
+      CK(lc, cudaEventRecord(lc->ev_done, lc->stream));
+      CK(ctx, cudaStreamWaitEvent(ctx->stream, lc->ev_done, 0));
+    }
+  }
   if (interrupted_at >= 0) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    guard.armed = false;
     char buf[96];
     snprintf(buf, sizeof buf, "interrupted after iteration %d", interrupted_at);
     return fail(ctx, TPPMX_ERR_INTERRUPTED, buf);
   }
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
+  const auto t_host1 = std::chrono::steady_clock::now();
   CK(ctx, cudaStreamSynchronize(ctx->stream));
-  guard.armed = false;   // the main stream has joined both side streams
+  if (trace)
+    fprintf(stderr, "tppmx_batch_run: %d iterations, %d groups, %d launches: host issue %.3f ms, until done %.3f ms\n", n_iter, G,
+            launches, std::chrono::duration<double, std::milli>(t_host1 - t_host0).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
+  guard.armed = false;   // the main stream has joined every side stream
   float ms = 0;
   CK(ctx, cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   b->last_ms = ms;
   b->last_launches = launches;
+  if (G > 1) b->last_impl = views[0].last_impl;
   return check_status(b);
 }
 
@@ -1475,7 +1606,9 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
 // at 64; chains with more clusters are rare and handled by the block itself falling back is not
 // possible mid-kernel, hence the cap decides the kernel for the whole launch.
 static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc,
-                          cudaStream_t st) {
+                          cudaStream_t st, double *dsum, int *launches) {
+  int nl_local = 0;
+  if (!launches) launches = &nl_local;
   tppmx_ctx *ctx = b->ctx;
   if (!st) st = ctx->stream;
   const DevBatch &d = b->d;
@@ -1493,19 +1626,22 @@ static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, in
       // the rest through the staged one; each block decides for itself and the other exits at once
       int kmin = 0;
       if (d.P <= 16 && d.D <= 3 && d.Q <= TPPMX_MAXQ) {
-        const dim3 grid(n_chains_launch, d.T);
-        if (d.P <= 4) predict_reg_kernel<4><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
-        else if (d.P <= 8) predict_reg_kernel<8><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
-        else if (d.P <= 12) predict_reg_kernel<12><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
-        else predict_reg_kernel<16><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
+        const dim3 grid((unsigned)n_chains_launch * d.T);
+        if (d.P <= 4) predict_reg_kernel<4><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
+        else if (d.P <= 8) predict_reg_kernel<8><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
+        else if (d.P <= 12) predict_reg_kernel<12><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
+        else predict_reg_kernel<16><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
         kmin = TPPMX_PRED_KR + 1;
+        (*launches)++;
       }
-      predict_fast_kernel<<<dim3(n_chains_launch, d.T), nth, smem, st>>>(d, seed, iter, KP, kmin, dpi, dy, dc);
+      predict_fast_kernel<<<dim3((unsigned)n_chains_launch * d.T), nth, smem, st>>>(d, seed, iter, KP, kmin, dpi, dy, dc, dsum);
+      (*launches)++;
       CK(ctx, cudaGetLastError());
       return TPPMX_OK;
     }
   }
-  predict_kernel<<<dim3(n_chains_launch, d.T), nth, 0, st>>>(d, seed, iter, dpi, dy, dc);
+  predict_kernel<<<dim3((unsigned)n_chains_launch * d.T), nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
+  (*launches)++;
   CK(ctx, cudaGetLastError());
   return TPPMX_OK;
 }
@@ -1535,9 +1671,9 @@ static int accumulate_launch(tppmx_batch *b, uint64_t seed, int32_t iter, int do
     (*launches)++;
   }
   if (do_pred) {
-    RC(predict_launch(b, d.n_chains, seed, iter, b->pred_pi, nullptr, nullptr, st));
-    pi_accumulate_kernel<<<d.n_chains, 256, 0, st>>>(d, b->pred_pi, b->pi_sum);
-    (*launches) += 2;
+    // the predictive kernels add each probability to its replicate dataset's sum themselves (no per-chain cube,
+    // no outcome draw: nothing reads ypred here)
+    RC(predict_launch(b, d.n_chains, seed, iter, nullptr, nullptr, nullptr, st, b->pi_sum, launches));
   }
   if (do_psm || do_pred) {
     count_saves_kernel<<<(d.n_chains + 255) / 256, 256, 0, st>>>(d, b->psm_n, b->pi_n, do_psm, do_pred);

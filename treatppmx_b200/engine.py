@@ -101,7 +101,7 @@ class Batch:
         il = np.asarray(init_labels, dtype=np.int32)
         if il.ndim == 2:
             il = np.broadcast_to(il, (nd, T, nt))
-        il = np.ascontiguousarray(np.stack([np.asfortranarray(a).ravel(order="F") for a in il]))
+        il = np.ascontiguousarray(il.transpose(0, 2, 1)).reshape(nd, T * nt)   # each dataset's T x ntmax, column-major
         ic = np.asarray(init_nclu, dtype=np.int32)
         if ic.ndim == 1:
             ic = np.broadcast_to(ic, (nd, T))
@@ -163,6 +163,16 @@ class Batch:
             self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 3, staged_clusters))
         if big_threads:
             self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 4, big_threads))
+
+    def set_chain_groups(self, groups: int = 0):
+        """run(): split the chains into `groups` contiguous groups iterating on their own streams (0 = automatic);
+        results do not depend on it (TPPMX_OPT_CHAIN_GROUPS)"""
+        self.ctx.check(self.ctx.L.tppmx_batch_set_option(self.h, 5, groups))
+
+    def last_chain_groups(self) -> int:
+        a = C.c_int32(0)
+        self.ctx.check(self.ctx.L.tppmx_batch_get_info(self.h, 3, C.byref(a)))
+        return a.value
 
     def last_sweep_info(self):
         """(kernel used by the last sweep: 'generic'|'fast', units handed over to generic)"""
