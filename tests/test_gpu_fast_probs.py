@@ -63,11 +63,13 @@ CASES = {
     "calib2_sqrt": lambda: build_case("calib2_sqrt", n_datasets=2),
     "dp_T3": lambda: build_case("dp_T3", n_datasets=2),
     "Q3_D3": lambda: build_case("Q3_D3", n_datasets=2),
+    # calibration 1: normalised similarities, their own instantiation (16 | 32 lanes per unit)
+    "calib1": lambda: build_case("calib1", n_datasets=2),
+    "calib1_dp_T3": lambda: build_case("calib1_dp_T3", n_datasets=2),
 }
 
 
-@pytest.mark.parametrize("lpu", [8, 16, 32])
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name,lpu", [(n, l) for n in CASES for l in (8, 16, 32) if not (n.startswith("calib1") and l == 8)])
 def test_fast_kernel_step_probabilities(ctx, name, lpu):
     from treatppmx_b200.engine import Batch
     model, dims, shared, dsets, labels, nclu, betas = CASES[name]()

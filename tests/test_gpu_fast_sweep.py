@@ -34,8 +34,12 @@ def _assert_same(g, o, dims, what=""):
             np.testing.assert_allclose(gv[k], ov[k], rtol=1e-12, atol=1e-13, err_msg=f"{what} {k}")
 
 
-@pytest.mark.parametrize("lpu", [8, 16, 32])
-@pytest.mark.parametrize("name", FAST_CASES)
+# calibration 1 (similarities normalised over the clusters, src/dm_ppmx_ct.cpp:717-788) has its own instantiation
+# of the fast kernel, for 16 | 32 lanes per unit
+CAL1_CASES = [("calib1", 16), ("calib1", 32), ("calib1_dp_T3", 16), ("calib1_dp_T3", 32)]
+
+
+@pytest.mark.parametrize("name,lpu", [(n, l) for n in FAST_CASES for l in (8, 16, 32)] + CAL1_CASES)
 def test_fast_lockstep_with_oracle(ctx, name, lpu):
     from treatppmx_b200.engine import Batch
     model, dims, shared, dsets, labels, nclu, betas = build_case(name, n_datasets=2)
@@ -119,6 +123,27 @@ def test_small_kcap_capacity_error_and_handover(ctx):
     with pytest.raises(_lib.TppmxError) as ei:
         batch.sweep(1, 0, 200)
     assert ei.value.code == 3
+
+
+def test_calibration1_handover_beyond_the_lanes(ctx):
+    """Calibration 1 normalises over all K + CC candidates in one pass of the unit's lanes, so its staged capacity
+    is lanes - CC; a partition driven beyond that hands over to the generic kernel, exactly."""
+    from treatppmx_b200.engine import Batch
+    model, dims, shared, dsets, labels, nclu, betas = build_case("calib1_dp_T3")
+    labels, nclu = datagen.initial_partition(dsets[0].treat, dims.T, dims.ntmax, nclu_init=15)   # starts beyond 16 - CC
+    batch = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0, 0, 0])
+    batch.set_sweep_impl("fast", 16)
+    batch.init(5, labels, nclu, betas[0])
+    pb = ob.Problem(model, dims, shared, dsets[0])
+    sts = [pb.init_state(5, c, labels, nclu, betas[0]) for c in range(3)]
+    hand = 0
+    for l in range(6):
+        batch.sweep(5, l, 1)
+        hand += batch.last_sweep_info()[1]
+        for c in range(3):
+            pb.sweep(sts[c], 5, c, l, 1)
+            _assert_same(batch.get_state(c), sts[c], dims, f"calib1 hand-over chain {c} sweep {l}")
+    assert hand > 0
 
 
 def test_fast_rejected_for_ineligible_model(ctx):

@@ -256,7 +256,12 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
 #define TPPMX_FAST_MINB 12
 #endif
 // PC: compile-time number of covariates (0: run-time b.P)
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0>
+// CAL1: calibration == 1 (src/dm_ppmx_ct.cpp:717-788): the similarities enter the weight normalised over the
+//   clusters -- gtilN over all K + CC candidates ("without" value of an occupied cluster, the singleton value of
+//   an auxiliary one), gtilY over the occupied ones -- so the step carries lgN_j and lgY_j themselves
+//   (lgN = P A0[n] - sum_p sumx2/(2 v2) + H[n] a, sim.cuh) and two more log-sum-exps per unit.  The host keeps
+//   K + CC <= LPU for this instantiation (staged capacity LPU - CC; larger partitions hand over).
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0, bool CAL1 = false>
 __global__ void __launch_bounds__(32, TPPMX_FAST_MINB)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -584,8 +589,14 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     }
     __syncwarp();
     // a, b of this lane's cluster (lanes >= K: the empty cluster, column 32) against the staged statistics
-    auto dots = [&](const double *xv, double &a, double &bb) {
+    auto dots = [&](const double *xv, double &a, double &bb, double &ss) {
       const double *sx = U.sumx + ((ul < K) ? ul : TPPMX_FAST_KSMAX);
+      if constexpr (CAL1) {  // sum_p sumx2_jp of this lane's cluster (the empty column gives 0)
+        const double *sq = U.sumx2 + ((ul < K) ? ul : TPPMX_FAST_KSMAX);
+        double q0 = 0.0;
+        for (int p = 0; p < P; p++) q0 += sq[p * KSTR];
+        ss = q0;
+      }
       double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
       if constexpr (PC > 0) {  // compile-time P: straight-line code the scheduler can interleave with the draw's chain
 #pragma unroll
@@ -622,11 +633,12 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     int myn = (ul < K) ? U.nj[ul] : 0;  // size of this lane's cluster (0: auxiliary / none)
     int nzi = U.nj[labcur - 1];         // size of the current patient's cluster
     int pend = 0;                       // label whose statistics still miss patient it-1 (0: none)
-    double a_c, b_c;
-    dots(U.xs, a_c, b_c);
+    double a_c, b_c, ss_c = 0.0;
+    dots(U.xs, a_c, b_c, ss_c);
     if (ul == labcur - 1) {  // patient 0 leaves its own cluster
       b_c = fma(-iv2, qx, b_c);
       a_c = fma(-iv2, fma(iv2, qx, 2.0 * b_c), a_c);
+      ss_c -= qx;
     }
 
     for (int it = 0; it < nt_w; it++) {
@@ -749,11 +761,12 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         __syncwarp();
         // the lanes of a unit whose partition changed re-form their a, b, n from the statistics
         lab_n = labp[it + 1];
-        double ar, br;
-        dots(xs, ar, br);
+        double ar, br, sr = 0.0;
+        dots(xs, ar, br, sr);
         if (single) {
           a_c = ar;
           b_c = br;
+          ss_c = sr;
           myn = (ul < K) ? U.nj[ul] : 0;
           t01 = tab2[2 * myn];
           t23 = tab2[2 * myn + 1];
@@ -774,10 +787,24 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       int newci;
       const double t1 = fma(iv2, qx, 2.0 * b_c);
       double w, wmax;
-      {
+      if constexpr (!CAL1) {
         const double tY = fma(iv2, t1, a_c);
         const double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a_c);
         const double wv = dV + lgn + simscale * d + likv;
+        w = act0 ? wv : -INFINITY;
+        wmax = unit_shift<LPU>(w, sub);
+      } else {
+        const bool occ = ul < K;
+        const double tY = fma(iv2, t1, a_c);
+        const double lgN = t23.y - hiv2 * ss_c + t01.y * a_c;                     // P A0[n] - ... + H[n] a
+        const double lgY = (t23.y + t01.x) - hiv2 * (ss_c + qx) + t23.x * tY;     // P A0[n+1] - ... + H[n+1] t_Y
+        const double gN = act0 ? (occ ? lgN : lgY) : -INFINITY;                   // :670-671 auxiliary: the singleton value
+        const double gY = occ ? lgY : -INFINITY;
+        const double mN = unit_shift<LPU>(gN, sub), mY = unit_shift<LPU>(gY, sub);
+        const double sN = unit_sum<LPU>(fast_exp(gN - mN)), sY = unit_sum<LPU>(fast_exp(gY - mY));
+        const double ltN = (gN - mN) - fast_log(sN);                              // log gtilN
+        const double ltY = (gY - mY) - fast_log(sY);                              // log gtilY (occupied)
+        const double wv = dV + lgn + likv + (occ ? ltY - ltN : ltN);
         w = act0 ? wv : -INFINITY;
         wmax = unit_shift<LPU>(w, sub);
       }
@@ -785,13 +812,14 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       //      draw; placed here so that the scheduler interleaves it with the exp / scan chain below.
       //      The next patient's own cluster is corrected for its removal.
       const int zn = (it + 1 < nt) ? lab_n - 1 : 0;
-      double a_n, b_n;
-      dots(xs_n, a_n, b_n);
+      double a_n, b_n, ss_n = 0.0;
+      dots(xs_n, a_n, b_n, ss_n);
       {
         const double bs = fma(-iv2, qx_n, b_n);
         const double as = fma(-iv2, fma(iv2, qx_n, 2.0 * bs), a_n);
         b_n = (ul == zn) ? bs : b_n;
         a_n = (ul == zn) ? as : a_n;
+        if constexpr (CAL1) ss_n = (ul == zn) ? ss_n - qx_n : ss_n;
       }
       const int nj_n = U.nj[zn];  // size of the next patient's cluster before this step's arrival
       {
@@ -811,7 +839,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
       }
       const bool multi = on && ntot > LPU;
-      if (__builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
+      if (!CAL1 && __builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
         double *prow = nullptr;
         if constexpr (PROBE) {
           const int pu = unit - fa.probe_unit0;
@@ -880,6 +908,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         myn += mine ? 1 : 0;
         b_n = mine ? bq : b_n;
         a_n = mine ? aq : a_n;
+        if constexpr (CAL1) ss_n = mine ? ss_n + qx : ss_n;
       }
       pend = on ? lab : 0;
       nzi = nj_n + ((on && lab - 1 == zn) ? 1 : 0);
@@ -895,6 +924,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       labcur = lab_n;
       a_c = a_n;
       b_c = b_n;
+      ss_c = ss_n;
       __syncwarp();
     }
     // ---- the statistics still miss the last patient of the arm
@@ -958,14 +988,14 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
 }
 
 // ---- launch: instantiation picked from the batch shape (one translation unit per LPU) ----------
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC>
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC, bool CAL1 = false>
 static cudaError_t fast_launch7(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
 }
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
@@ -973,6 +1003,13 @@ static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t sm
                                 int n_sweeps, cudaStream_t stream) {
   // the package's shape (genmech: 10 predictive covariates, D = 3 outcome categories, two units per warp) is
   // compiled with P as a constant: its dot products unroll into straight-line code
+  if (d.model.calibration == 1) {  // normalised similarities: instantiated for the package's case (D <= 3, short arms, 16 | 32 lanes)
+    if constexpr (LPU >= 16 && DR == 3 && !NOLIK && !BIG) {
+      if (fa.KS + d.CC > LPU) return cudaErrorInvalidConfiguration;
+      return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 0, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
+    }
+    return cudaErrorInvalidConfiguration;
+  }
   if constexpr (LPU == 16 && XR == 1 && DR == 3 && !NOLIK && !BIG)
     if (d.P == 10) return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 10>(d, fa, smem, seed, iter0, n_sweeps, stream);
   return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 0>(d, fa, smem, seed, iter0, n_sweeps, stream);

@@ -985,6 +985,7 @@ extern "C" int tppmx_batch_set_option(tppmx_batch *b, int32_t opt, int32_t value
   }
   if (opt == TPPMX_OPT_LANES_PER_UNIT && (value == 0 || value == 8 || value == 16 || value == 32)) {
     b->opt_lpu = value;
+    b->fast_ready = false;  // the staged capacity may depend on it (calibration 1)
     return TPPMX_OK;
   }
   if (opt == TPPMX_OPT_FAST_STAGED_CLUSTERS && value >= 0 && value <= TPPMX_BIG_KSMAX && !b->fast_ready) {
@@ -1015,7 +1016,8 @@ extern "C" int tppmx_batch_get_info(const tppmx_batch *b, int32_t what, int32_t 
 static bool fast_eligible(const tppmx_batch *b, int lpu) {
   const DevBatch &d = b->d;
   const tppmx_model &m = d.model;
-  return m.PPMx == 1 && m.consim == 1 && m.similarity == 1 && (m.calibration == 0 || m.calibration == 2) &&
+  if (m.calibration == 1 && (d.D > 3 || m.nolik || big_arms(d) || lpu < 16)) return false;  // instantiations of sweep_fast.cuh
+  return m.PPMx == 1 && m.consim == 1 && m.similarity == 1 && m.calibration >= 0 && m.calibration <= 2 &&
          d.ncat == 0 && m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
 }
 // arms too long for the small-arm kernel's shared-memory label / order / cohesion tables (thousands of
@@ -1055,6 +1057,7 @@ static int fast_reserve(tppmx_batch *b) {
       tg[(size_t)4 * n + 0] = (n == 0) ? dP * tab[1].A0 : dP * (tab[n + 1].A0 - tab[n].A0);
       tg[(size_t)4 * n + 1] = (n == 0) ? 0.0 : tab[n].H;
       tg[(size_t)4 * n + 2] = tab[n + 1].H;
+      tg[(size_t)4 * n + 3] = (n == 0) ? 0.0 : dP * tab[n].A0;  // calibration 1 scores lgN, lgY themselves
     }
     const double *tp = nullptr;
     RC(dev_upload(b, &tp, tg));
@@ -1075,6 +1078,8 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     } else {
       fa.KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
       if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
+      // calibration 1 normalises over all candidates in one pass of the unit's lanes: K + CC <= lanes
+      if (d.model.calibration == 1 && fa.KS > lpu - d.CC) fa.KS = lpu - d.CC;
     }
     fa.ntp = (d.ntmax + 3) & ~3;
     fa.ncol = fa.KS + d.CC;
