@@ -15,6 +15,7 @@ CASES = {
     "double_dipper": (dict(similarity=2), dict(T=2, n=60, P=6)),
     "nnig":          (dict(consim=2, cohesion=1), dict(T=2, n=60, P=5)),
     "nnig_dd":       (dict(consim=2, similarity=2), dict(T=2, n=50, P=4)),
+    "nnig_ngg_T3":   (dict(consim=2), dict(T=3)),
     "calib1":        (dict(calibration=1), dict(T=2, n=60, P=7)),
     "calib1_dp_T3":  (dict(calibration=1, cohesion=1, alpha=1.5), dict(T=3)),
     "calib2_sqrt":   (dict(calibration=2, coardegree=2), dict(T=2, n=60, P=7)),

@@ -66,10 +66,13 @@ CASES = {
     # calibration 1: normalised similarities, their own instantiation (16 | 32 lanes per unit)
     "calib1": lambda: build_case("calib1", n_datasets=2),
     "calib1_dp_T3": lambda: build_case("calib1_dp_T3", n_datasets=2),
+    # Normal-Normal-Inverse-Gamma similarity (consim = 2): its own instantiation too
+    "nnig": lambda: build_case("nnig", n_datasets=2),
+    "nnig_ngg_T3": lambda: build_case("nnig_ngg_T3", n_datasets=2),
 }
 
 
-@pytest.mark.parametrize("name,lpu", [(n, l) for n in CASES for l in (8, 16, 32) if not (n.startswith("calib1") and l == 8)])
+@pytest.mark.parametrize("name,lpu", [(n, l) for n in CASES for l in (8, 16, 32) if not (n.startswith(("calib1", "nnig")) and l == 8)])
 def test_fast_kernel_step_probabilities(ctx, name, lpu):
     from treatppmx_b200.engine import Batch
     model, dims, shared, dsets, labels, nclu, betas = CASES[name]()

@@ -37,6 +37,8 @@ def _assert_same(g, o, dims, what=""):
 # calibration 1 (similarities normalised over the clusters, src/dm_ppmx_ct.cpp:717-788) has its own instantiation
 # of the fast kernel, for 16 | 32 lanes per unit
 CAL1_CASES = [("calib1", 16), ("calib1", 32), ("calib1_dp_T3", 16), ("calib1_dp_T3", 32)]
+# so has the Normal-Normal-Inverse-Gamma similarity (consim = 2, src/utils_ct.cpp:427-459)
+CAL1_CASES += [("nnig", 16), ("nnig", 32), ("nnig_ngg_T3", 16), ("nnig_ngg_T3", 32)]
 
 
 @pytest.mark.parametrize("name,lpu", [(n, l) for n in FAST_CASES for l in (8, 16, 32)] + CAL1_CASES)
@@ -148,7 +150,7 @@ def test_calibration1_handover_beyond_the_lanes(ctx):
 
 def test_fast_rejected_for_ineligible_model(ctx):
     from treatppmx_b200.engine import Batch
-    model, dims, shared, dsets, labels, nclu, betas = build_case("nnig")
+    model, dims, shared, dsets, labels, nclu, betas = build_case("double_dipper")
     batch = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0])
     batch.set_sweep_impl("fast")
     batch.init(1, labels, nclu, betas[0])

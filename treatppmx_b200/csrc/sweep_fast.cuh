@@ -189,6 +189,32 @@ __device__ __forceinline__ double fast_lik_reg(const double *E, const double (&Z
   return w;
 }
 
+// ---- Normal-Normal-Inverse-Gamma similarity in the reference's own evaluation order (utils_ct.cpp:427-459;
+// oracle/ppmx_oracle.c:oracle_gsimconNNIG is compiled with -ffp-contract=off): explicit rounded operations, no
+// contraction, and every division by a quantity of n alone done as a correctly rounded quotient from its
+// tabulated reciprocal (q = a r; q += (a - q d) r -- Markstein's correction, exact with RN(1/d)).
+__device__ __forceinline__ double div_by_tab(double a, double d, double r) {
+  const double q = __dmul_rn(a, r);
+  return fma(fma(-q, d, a), r, q);
+}
+// gsimconNNIG(m0, k0, nu0, s20, S, SS, n, DD = 0, log) with row r of the table over n
+__device__ __forceinline__ double gsim_nnig_row(const double *__restrict__ r, double S, double SS, double m0, double k0m0,
+                                                double b0) {
+  const double mu = 10.0;
+  const double dn = r[1], kn = r[3], rkn = r[4];
+  const double xbar = __dmul_rn(S, r[2]);
+  const double nx = __dmul_rn(dn, xbar);
+  const double m0s = div_by_tab(__dadd_rn(k0m0, nx), kn, rkn);
+  const double dx = __dsub_rn(xbar, m0);
+  const double b0s = __dadd_rn(__dadd_rn(b0, __dmul_rn(0.5, __dsub_rn(SS, __dmul_rn(nx, xbar)))),
+                               div_by_tab(__dmul_rn(__dmul_rn(r[5], dx), dx), kn, rkn));
+  const double ld1 = __dsub_rn(r[0], __dmul_rn(5.0, __dadd_rn(__dsub_rn(SS, __dmul_rn(__dmul_rn(2.0, S), mu)), r[12])));
+  const double t = div_by_tab(__dsub_rn(mu, m0s), r[6], r[7]);
+  const double dnl = -(__dadd_rn(__dadd_rn(TPPMX_LN_SQRT_2PI, __dmul_rn(__dmul_rn(0.5, t), t)), r[8]));
+  const double ig = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(r[9], fast_log(b0s)), r[10]), r[11]), div_by_tab(b0s, 0.1, 10.0));
+  return __dsub_rn(__dadd_rn(ld1, r[13]), __dadd_rn(dnl, ig));
+}
+
 // cold path: a unit of the warp has more than LPU candidate clusters (`mine`).  Scores in
 // chunks through U.wsc; returns newci for the units with `mine`.
 template <int LPU>
@@ -261,7 +287,12 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
 //   an auxiliary one), gtilY over the occupied ones -- so the step carries lgN_j and lgY_j themselves
 //   (lgN = P A0[n] - sum_p sumx2/(2 v2) + H[n] a, sim.cuh) and two more log-sum-exps per unit.  The host keeps
 //   K + CC <= LPU for this instantiation (staged capacity LPU - CC; larger partitions hand over).
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0, bool CAL1 = false>
+// NNIG: consim == 2, the Normal-Normal-Inverse-Gamma similarity (src/utils_ct.cpp:427-459): per covariate the
+//   score is nonlinear in (sumx, sumx2), so there is no dot-product form to pipeline; each step evaluates
+//   gsimconNNIG for its lane's cluster with and without the patient straight from the staged statistics, in the
+//   function's own operation order for the large cancelling terms, everything that depends on n only from an
+//   eight-entry table row, and the P logarithms a0s log(b0s) folded into one log of a product per lane.
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0, bool CAL1 = false, bool NNIG = false>
 __global__ void __launch_bounds__(32, TPPMX_FAST_MINB)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -279,7 +310,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   // ---- per-CTA table over n (Normal-Normal log terms, utils_ct.cpp:389-400 via sim.cuh NNRow):
   //      entry n = (dA, HN, HY, -), built on the host (fa.tabg); staged in shared memory unless BIG
   const double2 *tab2;
-  if constexpr (BIG) {
+  if constexpr (BIG || NNIG) {
     tab2 = reinterpret_cast<const double2 *>(fa.tabg);
   } else {
     double2 *ts = reinterpret_cast<double2 *>(smem_raw);
@@ -677,7 +708,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       // rows of the tables over n for this lane's cluster after the removal (issued before the statistics'
       // read-modify-writes; re-read below if the partition changes)
       const int n_sc = myn - ((on && !single && ul == zi) ? 1 : 0);
-      double2 t01 = tab2[2 * n_sc], t23 = tab2[2 * n_sc + 1];  // (dA, HN), (HY, -)
+      double2 t01 = tab2[2 * n_sc], t23 = tab2[2 * n_sc + 1];  // (dA, HN), (HY, -); unused by the NNIG instantiation
       double lgn = lognp[n_sc];
       {
         const bool add = pend != 0;        // cluster pend-1 receives patient it-1
@@ -787,7 +818,23 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       int newci;
       const double t1 = fma(iv2, qx, 2.0 * b_c);
       double w, wmax;
-      if constexpr (!CAL1) {
+      if constexpr (NNIG) {
+        // rows myn ("without") and myn + 1 ("with") of the table over n (tppmx.cu:fast_reserve)
+        const bool occ = ul < K;
+        const double *rN = fa.tabg + (size_t)TPPMX_NNIG_ROW * myn, *rY = rN + TPPMX_NNIG_ROW;
+        const double *sx = U.sumx + (occ ? ul : TPPMX_FAST_KSMAX), *sq = U.sumx2 + (occ ? ul : TPPMX_FAST_KSMAX);
+        const double k0m0 = __dmul_rn(s.k0, s.m0), b0 = __dmul_rn(__dmul_rn(0.5, s.nu0), s.s20);
+        double lgN = 0.0, lgY = 0.0;
+        for (int p = 0; p < P; p++) {
+          const double S = sx[p * KSTR], SS = sq[p * KSTR], xv = xs[p];
+          lgN = __dadd_rn(lgN, gsim_nnig_row(rN, S, SS, s.m0, k0m0, b0));
+          lgY = __dadd_rn(lgY, gsim_nnig_row(rY, __dadd_rn(S, xv), __dadd_rn(SS, __dmul_rn(xv, xv)), s.m0, k0m0, b0));
+        }
+        if (!occ) lgN = 0.0;
+        const double wv = dV + lgn + simscale * (lgY - lgN) + likv;
+        w = act0 ? wv : -INFINITY;
+        wmax = unit_shift<LPU>(w, sub);
+      } else if constexpr (!CAL1) {
         const double tY = fma(iv2, t1, a_c);
         const double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a_c);
         const double wv = dV + lgn + simscale * d + likv;
@@ -839,7 +886,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
       }
       const bool multi = on && ntot > LPU;
-      if (!CAL1 && __builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
+      if (!CAL1 && !NNIG && __builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
         double *prow = nullptr;
         if constexpr (PROBE) {
           const int pu = unit - fa.probe_unit0;
@@ -988,14 +1035,14 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
 }
 
 // ---- launch: instantiation picked from the batch shape (one translation unit per LPU) ----------
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC, bool CAL1 = false>
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC, bool CAL1 = false, bool NNIG = false>
 static cudaError_t fast_launch7(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
 }
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
@@ -1003,6 +1050,13 @@ static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t sm
                                 int n_sweeps, cudaStream_t stream) {
   // the package's shape (genmech: 10 predictive covariates, D = 3 outcome categories, two units per warp) is
   // compiled with P as a constant: its dot products unroll into straight-line code
+  if (d.model.consim == 2) {  // NNIG similarity: the same restrictions as calibration 1 (tppmx.cu:fast_eligible)
+    if constexpr (LPU >= 16 && DR == 3 && !NOLIK && !BIG) {
+      if (fa.KS + d.CC > LPU || d.model.calibration == 1) return cudaErrorInvalidConfiguration;
+      return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 0, false, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
+    }
+    return cudaErrorInvalidConfiguration;
+  }
   if (d.model.calibration == 1) {  // normalised similarities: instantiated for the package's case (D <= 3, short arms, 16 | 32 lanes)
     if constexpr (LPU >= 16 && DR == 3 && !NOLIK && !BIG) {
       if (fa.KS + d.CC > LPU) return cudaErrorInvalidConfiguration;

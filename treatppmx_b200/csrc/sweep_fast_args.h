@@ -47,9 +47,12 @@ __host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC
   size_t in = (size_t)KS + 2 * (KS + CC) + (big ? 0 : 2 * (ntp + 1)) + 1;
   return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t fast_tab_bytes(int ntmax, int big) {
-  return big ? 16 : (size_t)4 * (ntmax + 2) * 8;  // (dA, HN, HY, -) per n
+// per-n table (dA, HN, HY, P A0) of the Normal-Normal similarity, staged in shared memory for short arms.  The
+// Normal-Normal-Inverse-Gamma similarity (consim == 2) reads its 16-entry rows from global memory (L1).
+__host__ __device__ inline size_t fast_tab_bytes(int ntmax, int big, int nnig = 0) {
+  return (big || nnig) ? 16 : (size_t)4 * (ntmax + 2) * 8;
 }
+#define TPPMX_NNIG_ROW 16  // doubles per n of the NNIG table (tppmx.cu:fast_reserve, sweep_fast.cuh)
 
 // Launch for LPU lanes per (chain, arm) on `stream`; picks the instantiation from the batch shape
 // (P -> XR, D -> DR, model.nolik, fa.big).  fa.big requires LPU = 32.

@@ -1016,15 +1016,19 @@ extern "C" int tppmx_batch_get_info(const tppmx_batch *b, int32_t what, int32_t 
 static bool fast_eligible(const tppmx_batch *b, int lpu) {
   const DevBatch &d = b->d;
   const tppmx_model &m = d.model;
-  if (m.calibration == 1 && (d.D > 3 || m.nolik || big_arms(d) || lpu < 16)) return false;  // instantiations of sweep_fast.cuh
-  return m.PPMx == 1 && m.consim == 1 && m.similarity == 1 && m.calibration >= 0 && m.calibration <= 2 &&
+  // calibration 1 and the NNIG similarity have their own instantiations of sweep_fast.cuh: the package's case only
+  // (D <= 3, short arms, 16 | 32 lanes per unit)
+  const bool special = m.calibration == 1 || m.consim == 2;
+  if (special && (d.D > 3 || m.nolik || big_arms(d) || lpu < 16)) return false;
+  if (m.consim == 2 && (m.calibration == 1 || d.P > 32)) return false;
+  return m.PPMx == 1 && (m.consim == 1 || m.consim == 2) && m.similarity == 1 && m.calibration >= 0 && m.calibration <= 2 &&
          d.ncat == 0 && m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
 }
 // arms too long for the small-arm kernel's shared-memory label / order / cohesion tables (thousands of
 // patients, BASELINE config 4) run the long-arm kernel (sweep_big.cuh): one CTA per (chain, arm)
 static bool big_arms(const DevBatch &d) {
   const size_t ks = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX, ntp = (d.ntmax + 3) & ~3;
-  return fast_tab_bytes(d.ntmax, 0) + 2 * fast_unit_bytes(d.P, (int)ks, (int)ntp, d.CC, d.D, 0) > 48 * 1024;
+  return fast_tab_bytes(d.ntmax, 0, d.model.consim == 2) + 2 * fast_unit_bytes(d.P, (int)ks, (int)ntp, d.CC, d.D, 0) > 48 * 1024;
 }
 // largest staged cluster capacity of the long-arm kernel: min(kcap, 256), lowered until one CTA fits an SM
 static int big_ks(const DevBatch &d, int opt_ks) {
@@ -1049,15 +1053,56 @@ static int fast_reserve(tppmx_batch *b) {
   fa.lik_unit_stride = (KS + d.CC) * ntp;
   RC(dev_alloc(b, &fa.logng, units * (ntp + 1)));
   RC(dev_alloc(b, &fa.patpad, units * (ntp + 1)));
-  {  // the three tables over n of sweep_fast.cuh, for arms too long to keep them in shared memory
-    std::vector<NNRow> tab = build_nn_tab(d.model, d.ntmax);
-    std::vector<double> tg((size_t)4 * (d.ntmax + 2), 0.0);
+  {  // the tables over n of sweep_fast.cuh (also read from global memory by the long-arm kernels)
+    std::vector<double> tg;
     const double dP = (double)d.P;
-    for (int n = 0; n <= d.ntmax; n++) {
-      tg[(size_t)4 * n + 0] = (n == 0) ? dP * tab[1].A0 : dP * (tab[n + 1].A0 - tab[n].A0);
-      tg[(size_t)4 * n + 1] = (n == 0) ? 0.0 : tab[n].H;
-      tg[(size_t)4 * n + 2] = tab[n + 1].H;
-      tg[(size_t)4 * n + 3] = (n == 0) ? 0.0 : dP * tab[n].A0;  // calibration 1 scores lgN, lgY themselves
+    if (d.model.consim == 2) {
+      // Normal-Normal-Inverse-Gamma similarity (utils_ct.cpp:427-459 with dN_IG :181-200, dinvgamma :161-176):
+      // everything of gsimconNNIG(sumx, sumx2, n) that depends on n only, formed with the reference's own
+      // operations (the kernel mirrors its evaluation order: the function cancels terms of order 500 n, so
+      // any other association differs from it by ~1e-10 on a log-weight).  Row n (TPPMX_NNIG_ROW doubles):
+      //   0 An = (-0.5 n) log(2 pi v)   1 n   2 1/n   3 k0 + n   4 RN(1/(k0+n))   5 (0.5 n) k0   6 sd = sqrt(v/(k0+n))
+      //   7 RN(1/sd)   8 log sd   9 a0s = nu0/2 + 0.5 n   10 lgamma(a0s)   11 (a0s + 1) log v   12 (n mu) mu
+      // with the function's own evaluation point mu = 10, v = 0.1 (:431-432).
+      //   13 ld2 = dN_IG(mu, v; m0, k0, nu0/2, nu0 s20/2) (:451, the same in every row)
+      const double mu = 10.0, v = 0.1, m0 = d.model.similparam[0], s20 = d.model.similparam[1], k0 = d.model.similparam[3],
+                   nu0 = d.model.similparam[4];
+      const double a0 = 0.5 * nu0, b0 = 0.5 * nu0 * s20;
+      double ld2;
+      {
+        const double sd0 = sqrt(v / k0), t = (mu - m0) / sd0;
+        const double dnl = -(0.918938533204672741780329736406 + 0.5 * t * t + log(sd0));
+        const double ig = a0 * log(b0) - lgamma(a0) - (a0 + 1) * log(v) - (b0 / v);
+        ld2 = dnl + ig;
+      }
+      tg.assign((size_t)TPPMX_NNIG_ROW * (d.ntmax + 2), 0.0);
+      for (int n = 0; n <= d.ntmax + 1; n++) {
+        const double a0s = a0 + 0.5 * n, kn = k0 + n, sd = sqrt(v / kn);
+        double *r = &tg[(size_t)TPPMX_NNIG_ROW * n];
+        r[0] = -0.5 * n * log(2 * M_PI * v);
+        r[1] = (double)n;
+        r[2] = n > 0 ? 1 / (double)n : 0.0;
+        r[3] = kn;
+        r[4] = 1.0 / kn;
+        r[5] = 0.5 * n * k0;
+        r[6] = sd;
+        r[7] = 1.0 / sd;
+        r[8] = log(sd);
+        r[9] = a0s;
+        r[10] = lgamma(a0s);
+        r[11] = (a0s + 1) * log(v);
+        r[12] = n * mu * mu;
+        r[13] = ld2;
+      }
+    } else {
+      std::vector<NNRow> tab = build_nn_tab(d.model, d.ntmax);
+      tg.assign((size_t)4 * (d.ntmax + 2), 0.0);
+      for (int n = 0; n <= d.ntmax; n++) {
+        tg[(size_t)4 * n + 0] = (n == 0) ? dP * tab[1].A0 : dP * (tab[n + 1].A0 - tab[n].A0);
+        tg[(size_t)4 * n + 1] = (n == 0) ? 0.0 : tab[n].H;
+        tg[(size_t)4 * n + 2] = tab[n + 1].H;
+        tg[(size_t)4 * n + 3] = (n == 0) ? 0.0 : dP * tab[n].A0;  // calibration 1 scores lgN, lgY themselves
+      }
     }
     const double *tp = nullptr;
     RC(dev_upload(b, &tp, tg));
@@ -1078,14 +1123,15 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
     } else {
       fa.KS = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX;
       if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
-      // calibration 1 normalises over all candidates in one pass of the unit's lanes: K + CC <= lanes
-      if (d.model.calibration == 1 && fa.KS > lpu - d.CC) fa.KS = lpu - d.CC;
+      // calibration 1 normalises over all candidates in one pass of the unit's lanes (and the NNIG instantiation
+      // has no chunked scoring path): K + CC <= lanes
+      if ((d.model.calibration == 1 || d.model.consim == 2) && fa.KS > lpu - d.CC) fa.KS = lpu - d.CC;
     }
     fa.ntp = (d.ntmax + 3) & ~3;
     fa.ncol = fa.KS + d.CC;
     fa.n_units = d.n_chains * d.T;
     fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D, 0);
-    fa.tab_bytes = (int)fast_tab_bytes(d.ntmax, 0);
+    fa.tab_bytes = (int)fast_tab_bytes(d.ntmax, 0, d.model.consim == 2);
     b->fast_ready = true;
   }
   if (fa.big) {
