@@ -391,29 +391,38 @@ def extra_config_legs(ctx, args) -> dict:
     # ---- config 4 and config 5 shape
     for name, kw, mode in (
             ("config4", dict(datasets=1, chains_per_dataset=1024, n=20000, npred=0, P=50, Q=2, T=3, cohesion=2, kcap=128, mixture=8), "sweep"),
+            # the same shape with a tighter within-cluster variance (similparam v = 0.42): ~45 clusters per arm, beyond
+            # the one-warp kernel's 32 -- every unit runs the CTA-per-unit long-arm kernel, no hand-over to the generic one
+            ("config4_k45", dict(datasets=1, chains_per_dataset=1024, n=20000, npred=0, P=50, Q=2, T=3, cohesion=2, kcap=256, mixture=8, v=0.42), "sweep"),
             ("config5_shape_1gpu", dict(datasets=256, chains_per_dataset=4, n=152, npred=10000, P=10, Q=2, T=3, cohesion=2, kcap=0, mixture=0), "full")):
         try:
+            kw = dict(kw)
+            v_sim = kw.pop("v", None)
             a = _ap.Namespace(**kw)
             t0 = time.perf_counter()
             w = build_workload(a, 0)
+            if v_sim is not None:
+                w["model"].similparam[2] = v_sim
             b = Batch(ctx, w["model"], w["dims"], w["shared"], w["dsets"], chain_dataset=w["chain_ds"], chain_id=w["chain_id"])
             b.init(7, w["labels"], w["nclu"], w["beta0"])
             setup_s = time.perf_counter() - t0
             nch, d = int(w["chain_ds"].size), w["dims"]
             if mode == "sweep":
                 b.run(7, 0, 2)              # two full iterations: leaves the initial partition behind
-                b.sweep(7, 2, 1)
+                nwarm = 1 if v_sim is None else 4
+                b.sweep(7, 2, nwarm)
                 ms = []
                 for r in range(3):
-                    b.sweep(7, 3 + r, 1)
+                    b.sweep(7, 2 + nwarm + r, 1)
                     ms.append(b.last_timing()[0])
                 impl, hand = b.last_sweep_info()
                 _, ncl = b.get_partitions()
                 med = float(np.median(ms))
                 Kb = float(ncl.mean())
                 B = algorithmic_bytes_per_realloc(d, w["model"].CC, Kb)
-                out[name] = {"workload": f"n={d.nobs} T={d.T} P={d.P} NGG, compact V table, kcap={d.kcap}, {nch} chains on one dataset; "
-                                         "3 timed launches of one sweep after 2 full iterations + 1 sweep",
+                out[name] = {"workload": f"n={d.nobs} T={d.T} P={d.P} NGG, compact V table, kcap={d.kcap}, {nch} chains on one dataset"
+                                         + (f", similparam v={v_sim}" if v_sim is not None else "")
+                                         + f"; 3 timed launches of one sweep after 2 full iterations + {nwarm} sweep(s)",
                              "reallocations_per_sec": nch * d.nobs / (med * 1e-3), "ms_per_sweep": med,
                              "mean_clusters_per_arm": Kb, "max_clusters_per_arm": int(ncl.max()),
                              "sweep_kernel": impl, "handovers_last_sweep": hand, "bytes_per_reallocation": B,
@@ -434,6 +443,29 @@ def extra_config_legs(ctx, args) -> dict:
             b.close()
         except Exception as e:
             out[name] = {"error": repr(e)}
+    # ---- production switches beside the defaults: calibration 1 and the NNIG similarity have their own
+    #      instantiations of the fast sweep kernel; the generic kernel is timed beside them
+    try:
+        from cases import build_case
+        sw = {}
+        for name in ("calib1_dp_T3", "nnig_ngg_T3"):
+            model, dims, shared, dsets, labels, nclu, betas = build_case(name, n_datasets=256)
+            cds = np.repeat(np.arange(256, dtype=np.int32), 4)
+            b = Batch(ctx, model, dims, shared, dsets, chain_dataset=cds)
+            b.init(1, labels, nclu, betas[0])
+            b.sweep(1, 0, 10)
+            b.sweep(1, 10, 10)
+            rec = {"workload": f"n={dims.nobs} T={dims.T} P={dims.P}, 1024 chains over 256 replicate datasets, 10 sweeps timed",
+                   "sweep_kernel": b.last_sweep_info()[0],
+                   "reallocations_per_sec": len(cds) * dims.nobs * 10 / (b.last_timing()[0] * 1e-3)}
+            b.set_sweep_impl("generic")
+            b.sweep(1, 20, 10)
+            rec["generic_kernel_reallocations_per_sec"] = len(cds) * dims.nobs * 10 / (b.last_timing()[0] * 1e-3)
+            sw[name] = rec
+            b.close()
+        out["nondefault_switches"] = sw
+    except Exception as e:
+        out["nondefault_switches"] = {"error": repr(e)}
     return out
 
 

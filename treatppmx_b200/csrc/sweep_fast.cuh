@@ -1064,7 +1064,7 @@ static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t sm
     }
     return cudaErrorInvalidConfiguration;
   }
-  if constexpr (LPU == 16 && XR == 1 && DR == 3 && !NOLIK && !BIG)
+  if constexpr ((LPU == 16 || LPU == 32) && XR == 1 && DR == 3 && !NOLIK && !BIG)
     if (d.P == 10) return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 10>(d, fa, smem, seed, iter0, n_sweeps, stream);
   return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 0>(d, fa, smem, seed, iter0, n_sweeps, stream);
 }

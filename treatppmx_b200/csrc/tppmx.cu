@@ -1176,7 +1176,9 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   int lpu = b->opt_lpu;
   const bool big = big_arms(b->d);
   if (big) lpu = 32;  // long arms: one CTA per (chain, arm), P <= 128 covariate owners
-  else if (!lpu) lpu = 16;
+  // few units (one ppmxct() call = one chain): latency, not residency, is what counts -- one unit per warp puts
+  // twice the lanes on the sweep's parallel pre-pass
+  else if (!lpu) lpu = ((long long)b->d.n_chains * b->d.T <= 296) ? 32 : 16;
   size_t smem = 0;
   bool use_fast = b->opt_impl != 1 && fast_eligible(b, lpu) && b->fa.lik;
   if (use_fast) {
@@ -1954,12 +1956,19 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
     // the horseshoe update (a ~100 us serial chain that nothing reads before the NEXT iteration's beta step and
     // no output saves) runs on the context's third stream beside the gamma draws, the in-sample fit and the
     // predictive step: for ONE chain it was half of the iteration's latency
-    if (!rc) rc = update_launch(B, a->seed, l, &launches, nullptr, true);
+    const bool saved = (l > (a->burn - 1)) && ((l + 1) % a->thin == 0) && ll < nout;  // :1060
+    const bool pred = saved && npred > 0;
+    if (!rc) rc = update_launch(B, a->seed, l, &launches, pred ? ctx->ev_upd : nullptr, true);
     if (rc) break;
+    if (pred) {  // the predictive step only reads what the update kernel left: it runs on the side stream beside the gamma draws
+      if (cudaStreamWaitEvent(ctx->side, ctx->ev_upd, 0) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: stream wait");
+      if (!rc) rc = predict_launch(B, 1, a->seed, l, B->pred_pi, B->pred_y, B->pred_c, ctx->side);
+      if (!rc && (cudaEventRecord(ctx->ev_side, ctx->side) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0) != cudaSuccess))
+        rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: stream wait");
+      if (rc) break;
+    }
     sumtotclu_kernel<<<1, 32, 0, ctx->stream>>>(d, tr);
-    if ((l > (a->burn - 1)) && ((l + 1) % a->thin == 0) && ll < nout) {  // :1060
-      if (npred > 0)
-        rc = predict_launch(B, 1, a->seed, l, B->pred_pi, B->pred_y, B->pred_c);
+    if (saved) {
       insample_save_kernel<<<1, 256, 0, ctx->stream>>>(d, tr, a->seed, l, ll, B->pred_pi, B->pred_y, B->pred_c);
       ll++;
     }
