@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -4
-python scripts/single_chain.py 2>&1 | tail -3
+python scripts/e2e_pipeline.py 12 1 2 3 4 6
+python scripts/e2e_phases.py | tail -3
