@@ -444,18 +444,18 @@ def extra_config_legs(ctx, args) -> dict:
         except Exception as e:
             out[name] = {"error": repr(e)}
     # ---- production switches beside the defaults: calibration 1 and the NNIG similarity have their own
-    #      instantiations of the fast sweep kernel; the generic kernel is timed beside them
+    #      instantiations of the fast sweep kernel, and so have categorical covariates; the generic kernel is timed beside them
     try:
         from cases import build_case
         sw = {}
-        for name in ("calib1_dp_T3", "nnig_ngg_T3"):
+        for name in ("calib1_dp_T3", "nnig_ngg_T3", "categorical_T3"):
             model, dims, shared, dsets, labels, nclu, betas = build_case(name, n_datasets=256)
             cds = np.repeat(np.arange(256, dtype=np.int32), 4)
             b = Batch(ctx, model, dims, shared, dsets, chain_dataset=cds)
             b.init(1, labels, nclu, betas[0])
             b.sweep(1, 0, 10)
             b.sweep(1, 10, 10)
-            rec = {"workload": f"n={dims.nobs} T={dims.T} P={dims.P}, 1024 chains over 256 replicate datasets, 10 sweeps timed",
+            rec = {"workload": f"n={dims.nobs} T={dims.T} P={dims.P} ncat={dims.ncat}, 1024 chains over 256 replicate datasets, 10 sweeps timed",
                    "sweep_kernel": b.last_sweep_info()[0],
                    "reallocations_per_sec": len(cds) * dims.nobs * 10 / (b.last_timing()[0] * 1e-3)}
             b.set_sweep_impl("generic")

@@ -23,6 +23,8 @@ CASES = {
     "noreuse":       (dict(reuse=0, CC=2), dict(T=2, n=50, P=5)),
     "ppm_only":      (dict(PPMx=0, cohesion=1), dict(T=2, n=50, P=3)),
     "categorical":   (dict(cohesion=1), dict(T=2, n=60, P=4, ncat=2, maxC=3, npred=20)),
+    "categorical_T3": (dict(cohesion=1, alpha=1.5), dict(T=3, ncat=3, maxC=4)),
+    "cat_calib2":    (dict(cohesion=1, calibration=2), dict(T=2, n=60, P=4, ncat=2, maxC=3, npred=20)),
     "cat_dd_calib1": (dict(similarity=2, calibration=1), dict(T=2, n=48, P=3, ncat=3, maxC=4, npred=16)),
     "prior_only":    (dict(nolik=1, CC=1, cohesion=1), dict(T=1, n=40, P=4)),
     "Q3_D3":         (dict(), dict(T=2, n=40, P=3, Q=3)),

@@ -69,10 +69,14 @@ CASES = {
     # Normal-Normal-Inverse-Gamma similarity (consim = 2): its own instantiation too
     "nnig": lambda: build_case("nnig", n_datasets=2),
     "nnig_ngg_T3": lambda: build_case("nnig_ngg_T3", n_datasets=2),
+    # categorical covariates beside the continuous ones
+    "categorical": lambda: build_case("categorical", n_datasets=2),
+    "categorical_T3": lambda: build_case("categorical_T3", n_datasets=2),
+    "cat_calib2": lambda: build_case("cat_calib2", n_datasets=2),
 }
 
 
-@pytest.mark.parametrize("name,lpu", [(n, l) for n in CASES for l in (8, 16, 32) if not (n.startswith(("calib1", "nnig")) and l == 8)])
+@pytest.mark.parametrize("name,lpu", [(n, l) for n in CASES for l in (8, 16, 32) if not (n.startswith(("calib1", "nnig", "cat")) and l == 8)])
 def test_fast_kernel_step_probabilities(ctx, name, lpu):
     from treatppmx_b200.engine import Batch
     model, dims, shared, dsets, labels, nclu, betas = CASES[name]()

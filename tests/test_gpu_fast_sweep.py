@@ -39,6 +39,8 @@ def _assert_same(g, o, dims, what=""):
 CAL1_CASES = [("calib1", 16), ("calib1", 32), ("calib1_dp_T3", 16), ("calib1_dp_T3", 32)]
 # so has the Normal-Normal-Inverse-Gamma similarity (consim = 2, src/utils_ct.cpp:427-459)
 CAL1_CASES += [("nnig", 16), ("nnig", 32), ("nnig_ngg_T3", 16), ("nnig_ngg_T3", 32)]
+# and categorical covariates beside the continuous ones (Dirichlet-multinomial similarity, src/utils_ct.cpp:468-495)
+CAL1_CASES += [(n, l) for n in ("categorical", "categorical_T3", "cat_calib2") for l in (16, 32)]
 
 
 @pytest.mark.parametrize("name,lpu", [(n, l) for n in FAST_CASES for l in (8, 16, 32)] + CAL1_CASES)

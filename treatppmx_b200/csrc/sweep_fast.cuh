@@ -41,9 +41,10 @@ namespace tppmx {
 struct UnitSmem {
   double *sumx, *sumx2, *logn, *xs, *wsc, *E;
   int *nj, *col, *freec, *lab, *pat;
+  int *njc, *xcs;  // categorical counts [ncat * maxC][KSTR], ring of four categorical rows (CAT instantiation)
 };
 
-__device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int ntp, int CC, int D, int big) {
+__device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int ntp, int CC, int D, int big, int ncatC = 0) {
   UnitSmem U;
   double *d = reinterpret_cast<double *>(base);
   U.sumx = d; d += (size_t)P * TPPMX_FAST_KSTR;
@@ -58,6 +59,9 @@ __device__ __forceinline__ UnitSmem fast_carve(char *base, int P, int KS, int nt
   U.freec = q; q += KS + CC;
   U.lab = q; q += big ? 0 : ntp + 1;
   U.pat = q;  // ntp + 1 entries (the prefetch of step it+1 may read one past the arm)
+  q += big ? 0 : ntp + 1;
+  U.njc = q;
+  U.xcs = q + (size_t)ncatC * TPPMX_FAST_KSTR;
   return U;   // big: logn / lab / pat are re-pointed at global memory by the kernel
 }
 
@@ -292,7 +296,11 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
 //   gsimconNNIG for its lane's cluster with and without the patient straight from the staged statistics, in the
 //   function's own operation order for the large cancelling terms, everything that depends on n only from an
 //   eight-entry table row, and the P logarithms a0s log(b0s) folded into one log of a product per lane.
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0, bool CAL1 = false, bool NNIG = false>
+// CAT: categorical covariates beside the continuous ones (Dirichlet-multinomial similarity, src/utils_ct.cpp:468-495):
+//   with the patient's category c* in covariate p the "with" minus "without" term is log(n_jc* + w) - log(n_j + C_p w)
+//   (Gamma(x + 1) = x Gamma(x) on both lgamma differences): the counts n_jc live in shared memory beside sumx, the
+//   two logarithms come from tables over the integers.
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0, bool CAL1 = false, bool NNIG = false, bool CAT = false>
 __global__ void __launch_bounds__(32, TPPMX_FAST_MINB)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -324,7 +332,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const int nt = valid ? b.arm_n[(size_t)ds * b.T + tt] : 0;
   const int nt_w = warp_max_over_units<LPU>(nt);
   const Rng rng = make_rng(seed, b.chain_id[chain]);
-  UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC, D, BIG ? 1 : 0);
+  const int ncat = CAT ? b.ncat : 0, maxC = CAT ? b.maxC : 0, ncC = ncat * maxC;
+  UnitSmem U = fast_carve(smem_raw + fa.tab_bytes + (size_t)sub * fa.unit_bytes, P, KS, ntp, CC, D, BIG ? 1 : 0, ncC);
 
   // global state of this unit
   double *g_sumx = b.sumx + ((size_t)chain * b.T + tt) * P * kcap;
@@ -355,6 +364,13 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     U.sumx2[e] = (j < KS) ? g_sumx2[(size_t)p * kcap + j] : 0.0;
   }
   for (int j = ul; j < KS; j += LPU) U.nj[j] = g_nj[j];
+  int *g_njc = b.njc + ((size_t)chain * b.T + tt) * (ncC > 0 ? ncC : 1) * kcap;
+  const int *g_xc = b.xcat + (size_t)ds * b.nobs * (ncat > 0 ? ncat : 1);
+  if constexpr (CAT)
+    for (int e = ul; e < ncC * KSTR; e += LPU) {
+      const int pc = e / KSTR, j = e % KSTR;
+      U.njc[e] = (j < KS) ? g_njc[(size_t)pc * kcap + j] : 0;
+    }
   // patient-indexed arrays: shared memory, or (BIG: arms of thousands of patients) global memory.
   // Kept in separate variables so the compiler sees one address space per instantiation.
   int *labp, *patp;
@@ -617,6 +633,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
       }
       if (!NOLIK) likv = likp[0];
+      if constexpr (CAT)
+        for (int p = ul; p < ncat; p += LPU) {
+          U.xcs[p] = g_xc[(size_t)i0 * ncat + p];
+          U.xcs[ncat + p] = g_xc[(size_t)i1 * ncat + p];
+        }
     }
     __syncwarp();
     // a, b of this lane's cluster (lanes >= K: the empty cluster, column 32) against the staged statistics
@@ -693,6 +714,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           xr_n[r] = (p < P) ? xrow[p] : 0.0;
         }
       }
+      int xc_n = 0;  // lane p < ncat: category of patient it+2 in covariate p
+      if constexpr (CAT)
+        if (ul < ncat) xc_n = g_xc[(size_t)patp[min(it + 2, ntp)] * ncat + ul];
       const double uu_n = uq[it + 1], qx_n = uq[uqs + it + 1], g_n = uq[2 * uqs + it + 1];
       int lab_n = labp[it + 1];  // label of the next patient (re-read after a relabelling)
       if (!NOLIK) lik_n = likp[it + 1];
@@ -732,6 +756,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           *pr1 = nr1;
           *pr2 = nr2;
         }
+        if constexpr (CAT)
+          if (ul < ncat) {  // the categorical counts follow the same two moves (integers: any order)
+            if (add) U.njc[(ul * maxC + U.xcs[((it + 3) & 3) * ncat + ul]) * KSTR + ca] += 1;
+            if (rem) U.njc[(ul * maxC + U.xcs[(it & 3) * ncat + ul]) * KSTR + zi] -= 1;
+          }
         // cluster sizes: every lane keeps its cluster's size in a register (the arrival was counted when
         // it was drawn) and stores it; clusters beyond the lanes (K > LPU, rare) are updated by lane 0
         myn = n_sc;
@@ -772,6 +801,12 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
             U.sumx2[p * KSTR + iaux - 1] = U.sumx2[p * KSTR + Kc - 1];
             U.sumx2[p * KSTR + Kc - 1] = t;
           }
+          if constexpr (CAT)
+            for (int pc = ul; pc < ncC; pc += LPU) {
+              const int t = U.njc[pc * KSTR + iaux - 1];
+              U.njc[pc * KSTR + iaux - 1] = U.njc[pc * KSTR + Kc - 1];
+              U.njc[pc * KSTR + Kc - 1] = t;
+            }
         }
         __syncwarp();
         if (single) {  // empty slot Kc-1 (keeps the rounding residue, as the reference does)
@@ -785,6 +820,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
             U.sumx[p * KSTR + Kc - 1] = __dsub_rn(U.sumx[p * KSTR + Kc - 1], xv);
             U.sumx2[p * KSTR + Kc - 1] = __dsub_rn(U.sumx2[p * KSTR + Kc - 1], __dmul_rn(xv, xv));
           }
+          if constexpr (CAT)
+            if (ul < ncat) U.njc[(ul * maxC + U.xcs[(it & 3) * ncat + ul]) * KSTR + Kc - 1] -= 1;
           K = Kc - 1;
           dV = dV_of(K);
         }
@@ -836,7 +873,13 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         wmax = unit_shift<LPU>(w, sub);
       } else if constexpr (!CAL1) {
         const double tY = fma(iv2, t1, a_c);
-        const double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a_c);
+        double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a_c);
+        if constexpr (CAT) {  // + sum_p [ log(n_jc* + w) - log(n_j + C_p w) ], counts after the removal
+          const int colj = (ul < K) ? ul : TPPMX_FAST_KSMAX;
+          const int *xc = U.xcs + (it & 3) * ncat;
+          for (int p = 0; p < ncat; p++)
+            d += fa.cat_lw[U.njc[(p * maxC + xc[p]) * KSTR + colj]] - fa.cat_ln[p * (b.ntmax + 2) + myn];
+        }
         const double wv = dV + lgn + simscale * d + likv;
         w = act0 ? wv : -INFINITY;
         wmax = unit_shift<LPU>(w, sub);
@@ -886,7 +929,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
       }
       const bool multi = on && ntot > LPU;
-      if (!CAL1 && !NNIG && __builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
+      if (!CAL1 && !NNIG && !CAT && __builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
         double *prow = nullptr;
         if constexpr (PROBE) {
           const int pu = unit - fa.probe_unit0;
@@ -965,6 +1008,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         const int p = ul + r * LPU;
         if (p < P) U.xs[((it + 2) & 3) * Pp + p] = xr_n[r];
       }
+      if constexpr (CAT)
+        if (ul < ncat) U.xcs[((it + 2) & 3) * ncat + ul] = xc_n;
       uu = uu_n;
       qx = qx_n;
       likv = lik_n;
@@ -989,6 +1034,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           }
         }
         if (ul == 0) U.nj[ca] += 1;
+        if constexpr (CAT)
+          if (ul < ncat) U.njc[(ul * maxC + U.xcs[((nt_w + 3) & 3) * ncat + ul]) * KSTR + ca] += 1;
       }
       __syncwarp();
     }
@@ -1005,6 +1052,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       }
     }
     for (int j = ul; j < KS; j += LPU) g_nj[j] = U.nj[j];
+    if constexpr (CAT)
+      for (int e = ul; e < ncC * KSTR; e += LPU) {
+        const int pc = e / KSTR, j = e % KSTR;
+        if (j < KS) g_njc[(size_t)pc * kcap + j] = U.njc[e];
+      }
     if (!BIG)
       for (int it = ul; it < nt; it += LPU) g_lab[it] = labp[it];
     if (ul == 0) {
@@ -1035,14 +1087,14 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
 }
 
 // ---- launch: instantiation picked from the batch shape (one translation unit per LPU) ----------
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC, bool CAL1 = false, bool NNIG = false>
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC, bool CAL1 = false, bool NNIG = false, bool CAT = false>
 static cudaError_t fast_launch7(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
 }
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
@@ -1050,6 +1102,13 @@ static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t sm
                                 int n_sweeps, cudaStream_t stream) {
   // the package's shape (genmech: 10 predictive covariates, D = 3 outcome categories, two units per warp) is
   // compiled with P as a constant: its dot products unroll into straight-line code
+  if (d.ncat > 0) {  // categorical covariates beside the continuous ones (Normal-Normal, calibration 0 | 2)
+    if constexpr (LPU >= 16 && DR == 3 && !NOLIK && !BIG) {
+      if (fa.KS + d.CC > LPU || d.model.calibration == 1 || d.model.consim != 1 || d.ncat > LPU) return cudaErrorInvalidConfiguration;
+      return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 0, false, false, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
+    }
+    return cudaErrorInvalidConfiguration;
+  }
   if (d.model.consim == 2) {  // NNIG similarity: the same restrictions as calibration 1 (tppmx.cu:fast_eligible)
     if constexpr (LPU >= 16 && DR == 3 && !NOLIK && !BIG) {
       if (fa.KS + d.CC > LPU || d.model.calibration == 1) return cudaErrorInvalidConfiguration;

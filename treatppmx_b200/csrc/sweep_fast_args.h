@@ -35,6 +35,10 @@ struct FastArgs {
   int probe_stride, probe_unit0, probe_nunits;
   // long-arm kernel (sweep_big.cuh): the staged capacity KS is chosen per launch, the likelihood table
   // keeps the stride of the largest one; kmax_dev receives the largest K any unit reached
+  // categorical covariates (Dirichlet-multinomial similarity, utils_ct.cpp:468-495) in the fast kernel: with the
+  // patient's category c* in covariate p, lgY - lgN = log(n_jc* + w) - log(n_j + C_p w) -- two table entries
+  const double *cat_lw;    // [ntmax + 2]          log(m + dirw)
+  const double *cat_ln;    // [ncat][ntmax + 2]    log(n + C_p dirw)
   size_t lik_unit_stride;  // doubles per unit of `lik`
   int *kmax_dev;
   int resume_mode;         // 1: run only the units with resume_l >= 0, from (resume_l, resume_it) (second stage)
@@ -42,9 +46,10 @@ struct FastArgs {
 
 __host__ __device__ inline int fast_pp(int P) { return (P + 1) & ~1; }
 // bytes of shared memory of one unit
-__host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D, int big) {
+// ncat / maxC: categorical covariates staged by the CAT instantiation (counts [ncat * maxC][KSTR] + a ring of four rows)
+__host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC, int D, int big, int ncat = 0, int maxC = 0) {
   size_t dbl = (size_t)2 * P * TPPMX_FAST_KSTR + (big ? 0 : (ntp + 1)) + 4 * fast_pp(P) + (KS + CC) + (size_t)(KS + CC) * D;
-  size_t in = (size_t)KS + 2 * (KS + CC) + (big ? 0 : 2 * (ntp + 1)) + 1;
+  size_t in = (size_t)KS + 2 * (KS + CC) + (big ? 0 : 2 * (ntp + 1)) + 1 + (size_t)ncat * maxC * TPPMX_FAST_KSTR + 4 * (size_t)ncat;
   return ((dbl * 8 + in * 4) + 15) & ~(size_t)15;
 }
 // per-n table (dA, HN, HY, P A0) of the Normal-Normal similarity, staged in shared memory for short arms.  The

@@ -108,6 +108,7 @@ struct tppmx_batch {
   int *psm_cnt = nullptr, *psm_n = nullptr, *pi_n = nullptr, *best_arm = nullptr;
   double *pi_sum = nullptr, *psm_mean = nullptr, *pi_mean = nullptr, *utility = nullptr, *util_w = nullptr;
   std::vector<int> arm_n;     // [nd][T]
+  std::vector<int> catvec_host;  // [ncat] categories per categorical covariate
   std::vector<int> chain_ds;  // [nc+1]
   cudaEvent_t ev0, ev1;
   double last_ms;
@@ -369,6 +370,7 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
     // shared
     std::vector<int> catvec(nc1, 0);
     for (int p = 0; p < ncat; p++) catvec[p] = shared->catvec[p];
+    b->catvec_host = catvec;
     std::vector<double> grid(shared->grid, shared->grid + 2 * (size_t)d.G);
     TRY(dev_upload(b, &d.catvec, catvec));
     TRY(dev_upload(b, &d.grid, grid));
@@ -1018,17 +1020,18 @@ static bool fast_eligible(const tppmx_batch *b, int lpu) {
   const tppmx_model &m = d.model;
   // calibration 1 and the NNIG similarity have their own instantiations of sweep_fast.cuh: the package's case only
   // (D <= 3, short arms, 16 | 32 lanes per unit)
-  const bool special = m.calibration == 1 || m.consim == 2;
+  const bool special = m.calibration == 1 || m.consim == 2 || d.ncat > 0;
   if (special && (d.D > 3 || m.nolik || big_arms(d) || lpu < 16)) return false;
   if (m.consim == 2 && (m.calibration == 1 || d.P > 32)) return false;
+  if (d.ncat > 0 && (m.calibration == 1 || m.consim != 1 || d.ncat > 16 || d.ncat * d.maxC > 256)) return false;
   return m.PPMx == 1 && (m.consim == 1 || m.consim == 2) && m.similarity == 1 && m.calibration >= 0 && m.calibration <= 2 &&
-         d.ncat == 0 && m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
+         m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
 }
 // arms too long for the small-arm kernel's shared-memory label / order / cohesion tables (thousands of
 // patients, BASELINE config 4) run the long-arm kernel (sweep_big.cuh): one CTA per (chain, arm)
 static bool big_arms(const DevBatch &d) {
   const size_t ks = d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX, ntp = (d.ntmax + 3) & ~3;
-  return fast_tab_bytes(d.ntmax, 0, d.model.consim == 2) + 2 * fast_unit_bytes(d.P, (int)ks, (int)ntp, d.CC, d.D, 0) > 48 * 1024;
+  return fast_tab_bytes(d.ntmax, 0, d.model.consim == 2) + 2 * fast_unit_bytes(d.P, (int)ks, (int)ntp, d.CC, d.D, 0, d.ncat, d.maxC) > 48 * 1024;
 }
 // largest staged cluster capacity of the long-arm kernel: min(kcap, 256), lowered until one CTA fits an SM
 static int big_ks(const DevBatch &d, int opt_ks) {
@@ -1108,6 +1111,16 @@ static int fast_reserve(tppmx_batch *b) {
     RC(dev_upload(b, &tp, tg));
     fa.tabg = const_cast<double *>(tp);
   }
+  fa.cat_lw = fa.cat_ln = nullptr;
+  if (d.ncat > 0) {  // gsimcatDM (utils_ct.cpp:468-495) as two logarithms over the integers (sweep_fast.cuh, CAT)
+    const double w = d.model.similparam[6];
+    std::vector<double> lw((size_t)d.ntmax + 2), ln((size_t)d.ncat * (d.ntmax + 2));
+    for (int m = 0; m <= d.ntmax + 1; m++) lw[m] = log((double)m + w);
+    for (int p = 0; p < d.ncat; p++)
+      for (int n = 0; n <= d.ntmax + 1; n++) ln[(size_t)p * (d.ntmax + 2) + n] = log((double)n + (double)b->catvec_host[p] * w);
+    RC(dev_upload(b, &fa.cat_lw, lw));
+    RC(dev_upload(b, &fa.cat_ln, ln));
+  }
   return TPPMX_OK;
 }
 
@@ -1125,12 +1138,12 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
       if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
       // calibration 1 normalises over all candidates in one pass of the unit's lanes (and the NNIG instantiation
       // has no chunked scoring path): K + CC <= lanes
-      if ((d.model.calibration == 1 || d.model.consim == 2) && fa.KS > lpu - d.CC) fa.KS = lpu - d.CC;
+      if ((d.model.calibration == 1 || d.model.consim == 2 || d.ncat > 0) && fa.KS > lpu - d.CC) fa.KS = lpu - d.CC;
     }
     fa.ntp = (d.ntmax + 3) & ~3;
     fa.ncol = fa.KS + d.CC;
     fa.n_units = d.n_chains * d.T;
-    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D, 0);
+    fa.unit_bytes = (int)fast_unit_bytes(d.P, fa.KS, fa.ntp, d.CC, d.D, 0, d.ncat, d.maxC);
     fa.tab_bytes = (int)fast_tab_bytes(d.ntmax, 0, d.model.consim == 2);
     b->fast_ready = true;
   }
