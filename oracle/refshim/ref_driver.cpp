@@ -16,7 +16,6 @@
 #include <cstdint>
 #include <cstdio>
 
-#include "../../treatppmx_b200/csrc/incgamma.h" /* R::pgamma / R::qgamma stand-in, as the oracle */
 
 /* ---- the reference's declarations (src/utils_ct.h; the two samplers have no header) ----------
  * REFDRV_SHIM_ONLY (oracle/Makefile target `shim`): the same driver over the CUDA library's Rcpp shim
@@ -95,8 +94,39 @@ double tape_pop(int kind, double aux) {
   }
   return g_val[g_pos++];
 }
-double gammainc_lower(double a, double x) { return tppmx_gammainc(a, x); }
-double gammainc_lower_inv(double a, double p) { return tppmx_gammaincinv(a, p); }
+/* R::pgamma / R::qgamma stand-ins for the REFERENCE build.  Deliberately independent of the product's
+ * csrc/incgamma.h (closed forms / continued fraction / Newton from Wilson-Hilferty, shared by the device
+ * kernel and the oracle): here P(a, x) is Kummer's all-positive series
+ *     P(a, x) = x^a e^-x sum_{k>=0} x^k / Gamma(a + k + 1)
+ * summed in extended precision for every x (no cancellation, so it is accurate relative to P everywhere the
+ * path goes), and the inverse is plain bisection on it to the last bit.  The whole-run pin of the oracle
+ * against the reference (tests/test_oracle_vs_reference.py) therefore checks the product's incomplete-gamma
+ * pair against a second implementation, not against itself. */
+static long double gammainc_series_ld(long double a, long double x) {
+  if (!(x > 0.0L)) return 0.0L;
+  long double term = 1.0L / a, sum = term;
+  for (int k = 1; k < 100000; k++) {
+    term *= x / (a + (long double)k);
+    sum += term;
+    if (term < sum * 1e-21L) break;
+  }
+  const long double lp = a * logl(x) - x - lgammal(a) + logl(sum);
+  const long double p = expl(lp);
+  return p > 1.0L ? 1.0L : p;
+}
+double gammainc_lower(double a, double x) { return (double)gammainc_series_ld((long double)a, (long double)x); }
+double gammainc_lower_inv(double a, double p) {
+  if (!(p > 0.0)) return 0.0;
+  if (p >= 1.0) return INFINITY;
+  long double lo = 0.0L, hi = 1.0L;
+  while (gammainc_series_ld((long double)a, hi) < (long double)p) hi *= 2.0L;
+  for (int it = 0; it < 200; it++) {
+    const long double mid = 0.5L * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    if (gammainc_series_ld((long double)a, mid) < (long double)p) lo = mid; else hi = mid;
+  }
+  return (double)(0.5L * (lo + hi));
+}
 }  // namespace refshim
 
 static arma::vec mk_vec(const double *p, long n) {
