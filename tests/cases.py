@@ -13,6 +13,7 @@ CASES = {
     "default_ngg":   (dict(), dict(T=2)),
     "dp_T3":         (dict(cohesion=1, alpha=1.5), dict(T=3)),
     "double_dipper": (dict(similarity=2), dict(T=2, n=60, P=6)),
+    "dd_dp_T3":      (dict(similarity=2, cohesion=1, alpha=1.5, calibration=2), dict(T=3)),
     "nnig":          (dict(consim=2, cohesion=1), dict(T=2, n=60, P=5)),
     "nnig_dd":       (dict(consim=2, similarity=2), dict(T=2, n=50, P=4)),
     "nnig_ngg_T3":   (dict(consim=2), dict(T=3)),

@@ -41,6 +41,8 @@ CAL1_CASES = [("calib1", 16), ("calib1", 32), ("calib1_dp_T3", 16), ("calib1_dp_
 CAL1_CASES += [("nnig", 16), ("nnig", 32), ("nnig_ngg_T3", 16), ("nnig_ngg_T3", 32)]
 # and categorical covariates beside the continuous ones (Dirichlet-multinomial similarity, src/utils_ct.cpp:468-495)
 CAL1_CASES += [(n, l) for n in ("categorical", "categorical_T3", "cat_calib2") for l in (16, 32)]
+# and the double-dipper Normal-Normal similarity (similarity = 2)
+CAL1_CASES += [(n, l) for n in ("double_dipper", "dd_dp_T3") for l in (16, 32)]
 
 
 @pytest.mark.parametrize("name,lpu", [(n, l) for n in FAST_CASES for l in (8, 16, 32)] + CAL1_CASES)
@@ -152,7 +154,7 @@ def test_calibration1_handover_beyond_the_lanes(ctx):
 
 def test_fast_rejected_for_ineligible_model(ctx):
     from treatppmx_b200.engine import Batch
-    model, dims, shared, dsets, labels, nclu, betas = build_case("double_dipper")
+    model, dims, shared, dsets, labels, nclu, betas = build_case("nnig_dd")   # NNIG double dipper: generic kernel only
     batch = Batch(ctx, model, dims, shared, dsets, chain_dataset=[0])
     batch.set_sweep_impl("fast")
     batch.init(1, labels, nclu, betas[0])

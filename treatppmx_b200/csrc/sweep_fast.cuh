@@ -300,7 +300,12 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
 //   with the patient's category c* in covariate p the "with" minus "without" term is log(n_jc* + w) - log(n_j + C_p w)
 //   (Gamma(x + 1) = x Gamma(x) on both lgamma differences): the counts n_jc live in shared memory beside sumx, the
 //   two logarithms come from tables over the integers.
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0, bool CAL1 = false, bool NNIG = false, bool CAT = false>
+// DDIP: similarity == 2, the double-dipper Normal-Normal form (src/utils_ct.cpp:382-405 with DD = 1):
+//   g = P B0[n] - sum_p sumx2/(2 v2) - H[n] sum_p t^2 + H2[n] sum_p u^2,  u = sumx/v2 + t = 2 t - c0, so beside a and b
+//   the lane carries st = sum_p t (linear in the statistics: corrected by +- sum_p x / v2 on the touched lanes):
+//   sum u^2 = 4 a - 4 c0 st + P c0^2,  sum u x = 2 b - c0 sum_p x.  The fourth table entry of row n is H2[n].
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0, bool CAL1 = false, bool NNIG = false, bool CAT = false,
+          bool DDIP = false>
 __global__ void __launch_bounds__(32, TPPMX_FAST_MINB)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -346,7 +351,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const double *g_x = b.x + (size_t)ds * b.nobs * P;
   double *lik = fa.lik + (size_t)unit * fa.ncol * ntp;
   const int uqs = ntp + 1;
-  double *uq = fa.uq + (size_t)unit * 3 * uqs;  // rows: uniform, sum_p x^2, x_{it-1} . x_it
+  double *uq = fa.uq + (size_t)unit * 4 * uqs;  // rows: uniform, sum_p x^2, x_{it-1} . x_it, sum_p x (double dipper)
   double *g_ez = b.zb + (size_t)chain * b.nobs * D;   // here: exp(beta'z) (scratch, rebuilt per sweep)
   double *g_ljj = b.ljj + (size_t)chain * b.nobs * D;
   const double *beta = b.beta + (size_t)chain * Q * D;
@@ -512,6 +517,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
               gx = fma(xv, xm[p], gx);
             }
           }
+          if constexpr (DDIP) {
+            double sxv = 0.0;
+            for (int p = 0; p < P; p++) sxv += xi[p];
+            uq[3 * uqs + it] = sxv;
+          }
           if (!NOLIK)
             for (int q = 0; q < Q; q++) {
               const double zq = zi[q];
@@ -643,6 +653,11 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     // a, b of this lane's cluster (lanes >= K: the empty cluster, column 32) against the staged statistics
     auto dots = [&](const double *xv, double &a, double &bb, double &ss) {
       const double *sx = U.sumx + ((ul < K) ? ul : TPPMX_FAST_KSMAX);
+      if constexpr (DDIP) {  // sum_p t_jp (returned through ss)
+        double q0 = 0.0;
+        for (int p = 0; p < P; p++) q0 += fma(sx[p * KSTR], iv2, c0);
+        ss = q0;
+      }
       if constexpr (CAL1) {  // sum_p sumx2_jp of this lane's cluster (the empty column gives 0)
         const double *sq = U.sumx2 + ((ul < K) ? ul : TPPMX_FAST_KSMAX);
         double q0 = 0.0;
@@ -690,7 +705,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     if (ul == labcur - 1) {  // patient 0 leaves its own cluster
       b_c = fma(-iv2, qx, b_c);
       a_c = fma(-iv2, fma(iv2, qx, 2.0 * b_c), a_c);
-      ss_c -= qx;
+      ss_c -= DDIP ? iv2 * uq[3 * uqs] : qx;
     }
 
     for (int it = 0; it < nt_w; it++) {
@@ -871,6 +886,17 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         const double wv = dV + lgn + simscale * (lgY - lgN) + likv;
         w = act0 ? wv : -INFINITY;
         wmax = unit_shift<LPU>(w, sub);
+      } else if constexpr (DDIP) {
+        const double sxc = uq[3 * uqs + it];  // sum_p x of this patient (pre-pass)
+        const double tY = fma(iv2, t1, a_c);
+        const double au = 4.0 * a_c - 4.0 * c0 * ss_c + (double)P * c0 * c0;   // sum_p u^2 without the patient
+        const double bu = 2.0 * b_c - c0 * sxc;                                 // sum_p u x
+        const double uY = au + 4.0 * iv2 * (bu + iv2 * qx);                     // ... with it
+        const double h2y = tab2[2 * (myn + 1) + 1].y;                           // H2[n + 1]; t23.y = H2[n]
+        const double d = t01.x - hiv2 * qx - (t23.x * tY - t01.y * a_c) + (h2y * uY - t23.y * au);
+        const double wv = dV + lgn + simscale * d + likv;
+        w = act0 ? wv : -INFINITY;
+        wmax = unit_shift<LPU>(w, sub);
       } else if constexpr (!CAL1) {
         const double tY = fma(iv2, t1, a_c);
         double d = t01.x - hiv2 * qx + (t23.x * tY - t01.y * a_c);
@@ -910,6 +936,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         b_n = (ul == zn) ? bs : b_n;
         a_n = (ul == zn) ? as : a_n;
         if constexpr (CAL1) ss_n = (ul == zn) ? ss_n - qx_n : ss_n;
+        if constexpr (DDIP) ss_n = (ul == zn) ? ss_n - iv2 * uq[3 * uqs + it + 1] : ss_n;
       }
       const int nj_n = U.nj[zn];  // size of the next patient's cluster before this step's arrival
       {
@@ -929,7 +956,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         }
       }
       const bool multi = on && ntot > LPU;
-      if (!CAL1 && !NNIG && !CAT && __builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
+      if (!CAL1 && !NNIG && !CAT && !DDIP && __builtin_expect(anymulti && __any_sync(TPPMX_FULL, multi), 0)) {
         double *prow = nullptr;
         if constexpr (PROBE) {
           const int pu = unit - fa.probe_unit0;
@@ -999,6 +1026,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         b_n = mine ? bq : b_n;
         a_n = mine ? aq : a_n;
         if constexpr (CAL1) ss_n = mine ? ss_n + qx : ss_n;
+        if constexpr (DDIP) ss_n = mine ? ss_n + iv2 * uq[3 * uqs + it] : ss_n;
       }
       pend = on ? lab : 0;
       nzi = nj_n + ((on && lab - 1 == zn) ? 1 : 0);
@@ -1087,14 +1115,15 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
 }
 
 // ---- launch: instantiation picked from the batch shape (one translation unit per LPU) ----------
-template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC, bool CAL1 = false, bool NNIG = false, bool CAT = false>
+template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC, bool CAL1 = false, bool NNIG = false, bool CAT = false,
+          bool DDIP = false>
 static cudaError_t fast_launch7(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT, DDIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT, DDIP><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
 }
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
@@ -1102,6 +1131,13 @@ static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t sm
                                 int n_sweeps, cudaStream_t stream) {
   // the package's shape (genmech: 10 predictive covariates, D = 3 outcome categories, two units per warp) is
   // compiled with P as a constant: its dot products unroll into straight-line code
+  if (d.model.similarity == 2) {  // double dipper (Normal-Normal, no categorical covariates, calibration 0 | 2)
+    if constexpr (LPU >= 16 && DR == 3 && !NOLIK && !BIG) {
+      if (fa.KS + d.CC > LPU || d.model.calibration == 1 || d.model.consim != 1 || d.ncat > 0) return cudaErrorInvalidConfiguration;
+      return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 0, false, false, false, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
+    }
+    return cudaErrorInvalidConfiguration;
+  }
   if (d.ncat > 0) {  // categorical covariates beside the continuous ones (Normal-Normal, calibration 0 | 2)
     if constexpr (LPU >= 16 && DR == 3 && !NOLIK && !BIG) {
       if (fa.KS + d.CC > LPU || d.model.calibration == 1 || d.model.consim != 1 || d.ncat > LPU) return cudaErrorInvalidConfiguration;

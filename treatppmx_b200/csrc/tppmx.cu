@@ -1020,11 +1020,12 @@ static bool fast_eligible(const tppmx_batch *b, int lpu) {
   const tppmx_model &m = d.model;
   // calibration 1 and the NNIG similarity have their own instantiations of sweep_fast.cuh: the package's case only
   // (D <= 3, short arms, 16 | 32 lanes per unit)
-  const bool special = m.calibration == 1 || m.consim == 2 || d.ncat > 0;
+  const bool special = m.calibration == 1 || m.consim == 2 || d.ncat > 0 || m.similarity == 2;
+  if (m.similarity == 2 && (m.calibration == 1 || m.consim != 1 || d.ncat > 0)) return false;
   if (special && (d.D > 3 || m.nolik || big_arms(d) || lpu < 16)) return false;
   if (m.consim == 2 && (m.calibration == 1 || d.P > 32)) return false;
   if (d.ncat > 0 && (m.calibration == 1 || m.consim != 1 || d.ncat > 16 || d.ncat * d.maxC > 256)) return false;
-  return m.PPMx == 1 && (m.consim == 1 || m.consim == 2) && m.similarity == 1 && m.calibration >= 0 && m.calibration <= 2 &&
+  return m.PPMx == 1 && (m.consim == 1 || m.consim == 2) && (m.similarity == 1 || m.similarity == 2) && m.calibration >= 0 && m.calibration <= 2 &&
          m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
 }
 // arms too long for the small-arm kernel's shared-memory label / order / cohesion tables (thousands of
@@ -1048,7 +1049,7 @@ static int fast_reserve(tppmx_batch *b) {
   const size_t KS = big_arms(d) ? (size_t)big_ks(d, 0) : (d.kcap < TPPMX_FAST_KSMAX ? d.kcap : TPPMX_FAST_KSMAX);
   const size_t ntp = (d.ntmax + 3) & ~3, units = (size_t)d.n_chains * d.T;
   RC(dev_alloc(b, &fa.lik, units * (KS + d.CC) * ntp + ntp + 8));
-  RC(dev_alloc(b, &fa.uq, units * 3 * (ntp + 1) + 8));
+  RC(dev_alloc(b, &fa.uq, units * 4 * (ntp + 1) + 8));
   RC(dev_alloc(b, &fa.resume_l, units));
   RC(dev_alloc(b, &fa.resume_it, units));
   RC(dev_alloc(b, &fa.bail_count, TPPMX_MAX_GROUPS));  // one counter per chain group of tppmx_batch_run
@@ -1105,6 +1106,10 @@ static int fast_reserve(tppmx_batch *b) {
         tg[(size_t)4 * n + 1] = (n == 0) ? 0.0 : tab[n].H;
         tg[(size_t)4 * n + 2] = tab[n + 1].H;
         tg[(size_t)4 * n + 3] = (n == 0) ? 0.0 : dP * tab[n].A0;  // calibration 1 scores lgN, lgY themselves
+        if (d.model.similarity == 2) {  // double dipper: (dB, HN, HY, H2N)
+          tg[(size_t)4 * n + 0] = (n == 0) ? dP * tab[1].B0 : dP * (tab[n + 1].B0 - tab[n].B0);
+          tg[(size_t)4 * n + 3] = (n == 0) ? 0.0 : tab[n].H2;
+        }
       }
     }
     const double *tp = nullptr;
@@ -1138,7 +1143,7 @@ static int fast_prepare(tppmx_batch *b, int lpu, size_t *smem_out) {
       if (b->opt_ks > 0 && b->opt_ks < fa.KS) fa.KS = b->opt_ks;
       // calibration 1 normalises over all candidates in one pass of the unit's lanes (and the NNIG instantiation
       // has no chunked scoring path): K + CC <= lanes
-      if ((d.model.calibration == 1 || d.model.consim == 2 || d.ncat > 0) && fa.KS > lpu - d.CC) fa.KS = lpu - d.CC;
+      if ((d.model.calibration == 1 || d.model.consim == 2 || d.ncat > 0 || d.model.similarity == 2) && fa.KS > lpu - d.CC) fa.KS = lpu - d.CC;
     }
     fa.ntp = (d.ntmax + 3) & ~3;
     fa.ncol = fa.KS + d.CC;
@@ -1418,7 +1423,7 @@ static void batch_view(const tppmx_batch *b, tppmx_batch *v, tppmx_ctx *lane, in
   FastArgs &f = v->fa;
   if (f.lik) {
     const size_t u0 = c * T, ntp = (p.ntmax + 3) & ~3;
-    f.lik += u0 * f.lik_unit_stride; f.uq += u0 * 3 * (ntp + 1);
+    f.lik += u0 * f.lik_unit_stride; f.uq += u0 * 4 * (ntp + 1);
     f.resume_l += u0; f.resume_it += u0; f.logng += u0 * (ntp + 1); f.patpad += u0 * (ntp + 1);
     f.bail_count += g; f.kmax_dev += g;
   }

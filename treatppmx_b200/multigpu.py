@@ -9,6 +9,32 @@ from __future__ import annotations
 import numpy as np
 
 
+def pin_to_gpu_numa_node(device: int) -> dict:
+    """Restricts this process (and the threads it starts later) to the CPUs of the NUMA node the GPU hangs
+    off, so that the pinned staging buffers are first-touched next to the device and the host threads that
+    fill them run there (one process per GPU: eight unpinned processes share the box's memory channels
+    across sockets).  Reads /sys only; returns what it did ({"node": n, "cpus": k} or {"skipped": why})."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device)
+        pci = f"{getattr(bus, 'pci_domain_id', 0):04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read())
+        if node < 0:
+            return {"skipped": "no NUMA node reported for " + pci}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        mine = cpus & os.sched_getaffinity(0)
+        if len(mine) < 2:
+            return {"skipped": f"node {node} has {len(mine)} of this process's CPUs"}
+        os.sched_setaffinity(0, mine)
+        return {"node": node, "cpus": len(mine)}
+    except Exception as e:   # never fatal: the run is merely not pinned
+        return {"skipped": repr(e)}
+
+
 def shard_range(n_items: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous block [lo, hi) of `n_items` datasets owned by `rank` (sizes differ by at most 1)."""
     base, rem = divmod(n_items, world)
