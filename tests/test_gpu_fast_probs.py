@@ -63,6 +63,7 @@ CASES = {
     "calib2_sqrt": lambda: build_case("calib2_sqrt", n_datasets=2),
     "dp_T3": lambda: build_case("dp_T3", n_datasets=2),
     "Q3_D3": lambda: build_case("Q3_D3", n_datasets=2),
+    "ppm_only": lambda: build_case("ppm_only", n_datasets=2),   # PPMx = 0: cohesion x likelihood only
     # calibration 1: normalised similarities, their own instantiation (16 | 32 lanes per unit)
     "calib1": lambda: build_case("calib1", n_datasets=2),
     "calib1_dp_T3": lambda: build_case("calib1_dp_T3", n_datasets=2),
@@ -80,7 +81,7 @@ CASES = {
 
 
 @pytest.mark.parametrize("name,lpu", [(n, l) for n in CASES for l in (8, 16, 32) if not (n.startswith(("calib1", "nnig", "cat", "double", "dd_")) and l == 8)
-                                      and not (n == "double_dipper" and l == 16)])   # its partitions outgrow 16 - CC staged clusters
+                                      and not (n in ("double_dipper", "dd_dp_T3") and l == 16)])   # their partitions outgrow 16 - CC staged clusters
 def test_fast_kernel_step_probabilities(ctx, name, lpu):
     from treatppmx_b200.engine import Batch
     model, dims, shared, dsets, labels, nclu, betas = CASES[name]()

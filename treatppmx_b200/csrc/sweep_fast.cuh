@@ -360,7 +360,9 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   const double sigma = b.sigma[(size_t)chain * b.T + tt];
   const int idxs = b.idxs[chain];
   const double iv2 = s.iv2, c0 = s.c0, hiv2 = s.hiv2;
-  const double simscale = (s.calibration == 2) ? s.calscale : 1.0;
+  // PPMx == 0 (no covariate similarity, :401-409 skipped): the similarity term is multiplied by zero and the
+  // statistics, which the reference then never touches, are not written back
+  const double simscale = !s.PPMx ? 0.0 : ((s.calibration == 2) ? s.calscale : 1.0);
 
   // ---- stage the unit's state in shared memory
   for (int e = ul; e < P * KSTR; e += LPU) {
@@ -1072,13 +1074,14 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
   // ---- write the unit back in the library's global layout
   __syncwarp();
   if (valid) {
-    for (int e = ul; e < P * KSTR; e += LPU) {
-      const int p = e / KSTR, j = e % KSTR;
-      if (j < KS) {
-        g_sumx[(size_t)p * kcap + j] = U.sumx[e];
-        g_sumx2[(size_t)p * kcap + j] = U.sumx2[e];
+    if (s.PPMx)
+      for (int e = ul; e < P * KSTR; e += LPU) {
+        const int p = e / KSTR, j = e % KSTR;
+        if (j < KS) {
+          g_sumx[(size_t)p * kcap + j] = U.sumx[e];
+          g_sumx2[(size_t)p * kcap + j] = U.sumx2[e];
+        }
       }
-    }
     for (int j = ul; j < KS; j += LPU) g_nj[j] = U.nj[j];
     if constexpr (CAT)
       for (int e = ul; e < ncC * KSTR; e += LPU) {

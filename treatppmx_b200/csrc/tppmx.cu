@@ -70,12 +70,16 @@ struct tppmx_ctx {
   // own stream triple, so that the sweep of one group overlaps the updates of another -- chains are independent,
   // and at BASELINE's 1024 chains every kernel of the iteration is latency-bound (2.6 warps per scheduler)
   std::vector<tppmx_ctx *> lanes;
+  // device block of the drop-in's traces (tppmx_dm_ppmx_ct), kept across calls
+  void *trace = nullptr;
+  size_t trace_bytes = 0;
   cudaEvent_t ev_go = nullptr, ev_done = nullptr;
   bool side_pending = false;  // summaries of a saved iteration still running on `side`
 };
 static void ctx_release(tppmx_ctx *c) {
   cudaSetDevice(c->device);
   for (tppmx_ctx *l : c->lanes) ctx_release(l);
+  if (c->trace) cudaFree(c->trace);
   c->lanes.clear();
   if (c->ev_go) cudaEventDestroy(c->ev_go);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
@@ -1025,7 +1029,8 @@ static bool fast_eligible(const tppmx_batch *b, int lpu) {
   if (special && (d.D > 3 || m.nolik || big_arms(d) || lpu < 16)) return false;
   if (m.consim == 2 && (m.calibration == 1 || d.P > 32)) return false;
   if (d.ncat > 0 && (m.calibration == 1 || m.consim != 1 || d.ncat > 16 || d.ncat * d.maxC > 256)) return false;
-  return m.PPMx == 1 && (m.consim == 1 || m.consim == 2) && (m.similarity == 1 || m.similarity == 2) && m.calibration >= 0 && m.calibration <= 2 &&
+  if (m.PPMx == 0 && (special || big_arms(d))) return false;  // no similarity term: the plain instantiation with a zero factor
+  return (m.PPMx == 1 || m.PPMx == 0) && (m.consim == 1 || m.consim == 2) && (m.similarity == 1 || m.similarity == 2) && m.calibration >= 0 && m.calibration <= 2 &&
          m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
 }
 // arms too long for the small-arm kernel's shared-memory label / order / cohesion tables (thousands of
@@ -1943,23 +1948,37 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
   TraceBufs tr;
   memset(&tr, 0, sizeof(tr));
   tr.nout = nout > 0 ? nout : 1;
-  std::vector<void *> tofree;
-  auto dalloc = [&](double **p, size_t n) {
-    if (rc) return;
-    void *q = nullptr;
-    if (cudaMalloc(&q, sizeof(double) * (n ? n : 1)) != cudaSuccess) { rc = fail(ctx, TPPMX_ERR_NOMEM, "trace buffers"); return; }
-    cudaMemsetAsync(q, 0, sizeof(double) * (n ? n : 1), ctx->stream);
-    tofree.push_back(q);
-    *p = (double *)q;
-  };
+  // the traces of all saved iterations: ONE device block kept by the context and reused by later calls (a run of
+  // cudaMalloc / cudaFree per call costs up to hundreds of milliseconds on a busy box -- more than the sampler)
   const size_t no = (size_t)tr.nout, n1 = (size_t)npred * D * T;
-  dalloc(&tr.eta, no * T * D * ntm); dalloc(&tr.beta, no * Q * D); dalloc(&tr.sigma, no * T); dalloc(&tr.kappa, no * T);
-  dalloc(&tr.cl_lab, no * T * ntm); dalloc(&tr.pi, no * nobs * D); dalloc(&tr.pipred, no * n1);
-  dalloc(&tr.yispred, no * nobs * D); dalloc(&tr.ypred, no * n1); dalloc(&tr.clupred, no * npred * T);
-  dalloc(&tr.nclus, no * T); dalloc(&tr.lpml, no); dalloc(&tr.mnlike, nobs); dalloc(&tr.mnllike, nobs);
-  dalloc(&tr.sumtotclu, T);
+  {
+    struct Seg { double **p; size_t n; };
+    const Seg segs[] = {{&tr.eta, no * T * D * ntm}, {&tr.beta, no * Q * D}, {&tr.sigma, no * T}, {&tr.kappa, no * T},
+                        {&tr.cl_lab, no * T * ntm}, {&tr.pi, no * nobs * D}, {&tr.pipred, no * n1}, {&tr.yispred, no * nobs * D},
+                        {&tr.ypred, no * n1}, {&tr.clupred, no * npred * T}, {&tr.nclus, no * T}, {&tr.lpml, no},
+                        {&tr.mnlike, (size_t)nobs}, {&tr.mnllike, (size_t)nobs}, {&tr.sumtotclu, (size_t)T}};
+    size_t total = 0;
+    for (const Seg &sg : segs) total += al256(sizeof(double) * (sg.n ? sg.n : 1));
+    if (!rc && total > ctx->trace_bytes) {
+      if (ctx->trace) cudaFree(ctx->trace);
+      ctx->trace = nullptr;
+      ctx->trace_bytes = 0;
+      if (cudaMalloc(&ctx->trace, total) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_NOMEM, "trace buffers");
+      else ctx->trace_bytes = total;
+    }
+    if (!rc) {
+      char *q = (char *)ctx->trace;
+      for (const Seg &sg : segs) {
+        *sg.p = (double *)q;
+        q += al256(sizeof(double) * (sg.n ? sg.n : 1));
+      }
+      if (cudaMemsetAsync(ctx->trace, 0, total, ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "trace buffers");
+    }
+  }
 
   int launches = 0, ll = 0;
+  const bool one_stream = getenv("TPPMX_DROPIN_ONE_STREAM") != nullptr;  // A/B switch: everything on the context's main stream
+  const auto t_issue0 = std::chrono::steady_clock::now();
   for (int l = 0; l < a->iter && !rc; l++) {
     if (ctx->interrupt && l > 0 && l % ctx->check_every == 0) {  // tppmx_set_interrupt_flag
       if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: kernel failure");
@@ -1976,9 +1995,12 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
     // predictive step: for ONE chain it was half of the iteration's latency
     const bool saved = (l > (a->burn - 1)) && ((l + 1) % a->thin == 0) && ll < nout;  // :1060
     const bool pred = saved && npred > 0;
-    if (!rc) rc = update_launch(B, a->seed, l, &launches, pred ? ctx->ev_upd : nullptr, true);
+    if (!rc) rc = update_launch(B, a->seed, l, &launches, (pred && !one_stream) ? ctx->ev_upd : nullptr, !one_stream);
     if (rc) break;
-    if (pred) {  // the predictive step only reads what the update kernel left: it runs on the side stream beside the gamma draws
+    if (pred && one_stream) {
+      rc = predict_launch(B, 1, a->seed, l, B->pred_pi, B->pred_y, B->pred_c);
+      if (rc) break;
+    } else if (pred) {  // the predictive step only reads what the update kernel left: it runs on the side stream beside the gamma draws
       if (cudaStreamWaitEvent(ctx->side, ctx->ev_upd, 0) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: stream wait");
       if (!rc) rc = predict_launch(B, 1, a->seed, l, B->pred_pi, B->pred_y, B->pred_c, ctx->side);
       if (!rc && (cudaEventRecord(ctx->ev_side, ctx->side) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0) != cudaSuccess))
@@ -1992,7 +2014,12 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
     }
   }
   if (!rc) rc = hs_join(ctx);
+  const auto t_issue1 = std::chrono::steady_clock::now();
   if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "dm_ppmx_ct: kernel failure");
+  if (getenv("TPPMX_TRACE"))
+    fprintf(stderr, "tppmx_dm_ppmx_ct: %d iterations, %d launches: host issue %.3f ms, until done %.3f ms\n", a->iter, launches,
+            std::chrono::duration<double, std::milli>(t_issue1 - t_issue0).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_issue0).count());
   if (!rc) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, std::string("dm_ppmx_ct: ") + cudaGetErrorString(e));
@@ -2031,7 +2058,6 @@ extern "C" int tppmx_dm_ppmx_ct(tppmx_ctx *ctx, const tppmx_ppmxct_args *a, tppm
     st.Sigma = o->sigma_prior;
     if (!rc) rc = tppmx_batch_get_state(B, 0, &st);
   }
-  for (void *q : tofree) cudaFree(q);
   tppmx_batch_destroy(B);
   return rc;
 }
@@ -2097,6 +2123,8 @@ extern "C" int tppmx_prior_ppmx_core(tppmx_ctx *ctx, const tppmx_prior_args *a, 
   if (!rc && (cudaMalloc(&d_nclu, sizeof(double) * n1) != cudaSuccess || cudaMalloc(&d_nj, sizeof(double) * n2) != cudaSuccess))
     rc = fail(ctx, TPPMX_ERR_NOMEM, "trace buffers");
   int launches = 0, ll = 0;
+  const bool one_stream = getenv("TPPMX_DROPIN_ONE_STREAM") != nullptr;  // A/B switch: everything on the context's main stream
+  const auto t_issue0 = std::chrono::steady_clock::now();
   for (int l = 0; l < a->iter && !rc; l++) {
     if (ctx->interrupt && l > 0 && l % ctx->check_every == 0) {
       if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "prior_ppmx_core: kernel failure");
