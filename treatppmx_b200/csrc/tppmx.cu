@@ -2123,8 +2123,6 @@ extern "C" int tppmx_prior_ppmx_core(tppmx_ctx *ctx, const tppmx_prior_args *a, 
   if (!rc && (cudaMalloc(&d_nclu, sizeof(double) * n1) != cudaSuccess || cudaMalloc(&d_nj, sizeof(double) * n2) != cudaSuccess))
     rc = fail(ctx, TPPMX_ERR_NOMEM, "trace buffers");
   int launches = 0, ll = 0;
-  const bool one_stream = getenv("TPPMX_DROPIN_ONE_STREAM") != nullptr;  // A/B switch: everything on the context's main stream
-  const auto t_issue0 = std::chrono::steady_clock::now();
   for (int l = 0; l < a->iter && !rc; l++) {
     if (ctx->interrupt && l > 0 && l % ctx->check_every == 0) {
       if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TPPMX_ERR_CUDA, "prior_ppmx_core: kernel failure");
