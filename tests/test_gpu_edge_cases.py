@@ -71,6 +71,20 @@ def test_ragged_arms(ctx):
     _lockstep(ctx, _custom(48, 3, 4, 2, 3, 6, treat))
 
 
+@pytest.mark.parametrize("mkw", [dict(calibration=1), dict(calibration=1, cohesion=1), dict(consim=2), dict(consim=2, cohesion=1),
+                                 dict(similarity=2, cohesion=1), dict(PPMx=0, cohesion=1)],
+                         ids=["calib1-ngg", "calib1-dp", "nnig-ngg", "nnig-dp", "double-dipper-dp", "ppm-only"])
+def test_ragged_and_single_patient_arms_on_the_special_instantiations(ctx, mkw):
+    """The fast kernel's instantiations for calibration 1, the NNIG similarity, the double dipper and PPMx = 0 on arms of
+    40 / 7 / 1 patients (a one-patient arm is scored against auxiliary clusters only: the occupied-cluster normaliser
+    of calibration 1 is then empty) and on two one-patient arms."""
+    treat = [0] * 37 + [1] * 5 + [2] * 1 + [0] * 3 + [1] * 2
+    b, pb = _lockstep(ctx, _custom(48, 3, 4, 2, 3, 6, treat, **mkw))
+    assert b.last_sweep_info()[0] == "fast"
+    b, pb = _lockstep(ctx, _custom(2, 2, 3, 1, 3, 2, [0, 1], **dict(mkw, cohesion=1)))
+    assert b.last_sweep_info()[0] == "fast"
+
+
 def test_single_patient_arms_and_tiny_data(ctx):
     _lockstep(ctx, _custom(2, 2, 3, 1, 3, 2, [0, 1], cohesion=1))
     _lockstep(ctx, _custom(3, 1, 2, 2, 3, 1, [0, 0, 0], cohesion=1))
