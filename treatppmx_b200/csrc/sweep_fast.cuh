@@ -1095,7 +1095,8 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
       fa.resume_l[unit] = bail_l;
       fa.resume_it[unit] = bail_it;
       if (bail_l >= 0) atomicAdd(fa.bail_count, 1);
-      if (BIG && fa.kmax_dev) atomicMax(fa.kmax_dev, K);  // long arms: the next launch sizes its staging from it
+      // long arms: the next launch sizes its staging from it; special instantiations: the host picks 16 | 32 lanes from it
+      if ((BIG || CAL1 || NNIG || CAT || DDIP) && fa.kmax_dev) atomicMax(fa.kmax_dev, K);
     }
   }
   __syncwarp();

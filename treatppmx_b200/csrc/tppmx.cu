@@ -129,6 +129,11 @@ struct tppmx_batch {
   int big_ksmax = 0, big_nth = 0, kmax_hint = 0, opt_big_nth = 0, big_hint = 0;
   bool big_two_stage = false;
   int *kmax_host = nullptr;  // pinned
+  // special instantiations of the fast kernel (calibration 1, NNIG, categorical, double dipper) stage lanes - CC clusters:
+  // the hand-over count and the largest K of the previous launch are read back (pinned, no sync), and the automatic
+  // choice is 32 lanes per unit while partitions come close to 16 - CC clusters, 16 lanes otherwise
+  int *bail_host = nullptr;  // [2]: hand-overs, largest K at the end of the launch
+  int last_lpu = 0;
 };
 
 #define CK(ctx, call)                                                                      \
@@ -272,6 +277,7 @@ static T *dev_stage(tppmx_batch *b, const T **p, size_t n, int *rc) {
 }
 static bool fast_eligible(const tppmx_batch *b, int lpu);
 static bool big_arms(const DevBatch &d);
+static bool fast_special(const DevBatch &d);
 static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc,
                           cudaStream_t st = nullptr, double *dsum = nullptr, int *launches = nullptr);
 // one thread per new patient of an (chain, arm) block: no more threads than patients
@@ -514,6 +520,8 @@ extern "C" int tppmx_batch_create(tppmx_ctx *ctx, const tppmx_model *model, cons
       TRY(dev_alloc(b, &b->pred_c, (size_t)n_chains * npred * T));
     }
     if (fast_eligible(b, 32)) TRY(fast_reserve(b));
+    if (pass == 1 && b->fa.lik && fast_special(d) && !b->bail_host && cudaHostAlloc((void **)&b->bail_host, 2 * sizeof(int), cudaHostAllocDefault) == cudaSuccess)
+      b->bail_host[0] = b->bail_host[1] = 0;
     if (pass == 1 && big_arms(d) && !b->kmax_host && cudaHostAlloc((void **)&b->kmax_host, sizeof(int), cudaHostAllocDefault) == cudaSuccess)
       *b->kmax_host = 0;
     {  // posterior summaries; the co-clustering counts are skipped beyond 2 GiB (large-n config)
@@ -570,6 +578,7 @@ extern "C" int tppmx_batch_destroy(tppmx_batch *b) {
   cudaEventDestroy(b->ev0);
   cudaEventDestroy(b->ev1);
   if (b->kmax_host) cudaFreeHost(b->kmax_host);
+  if (b->bail_host) cudaFreeHost(b->bail_host);
   tppmx_ctx *c = b->ctx;
   delete b;
   if (--c->live_batches == 0 && c->closed) ctx_release(c);
@@ -705,6 +714,7 @@ extern "C" int tppmx_batch_init(tppmx_batch *b, uint64_t seed, const int32_t *in
   const int nd = d.n_datasets, T = d.T, nt = d.ntmax;
   b->kmax_hint = 0;
   if (b->kmax_host) *b->kmax_host = 0;
+  if (b->bail_host) b->bail_host[0] = b->bail_host[1] = 0;
   std::vector<int> lab((size_t)nd * T * nt), ncl((size_t)nd * T);
   for (int ds = 0; ds < nd; ds++)
     for (int t = 0; t < T; t++) {
@@ -1018,13 +1028,18 @@ extern "C" int tppmx_batch_get_info(const tppmx_batch *b, int32_t what, int32_t 
   return TPPMX_OK;
 }
 
+// models with their own instantiation of the fast kernel (staged capacity lanes - CC)
+static bool fast_special(const DevBatch &d) {
+  const tppmx_model &m = d.model;
+  return m.calibration == 1 || m.consim == 2 || d.ncat > 0 || m.similarity == 2;
+}
 // is the model one the fast kernel implements?
 static bool fast_eligible(const tppmx_batch *b, int lpu) {
   const DevBatch &d = b->d;
   const tppmx_model &m = d.model;
   // calibration 1 and the NNIG similarity have their own instantiations of sweep_fast.cuh: the package's case only
   // (D <= 3, short arms, 16 | 32 lanes per unit)
-  const bool special = m.calibration == 1 || m.consim == 2 || d.ncat > 0 || m.similarity == 2;
+  const bool special = fast_special(d);
   if (m.similarity == 2 && (m.calibration == 1 || m.consim != 1 || d.ncat > 0)) return false;
   if (special && (d.D > 3 || m.nolik || big_arms(d) || lpu < 16)) return false;
   if (m.consim == 2 && (m.calibration == 1 || d.P > 32)) return false;
@@ -1201,7 +1216,17 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   if (big) lpu = 32;  // long arms: one CTA per (chain, arm), P <= 128 covariate owners
   // few units (one ppmxct() call = one chain): latency, not residency, is what counts -- one unit per warp puts
   // twice the lanes on the sweep's parallel pre-pass
-  else if (!lpu) lpu = ((long long)b->d.n_chains * b->d.T <= 296) ? 32 : 16;
+  else if (!lpu) {
+    lpu = ((long long)b->d.n_chains * b->d.T <= 296) ? 32 : 16;
+    if (b->bail_host) {
+      const volatile int *bh = b->bail_host;
+      if ((long long)bh[0] * 50 > (long long)b->d.n_chains * b->d.T || bh[1] + b->d.CC + 2 > 16) lpu = 32;
+    }
+  }
+  if (lpu != b->last_lpu) {  // the staged capacity of the special instantiations follows the lanes
+    b->fast_ready = false;
+    b->last_lpu = lpu;
+  }
   size_t smem = 0;
   bool use_fast = b->opt_impl != 1 && fast_eligible(b, lpu) && b->fa.lik;
   if (use_fast) {
@@ -1211,6 +1236,7 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   if (b->opt_impl == 2 && !use_fast) return fail(ctx, TPPMX_ERR_ARG, "model/shape not eligible for the fast sweep kernel");
   if (use_fast) {
     CK(ctx, cudaMemsetAsync(b->fa.bail_count, 0, sizeof(int), ctx->stream));
+    if (!b->fa.big && b->bail_host) CK(ctx, cudaMemsetAsync(b->fa.kmax_dev, 0, sizeof(int), ctx->stream));
     cudaError_t e;
     if (b->fa.big) {
       CK(ctx, cudaMemsetAsync(b->fa.kmax_dev, 0, sizeof(int), ctx->stream));
@@ -1238,6 +1264,10 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
     (*launches)++;
     if (b->fa.big && b->kmax_host)
       CK(ctx, cudaMemcpyAsync(b->kmax_host, b->fa.kmax_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!b->fa.big && b->bail_host) {
+      CK(ctx, cudaMemcpyAsync(b->bail_host, b->fa.bail_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(ctx, cudaMemcpyAsync(b->bail_host + 1, b->fa.kmax_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     int nb = 1;
     if (sync_handover) {
       CK(ctx, cudaMemcpyAsync(&nb, b->fa.bail_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1434,6 +1464,7 @@ static void batch_view(const tppmx_batch *b, tppmx_batch *v, tppmx_ctx *lane, in
   }
   v->fast_ready = false;  // n_units follows the view
   v->kmax_host = nullptr;
+  v->bail_host = nullptr;
 }
 
 // one iteration (sweep, updates, and on a saved iteration the co-clustering counts / predictive step) of the
