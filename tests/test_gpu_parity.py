@@ -157,7 +157,7 @@ def test_L2_long_lockstep_1000_sweeps(ctx):
         _assert_state_equal(batch.get_state(c), st, dims)
 
 
-@pytest.mark.parametrize("name", ["default_ngg", "dp_T3", "calib1", "calib2", "categorical",
+@pytest.mark.parametrize("name", ["default_ngg", "dp_T3", "calib1", "calib2", "categorical", "categorical_T3", "cat_calib2",
                                   "cat_dd_calib1", "nnig", "double_dipper", "ppm_only"])
 def test_predict_matches_oracle(ctx, name):
     nchains = 2

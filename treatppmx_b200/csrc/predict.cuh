@@ -100,7 +100,7 @@ __device__ inline void pred_emit(const DevBatch &b, const Rng &rng, const ArmVie
 // grid = (chains, T); threads stride over new patients
 __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed, int iter,
                                                       double *pipred, double *ypred,
-                                                      int *predclass, double *pisum) {
+                                                      int *predclass, double *pisum, int kmin) {
   // block = (chain, arm): the arms of a chain (and the chains of a dataset) are adjacent blocks, so a dataset's new
   // patients are read from DRAM once (as grid (chains, T) every arm made its own pass: 930 MB against 250 MB of inputs)
   const int chain = blockIdx.x / b.T, tt = blockIdx.x % b.T;
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(128) predict_kernel(DevBatch b, uint64_t seed,
   const Rng rng = make_rng(seed, b.chain_id[chain]);
   const ArmView A = arm_view_global(b, chain, tt, ds);
   const int K = A.K, CC = b.CC, ntot = K + CC, D = b.D, npred = b.npred;
+  if (K < kmin) return;  // block-uniform: predict_reg_kernel took this arm
   const double sigma = b.sigma[(size_t)chain * b.T + tt];
   const int idxs = b.idxs[chain];
   const double log_alpha_cc = log(b.model.alpha) - log((double)CC);
@@ -296,8 +297,15 @@ __global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t 
 #define TPPMX_PRED_KR 16
 template <int PR>
 __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_t seed, int iter, double *pipred,
-                                                          double *ypred, int *predclass, double *pisum) {
+                                                          double *ypred, int *predclass, double *pisum,
+                                                          const double *cat_lw, const double *cat_ln) {
   constexpr int KR = TPPMX_PRED_KR, DR = 3;
+  // categorical covariates (cat_lw != nullptr): counts n_jc [ncat * maxC][KR] and sizes n_j [KR] in dynamic shared
+  // memory; the Dirichlet-multinomial "with minus without" term of covariate p is log(n_jc* + w) - log(n_j + C_p w)
+  // from the two tables (as the CAT instantiation of sweep_fast.cuh)
+  extern __shared__ int pred_dyn[];
+  const int ncat = cat_lw ? b.ncat : 0, ncC = ncat * b.maxC;
+  int *njcs = pred_dyn, *njs = pred_dyn + ncC * KR;
   __shared__ double ts[PR][KR];
   __shared__ double cs[3][KR];
   __shared__ double etas[DR][KR];
@@ -338,6 +346,15 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
       for (int k = 0; k < D; k++) etas[k][j] = A.eta[(size_t)k * A.ks + j];
     }
   }
+  if (ncat > 0) {
+    for (int e = tid; e < ncC * KR; e += nth) {
+      const int pc = e / KR, j = e - pc * KR;
+      njcs[e] = (j < K) ? A.njc[(size_t)pc * A.ks + j] : 0;
+    }
+    for (int j = tid; j < KR; j += nth) njs[j] = (j < K) ? A.nj[j] : 0;
+  }
+  double cat_aux = 0.0;  // an auxiliary cluster: counts zero, sum_p [log w - log(C_p w)]
+  for (int p = 0; p < ncat; p++) cat_aux += cat_lw[0] - cat_ln[(size_t)p * (b.ntmax + 2)];
   if (tid == 0) {  // chol_lower(Sigma) as pred_emit forms it, Theta
     const double *Sigma = b.Sigma + ((size_t)chain * b.T + tt) * D * D;
     for (int a = 0; a < D; a++)
@@ -375,15 +392,23 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
     double wmax;
     {
       const double tY = a_aux + s.iv2 * (2.0 * s.c0 * sx + s.iv2 * qx);
-      wmax = coh_aux + scale * (dP * q1.A0 - s.hiv2 * qx + q1.H * tY);  // the auxiliary clusters' weight
+      wmax = coh_aux + scale * (dP * q1.A0 - s.hiv2 * qx + q1.H * tY + cat_aux);  // the auxiliary clusters' weight
     }
+    // quirk (:1157): an occupied cluster's categorical "with" count uses the TRAINING row indexed by the prediction index
+    const int *xct = b.xcat + ((size_t)ds * b.nobs + (pp < b.nobs ? pp : 0)) * (ncat > 0 ? ncat : 1);
     const double w_aux = wmax;
 #pragma unroll 1
     for (int j = 0; j < K; j++) {
       double bj = 0.0;
 #pragma unroll
       for (int p = 0; p < PR; p++) bj = fma(ts[p][j], x[p], bj);
-      const double w = cs[0][j] + cs[1][j] * bj + cs[2][j] * qx;
+      double w = cs[0][j] + cs[1][j] * bj + cs[2][j] * qx;
+      if (ncat > 0) {
+        double cj = 0.0;
+        for (int p = 0; p < ncat; p++)
+          cj += cat_lw[njcs[(p * b.maxC + xct[p]) * KR + j]] - cat_ln[(size_t)p * (b.ntmax + 2) + njs[j]];
+        w += scale * cj;
+      }
       ws[j][tid] = w;
       wmax = fmax(wmax, w);
     }

@@ -1721,33 +1721,44 @@ static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, in
   const DevBatch &d = b->d;
   const tppmx_model &m = d.model;
   const int nth = predict_threads(d);
+  const bool cat = d.ncat > 0;
+  // categorical covariates ride on the register kernel (their term is two table logarithms per covariate); the tables
+  // are the fast sweep kernel's (reserved when the model is eligible for it)
   const bool eligible = b->opt_impl != 1 && m.PPMx == 1 && m.consim == 1 && m.similarity == 1 &&
-                        (m.calibration == 0 || m.calibration == 2) && d.ncat == 0 && d.P >= 1 && d.kcap <= 128;
+                        (m.calibration == 0 || m.calibration == 2) && d.P >= 1 && d.kcap <= 128 &&
+                        (!cat || (b->fa.cat_lw && d.ncat * d.maxC <= 256 && d.P <= 16 && d.D <= 3 && d.Q <= TPPMX_MAXQ));
   if (eligible) {
     const int KP = d.kcap;
     const size_t smem = sizeof(double) * ((size_t)(d.P + 3) * KP + (size_t)d.P * nth + (size_t)(KP + 1) * nth);
-    if (smem <= 200 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(predict_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("predict_fast_kernel: ") + cudaGetErrorString(e));
+    if (smem <= 200 * 1024 || cat) {
       // arms with at most TPPMX_PRED_KR clusters (all but a few) go through the register kernel,
-      // the rest through the staged one; each block decides for itself and the other exits at once
+      // the rest through the staged one (the generic one with categorical covariates); each block decides for
+      // itself and the other exits at once
       int kmin = 0;
       if (d.P <= 16 && d.D <= 3 && d.Q <= TPPMX_MAXQ) {
         const dim3 grid((unsigned)n_chains_launch * d.T);
-        if (d.P <= 4) predict_reg_kernel<4><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
-        else if (d.P <= 8) predict_reg_kernel<8><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
-        else if (d.P <= 12) predict_reg_kernel<12><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
-        else predict_reg_kernel<16><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
+        const size_t dyn = cat ? sizeof(int) * ((size_t)d.ncat * d.maxC + 1) * TPPMX_PRED_KR : 0;
+        const double *lw = cat ? b->fa.cat_lw : nullptr, *ln = cat ? b->fa.cat_ln : nullptr;
+        if (d.P <= 4) predict_reg_kernel<4><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
+        else if (d.P <= 8) predict_reg_kernel<8><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
+        else if (d.P <= 12) predict_reg_kernel<12><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
+        else predict_reg_kernel<16><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
         kmin = TPPMX_PRED_KR + 1;
         (*launches)++;
       }
-      predict_fast_kernel<<<dim3((unsigned)n_chains_launch * d.T), nth, smem, st>>>(d, seed, iter, KP, kmin, dpi, dy, dc, dsum);
+      if (cat) {
+        predict_kernel<<<dim3((unsigned)n_chains_launch * d.T), nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum, kmin);
+      } else {
+        cudaError_t e = cudaFuncSetAttribute(predict_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(ctx, TPPMX_ERR_CUDA, std::string("predict_fast_kernel: ") + cudaGetErrorString(e));
+        predict_fast_kernel<<<dim3((unsigned)n_chains_launch * d.T), nth, smem, st>>>(d, seed, iter, KP, kmin, dpi, dy, dc, dsum);
+      }
       (*launches)++;
       CK(ctx, cudaGetLastError());
       return TPPMX_OK;
     }
   }
-  predict_kernel<<<dim3((unsigned)n_chains_launch * d.T), nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum);
+  predict_kernel<<<dim3((unsigned)n_chains_launch * d.T), nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum, 0);
   (*launches)++;
   CK(ctx, cudaGetLastError());
   return TPPMX_OK;
