@@ -474,12 +474,14 @@ def extra_config_legs(ctx, args) -> dict:
             b = Batch(ctx, model, dims, shared, dsets, chain_dataset=cds)
             b.init(1, labels, nclu, betas[0])
             b.sweep(1, 0, 10)
-            b.sweep(1, 10, 10)
+            b.sweep(1, 10, 10)   # lanes per unit settle (and each instantiation's first launch loads it)
+            b.sweep(1, 20, 10)
             rec = {"workload": f"n={dims.nobs} T={dims.T} P={dims.P} ncat={dims.ncat}, 1024 chains over 256 replicate datasets, 10 sweeps timed",
                    "sweep_kernel": b.last_sweep_info()[0],
                    "reallocations_per_sec": len(cds) * dims.nobs * 10 / (b.last_timing()[0] * 1e-3)}
             b.set_sweep_impl("generic")
-            b.sweep(1, 20, 10)
+            b.sweep(1, 30, 10)
+            b.sweep(1, 40, 10)
             rec["generic_kernel_reallocations_per_sec"] = len(cds) * dims.nobs * 10 / (b.last_timing()[0] * 1e-3)
             sw[name] = rec
             b.close()

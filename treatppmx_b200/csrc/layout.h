@@ -18,6 +18,8 @@
 
 namespace tppmx {
 
+#define TPPMX_NNIG_ROW 16  // doubles per n of the NNIG table (tppmx.cu:fast_reserve, sim.cuh:gsim_nnig_row)
+
 struct NNRow {  // per-n constants of gsimconNN (utils_ct.cpp:382-405), see sim.cuh
   double A0, H, B0, H2;
 };
@@ -31,6 +33,7 @@ struct DevBatch {
   const double *grid;
   const double *logV;
   const NNRow *nn_tab;  // [ntmax+2]
+  const double *nnig_tab;  // [ntmax+2][TPPMX_NNIG_ROW] per-n terms of gsimconNNIG (consim == 2, tppmx.cu:fast_reserve) or nullptr
   // datasets
   const int *arm_n;     // [nd][T]
   const int *arm_pat;   // [nd][T][ntmax]

@@ -80,6 +80,32 @@ static __device__ __noinline__ double gsim_nnig(const SimConst &c, double sumx, 
   return ld1 + ld3 - ld4;
 }
 
+// ---- Normal-Normal-Inverse-Gamma similarity in the reference's own evaluation order (utils_ct.cpp:427-459;
+// oracle/ppmx_oracle.c:oracle_gsimconNNIG is compiled with -ffp-contract=off): explicit rounded operations, no
+// contraction, and every division by a quantity of n alone done as a correctly rounded quotient from its
+// tabulated reciprocal (q = a r; q += (a - q d) r -- Markstein's correction, exact with RN(1/d)).
+__device__ __forceinline__ double div_by_tab(double a, double d, double r) {
+  const double q = __dmul_rn(a, r);
+  return fma(fma(-q, d, a), r, q);
+}
+// gsimconNNIG(m0, k0, nu0, s20, S, SS, n, DD = 0, log) with row r of the table over n
+__device__ __forceinline__ double gsim_nnig_row(const double *__restrict__ r, double S, double SS, double m0, double k0m0,
+                                                double b0) {
+  const double mu = 10.0;
+  const double dn = r[1], kn = r[3], rkn = r[4];
+  const double xbar = __dmul_rn(S, r[2]);
+  const double nx = __dmul_rn(dn, xbar);
+  const double m0s = div_by_tab(__dadd_rn(k0m0, nx), kn, rkn);
+  const double dx = __dsub_rn(xbar, m0);
+  const double b0s = __dadd_rn(__dadd_rn(b0, __dmul_rn(0.5, __dsub_rn(SS, __dmul_rn(nx, xbar)))),
+                               div_by_tab(__dmul_rn(__dmul_rn(r[5], dx), dx), kn, rkn));
+  const double ld1 = __dsub_rn(r[0], __dmul_rn(5.0, __dadd_rn(__dsub_rn(SS, __dmul_rn(__dmul_rn(2.0, S), mu)), r[12])));
+  const double t = div_by_tab(__dsub_rn(mu, m0s), r[6], r[7]);
+  const double dnl = -(__dadd_rn(__dadd_rn(TPPMX_LN_SQRT_2PI, __dmul_rn(__dmul_rn(0.5, t), t)), r[8]));
+  const double ig = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(r[9], fast_log(b0s)), r[10]), r[11]), div_by_tab(b0s, 0.1, 10.0));
+  return __dsub_rn(__dadd_rn(ld1, r[13]), __dadd_rn(dnl, ig));
+}
+
 // gsimcatDM, utils_ct.cpp:468-495, for counts cnt[c*cstride] (+1 at category `add`, -1 = none)
 static __device__ __noinline__ double gsim_cat(const SimConst &s, const int *cnt, int cstride, int add, int C,
                                   int DD, bool zero_counts) {
@@ -147,6 +173,17 @@ __device__ inline void sim_terms(const DevBatch &b, const SimConst &s, const dou
       lgY = dP * rY.B0 - s.hiv2 * ssY - rY.H * tY + rY.H2 * uY;
     }
   } else {
+    if (b.nnig_tab && !s.DD) {  // the per-n table of the fast kernel is there: one log per evaluation, the reference's operation order
+      const double *rN = b.nnig_tab + (size_t)TPPMX_NNIG_ROW * n, *rY = rN + TPPMX_NNIG_ROW;
+      const double k0m0 = __dmul_rn(s.k0, s.m0), b0 = __dmul_rn(__dmul_rn(0.5, s.nu0), s.s20);
+      for (int p = 0; p < P; p++) {
+        const double S = occ ? sumx[(size_t)p * ks] : 0.0;
+        const double SS = occ ? sumx2[(size_t)p * ks] : 0.0;
+        const double xp = __ldg(x + p);
+        if (occ) lgN = __dadd_rn(lgN, gsim_nnig_row(rN, S, SS, s.m0, k0m0, b0));
+        lgY = __dadd_rn(lgY, gsim_nnig_row(rY, __dadd_rn(S, xp), __dadd_rn(SS, __dmul_rn(xp, xp)), s.m0, k0m0, b0));
+      }
+    } else
     for (int p = 0; p < P; p++) {
       const double S = occ ? sumx[(size_t)p * ks] : 0.0;
       const double SS = occ ? sumx2[(size_t)p * ks] : 0.0;

@@ -193,32 +193,6 @@ __device__ __forceinline__ double fast_lik_reg(const double *E, const double (&Z
   return w;
 }
 
-// ---- Normal-Normal-Inverse-Gamma similarity in the reference's own evaluation order (utils_ct.cpp:427-459;
-// oracle/ppmx_oracle.c:oracle_gsimconNNIG is compiled with -ffp-contract=off): explicit rounded operations, no
-// contraction, and every division by a quantity of n alone done as a correctly rounded quotient from its
-// tabulated reciprocal (q = a r; q += (a - q d) r -- Markstein's correction, exact with RN(1/d)).
-__device__ __forceinline__ double div_by_tab(double a, double d, double r) {
-  const double q = __dmul_rn(a, r);
-  return fma(fma(-q, d, a), r, q);
-}
-// gsimconNNIG(m0, k0, nu0, s20, S, SS, n, DD = 0, log) with row r of the table over n
-__device__ __forceinline__ double gsim_nnig_row(const double *__restrict__ r, double S, double SS, double m0, double k0m0,
-                                                double b0) {
-  const double mu = 10.0;
-  const double dn = r[1], kn = r[3], rkn = r[4];
-  const double xbar = __dmul_rn(S, r[2]);
-  const double nx = __dmul_rn(dn, xbar);
-  const double m0s = div_by_tab(__dadd_rn(k0m0, nx), kn, rkn);
-  const double dx = __dsub_rn(xbar, m0);
-  const double b0s = __dadd_rn(__dadd_rn(b0, __dmul_rn(0.5, __dsub_rn(SS, __dmul_rn(nx, xbar)))),
-                               div_by_tab(__dmul_rn(__dmul_rn(r[5], dx), dx), kn, rkn));
-  const double ld1 = __dsub_rn(r[0], __dmul_rn(5.0, __dadd_rn(__dsub_rn(SS, __dmul_rn(__dmul_rn(2.0, S), mu)), r[12])));
-  const double t = div_by_tab(__dsub_rn(mu, m0s), r[6], r[7]);
-  const double dnl = -(__dadd_rn(__dadd_rn(TPPMX_LN_SQRT_2PI, __dmul_rn(__dmul_rn(0.5, t), t)), r[8]));
-  const double ig = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(r[9], fast_log(b0s)), r[10]), r[11]), div_by_tab(b0s, 0.1, 10.0));
-  return __dsub_rn(__dadd_rn(ld1, r[13]), __dadd_rn(dnl, ig));
-}
-
 // cold path: a unit of the warp has more than LPU candidate clusters (`mine`).  Scores in
 // chunks through U.wsc; returns newci for the units with `mine`.
 template <int LPU>

@@ -57,7 +57,6 @@ __host__ __device__ inline size_t fast_unit_bytes(int P, int KS, int ntp, int CC
 __host__ __device__ inline size_t fast_tab_bytes(int ntmax, int big, int nnig = 0) {
   return (big || nnig) ? 16 : (size_t)4 * (ntmax + 2) * 8;
 }
-#define TPPMX_NNIG_ROW 16  // doubles per n of the NNIG table (tppmx.cu:fast_reserve, sweep_fast.cuh)
 
 // Launch for LPU lanes per (chain, arm) on `stream`; picks the instantiation from the batch shape
 // (P -> XR, D -> DR, model.nolik, fa.big).  fa.big requires LPU = 32.

@@ -1135,6 +1135,7 @@ static int fast_reserve(tppmx_batch *b) {
     const double *tp = nullptr;
     RC(dev_upload(b, &tp, tg));
     fa.tabg = const_cast<double *>(tp);
+    if (d.model.consim == 2) b->d.nnig_tab = tp;  // the generic kernels and the predictive step use it too (sim.cuh)
   }
   fa.cat_lw = fa.cat_ln = nullptr;
   if (d.ncat > 0) {  // gsimcatDM (utils_ct.cpp:468-495) as two logarithms over the integers (sweep_fast.cuh, CAT)
