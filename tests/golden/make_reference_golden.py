@@ -26,6 +26,11 @@ REF_GOLDEN = {  # name -> (iters, burn, thin, seed)
     "noreuse": (30, 10, 2, 8),
     "categorical": (30, 10, 2, 9),
     "Q3_D3": (30, 10, 2, 10),
+    # the shapes the fast kernel's special instantiations run at (n = 152, T = 3, P = 10)
+    "calib1_dp_T3": (30, 10, 2, 11),
+    "nnig_ngg_T3": (30, 10, 2, 12),
+    "categorical_T3": (30, 10, 2, 13),
+    "dd_dp_T3": (30, 10, 2, 14),
     # BASELINE config 1: the bundled simupats data (tests/golden/simupats_config1.npz), ppmxct()'s default
     # chain length iter = 1100 / burn = 100, thinned to 50 saved iterations to keep the file small
     "simupats_ngg": (1100, 100, 20, 121),
