@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128) predict_fast_kernel(DevBatch b, uint64_t 
 // waits for).  Softmax by fast_exp with the division-free draw of the sweep kernel.
 // Config 5 (10 000 new patients x 3 arms x 1024 chains): 5.5 ms -> see DESIGN.md.
 #define TPPMX_PRED_KR 16
-template <int PR>
+template <int PR, bool CAT>
 __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_t seed, int iter, double *pipred,
                                                           double *ypred, int *predclass, double *pisum,
                                                           const double *cat_lw, const double *cat_ln) {
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
   // memory; the Dirichlet-multinomial "with minus without" term of covariate p is log(n_jc* + w) - log(n_j + C_p w)
   // from the two tables (as the CAT instantiation of sweep_fast.cuh)
   extern __shared__ int pred_dyn[];
-  const int ncat = cat_lw ? b.ncat : 0, ncC = ncat * b.maxC;
+  const int ncat = CAT ? b.ncat : 0, ncC = ncat * b.maxC;
   int *njcs = pred_dyn, *njs = pred_dyn + ncC * KR;
   __shared__ double ts[PR][KR];
   __shared__ double cs[3][KR];
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
       for (int k = 0; k < D; k++) etas[k][j] = A.eta[(size_t)k * A.ks + j];
     }
   }
-  if (ncat > 0) {
+  if constexpr (CAT) {
     for (int e = tid; e < ncC * KR; e += nth) {
       const int pc = e / KR, j = e - pc * KR;
       njcs[e] = (j < K) ? A.njc[(size_t)pc * A.ks + j] : 0;
@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
     for (int j = tid; j < KR; j += nth) njs[j] = (j < K) ? A.nj[j] : 0;
   }
   double cat_aux = 0.0;  // an auxiliary cluster: counts zero, sum_p [log w - log(C_p w)]
-  for (int p = 0; p < ncat; p++) cat_aux += cat_lw[0] - cat_ln[(size_t)p * (b.ntmax + 2)];
+  if constexpr (CAT)
+    for (int p = 0; p < ncat; p++) cat_aux += cat_lw[0] - cat_ln[(size_t)p * (b.ntmax + 2)];
   if (tid == 0) {  // chol_lower(Sigma) as pred_emit forms it, Theta
     const double *Sigma = b.Sigma + ((size_t)chain * b.T + tt) * D * D;
     for (int a = 0; a < D; a++)
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(128, 4) predict_reg_kernel(DevBatch b, uint64_
 #pragma unroll
       for (int p = 0; p < PR; p++) bj = fma(ts[p][j], x[p], bj);
       double w = cs[0][j] + cs[1][j] * bj + cs[2][j] * qx;
-      if (ncat > 0) {
+      if constexpr (CAT) {
         double cj = 0.0;
         for (int p = 0; p < ncat; p++)
           cj += cat_lw[njcs[(p * b.maxC + xct[p]) * KR + j]] - cat_ln[(size_t)p * (b.ntmax + 2) + njs[j]];

@@ -1740,10 +1740,17 @@ static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, in
         const dim3 grid((unsigned)n_chains_launch * d.T);
         const size_t dyn = cat ? sizeof(int) * ((size_t)d.ncat * d.maxC + 1) * TPPMX_PRED_KR : 0;
         const double *lw = cat ? b->fa.cat_lw : nullptr, *ln = cat ? b->fa.cat_ln : nullptr;
-        if (d.P <= 4) predict_reg_kernel<4><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
-        else if (d.P <= 8) predict_reg_kernel<8><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
-        else if (d.P <= 12) predict_reg_kernel<12><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
-        else predict_reg_kernel<16><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
+        if (cat) {
+          if (d.P <= 4) predict_reg_kernel<4, true><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
+          else if (d.P <= 8) predict_reg_kernel<8, true><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
+          else if (d.P <= 12) predict_reg_kernel<12, true><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
+          else predict_reg_kernel<16, true><<<grid, nth, dyn, st>>>(d, seed, iter, dpi, dy, dc, dsum, lw, ln);
+        } else {
+          if (d.P <= 4) predict_reg_kernel<4, false><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum, nullptr, nullptr);
+          else if (d.P <= 8) predict_reg_kernel<8, false><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum, nullptr, nullptr);
+          else if (d.P <= 12) predict_reg_kernel<12, false><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum, nullptr, nullptr);
+          else predict_reg_kernel<16, false><<<grid, nth, 0, st>>>(d, seed, iter, dpi, dy, dc, dsum, nullptr, nullptr);
+        }
         kmin = TPPMX_PRED_KR + 1;
         (*launches)++;
       }
