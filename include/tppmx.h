@@ -235,14 +235,14 @@ int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t
                             int32_t stride, double *prob_out, int32_t *K_out);
 
 /* Kernel selection.  The library has three sweep kernels with identical results:
- *   fast    — PPMx=1, reuse=1, auxiliary similarity: cluster statistics staged in shared memory,
+ *   fast    — auxiliary similarity: cluster statistics staged in shared memory,
  *             likelihood terms hoisted into a parallel pre-pass, TPPMX_OPT_LANES_PER_UNIT (8|16|32)
  *             lanes per (chain, arm); 0 = automatic (16; 32 below 300 units and for long arms).
  *             Default switches (consim=1, similarity=1, calibration 0|2, ncat=0) for any shape, and
  *             -- for D <= 3 outcome categories, arms short enough for shared-memory label tables,
  *             16|32 lanes and at most lanes - CC staged clusters per arm -- one of: calibration 1;
  *             consim=2 (NNIG, P <= 32); categorical covariates (ncat <= 16); similarity=2 (double
- *             dipper, Normal-Normal)
+ *             dipper, Normal-Normal); reuse=0; PPMx=0
  *   long-arm — arms of thousands of patients (default switches): the fast kernel in big-arm mode up
  *             to 32 clusters per arm, then one CTA per (chain, arm) with up to 256 staged clusters
  *   generic — every switch combination of the reference, one warp per (chain, arm)

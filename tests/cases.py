@@ -22,6 +22,7 @@ CASES = {
     "calib2_sqrt":   (dict(calibration=2, coardegree=2), dict(T=2, n=60, P=7)),
     "calib2":        (dict(calibration=2, coardegree=1, cohesion=1), dict(T=3, n=66, P=4)),
     "noreuse":       (dict(reuse=0, CC=2), dict(T=2, n=50, P=5)),
+    "noreuse_T3":    (dict(reuse=0, cohesion=1, alpha=2.0), dict(T=3)),
     "ppm_only":      (dict(PPMx=0, cohesion=1), dict(T=2, n=50, P=3)),
     "categorical":   (dict(cohesion=1), dict(T=2, n=60, P=4, ncat=2, maxC=3, npred=20)),
     "categorical_T3": (dict(cohesion=1, alpha=1.5), dict(T=3, ncat=3, maxC=4)),

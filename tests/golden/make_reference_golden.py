@@ -31,6 +31,7 @@ REF_GOLDEN = {  # name -> (iters, burn, thin, seed)
     "nnig_ngg_T3": (30, 10, 2, 12),
     "categorical_T3": (30, 10, 2, 13),
     "dd_dp_T3": (30, 10, 2, 14),
+    "noreuse_T3": (30, 10, 2, 15),
     # BASELINE config 1: the bundled simupats data (tests/golden/simupats_config1.npz), ppmxct()'s default
     # chain length iter = 1100 / burn = 100, thinned to 50 saved iterations to keep the file small
     "simupats_ngg": (1100, 100, 20, 121),

@@ -64,6 +64,8 @@ CASES = {
     "dp_T3": lambda: build_case("dp_T3", n_datasets=2),
     "Q3_D3": lambda: build_case("Q3_D3", n_datasets=2),
     "ppm_only": lambda: build_case("ppm_only", n_datasets=2),   # PPMx = 0: cohesion x likelihood only
+    "noreuse": lambda: build_case("noreuse", n_datasets=2),     # reuse = 0: auxiliary eta redrawn per patient
+    "noreuse_T3": lambda: build_case("noreuse_T3", n_datasets=2),
     # calibration 1: normalised similarities, their own instantiation (16 | 32 lanes per unit)
     "calib1": lambda: build_case("calib1", n_datasets=2),
     "calib1_dp_T3": lambda: build_case("calib1_dp_T3", n_datasets=2),

@@ -12,7 +12,7 @@ from treatppmx_b200._abi import default_model
 
 pytestmark = pytest.mark.gpu
 
-FAST_CASES = ["default_ngg", "dp_T3", "calib2", "calib2_sqrt", "Q3_D3", "prior_only", "ppm_only"]
+FAST_CASES = ["default_ngg", "dp_T3", "calib2", "calib2_sqrt", "Q3_D3", "prior_only", "ppm_only", "noreuse", "noreuse_T3"]
 
 
 @pytest.fixture(scope="module")

@@ -128,7 +128,7 @@ RUNS = [("default_ngg", {}), ("dp_T3", {}), ("nnig", {}), ("nnig_dd", {}), ("cal
         ("double_dipper", {"cohesion": 1}), ("cat_dd_calib1", {"cohesion": 1}),
         # the shapes of the fast kernel's special instantiations (n = 152, T = 3, P = 10): calibration 1 with DP cohesion,
         # NNIG with NGG cohesion, three categorical covariates, double dipper with coarsened similarity
-        ("calib1_dp_T3", {}), ("nnig_ngg_T3", {}), ("categorical_T3", {}), ("dd_dp_T3", {}), ("cat_calib2", {}),
+        ("calib1_dp_T3", {}), ("nnig_ngg_T3", {}), ("categorical_T3", {}), ("dd_dp_T3", {}), ("cat_calib2", {}), ("noreuse_T3", {}),
         # the switches of the update part: no prognostic coefficients, frozen hierarchy, no horseshoe
         ("default_ngg", {"noprog": 1}), ("dp_T3", {"upd_hier": 0}), ("default_ngg", {"hsp": 0}),
         ("dp_T3", {"noprog": 1, "upd_hier": 0, "hsp": 0})]

@@ -278,8 +278,12 @@ __device__ __noinline__ int fast_score_multi(UnitSmem U, const double2 *tab2, co
 //   g = P B0[n] - sum_p sumx2/(2 v2) - H[n] sum_p t^2 + H2[n] sum_p u^2,  u = sumx/v2 + t = 2 t - c0, so beside a and b
 //   the lane carries st = sum_p t (linear in the statistics: corrected by +- sum_p x / v2 on the touched lanes):
 //   sum u^2 = 4 a - 4 c0 st + P c0^2,  sum u x = 2 b - c0 sum_p x.  The fourth table entry of row n is H2[n].
+// R0: reuse == 0 (:605-610): the CC auxiliary eta are redrawn for every patient, so an auxiliary column of the
+//   likelihood table holds patient-specific entries (drawn and evaluated in the pre-pass: the draws are counter-based,
+//   keyed by (patient, slot)), a new cluster takes its patient's draw and gets a column of its own for the patients
+//   that follow, and the auxiliary slots keep theirs.
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC = 0, bool CAL1 = false, bool NNIG = false, bool CAT = false,
-          bool DDIP = false>
+          bool DDIP = false, bool R0 = false>
 __global__ void __launch_bounds__(32, TPPMX_FAST_MINB)
 sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweeps) {
   constexpr int UPW = 32 / LPU;
@@ -404,12 +408,12 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
     }
     if (!__any_sync(TPPMX_FULL, live)) break;
     // =========================== parallel pre-pass of the sweep ===========================
-    if (live)  // :351-360 auxiliary eta ~ N(0, I)
+    if (live && !R0)  // :351-360 auxiliary eta ~ N(0, I)
       for (int mm = ul; mm < CC; mm += LPU)
         rng_normals(rng, l, TPPMX_SITE_AUX_SWEEP, tt, (uint32_t)mm, D, g_etae + mm, CC);
     __syncwarp();
     if (live && !NOLIK) {  // exp(eta) of every candidate cluster, stored by column id
-      const int ntot = K + CC;
+      const int ntot = R0 ? K : K + CC;  // R0: the auxiliary eta are per patient (phase B)
       for (int e = ul; e < ntot * D; e += LPU) {
         const int c = e / D, k = e - c * D;
         const double eta = (c < K) ? g_eta[(size_t)k * kcap + c] : g_etae[k * CC + (c - K)];
@@ -528,7 +532,7 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         // pair e -> (c, it) = (e / nt, e % nt), kept incrementally; consecutive lanes write
         // consecutive rows of one table column.  D <= 3: the operands of the NEXT pair are fetched
         // before the current pair's three lgamma evaluations.
-        const int npair = (K + CC) * nt;
+        const int npair = (R0 ? K : K + CC) * nt;
         int c = ul / nt, it = ul - c * nt;
         if constexpr (DR == 3) {
           const bool h1 = D > 1, h2 = D > 2;
@@ -583,6 +587,21 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
               it -= nt;
               c += 1;
             }
+          }
+        }
+      }
+      if constexpr (R0 && DR == 3) {
+        if (live && !NOLIK) {  // auxiliary columns: slot m of patient it scores the patient's own draw eta_aux(i, m)
+          for (int e = ul; e < CC * nt; e += LPU) {
+            const int m = e / nt, it = e - m * nt;
+            const int i = patp[it];
+            double zn[4], Ea[3];
+            rng_normals(rng, l, TPPMX_SITE_AUX_PATIENT, tt, (uint32_t)(i * CC + m), D, zn, 1);
+            for (int k = 0; k < 3; k++) Ea[k] = (k < D) ? fast_exp(zn[k]) : 1.0;
+            const size_t o = (size_t)i * D;
+            lik[(size_t)colmap(K + m, K) * ntp + it] =
+                fast_lik3(Ea, D, g_ez[o], D > 1 ? g_ez[o + 1] : 1.0, D > 2 ? g_ez[o + 2] : 1.0, g_ljj[o], D > 1 ? g_ljj[o + 1] : 0.0,
+                          D > 2 ? g_ljj[o + 2] : 0.0);
           }
         }
       }
@@ -943,6 +962,10 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
         if (multi) newci = r;
       }
 
+      if constexpr (R0) {  // the state the arm leaves behind: eta_empty holds the LAST patient's draws (:605-610)
+        if (on && it == nt - 1 && ul < CC)
+          rng_normals(rng, l, TPPMX_SITE_AUX_PATIENT, tt, (uint32_t)(patp[it] * CC + ul), D, g_etae + ul, CC);
+      }
       // ---- :820-856 assign; the statistics receive the patient at the top of the next step
       TPPMX_ASSERT(!on || (newci >= 1 && newci <= K + CC), 4);
       const bool born = on && newci > K;
@@ -963,16 +986,24 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
           if (ul == 0) {
             labp[it] = lab;
             U.nj[lab - 1] = 0;  // the arrival is counted with the statistics, at the top of the next step
-            U.col[lab - 1] = U.col[KS + m];
-            U.col[KS + m] = newcol;
+            if constexpr (R0) {
+              U.col[lab - 1] = newcol;  // the auxiliary slot keeps its (patient-specific) column
+              rng_normals(rng, l, TPPMX_SITE_AUX_PATIENT, tt, (uint32_t)(i * CC + m), D, g_etae + m, CC);  // this patient's draw
+            } else {
+              U.col[lab - 1] = U.col[KS + m];
+              U.col[KS + m] = newcol;
+            }
           }
+        }
+        if constexpr (R0) __syncwarp();
+        if (born) {
           for (int k = ul; k < D; k += LPU) g_eta[(size_t)k * kcap + lab - 1] = g_etae[k * CC + m];
         }
         __syncwarp();
         if (born && ul == 0) rng_normals(rng, l, TPPMX_SITE_AUX_REFRESH, tt, (uint32_t)i, D, g_etae + m, CC);
         __syncwarp();
-        if (born && !NOLIK)
-          for (int k = ul; k < D; k += LPU) U.E[newcol * D + k] = fast_exp(g_etae[k * CC + m]);
+        if (born && !NOLIK)  // the column filled below: the refreshed auxiliary eta (reuse) / the new cluster's own eta (R0)
+          for (int k = ul; k < D; k += LPU) U.E[newcol * D + k] = fast_exp(R0 ? g_eta[(size_t)k * kcap + lab - 1] : g_etae[k * CC + m]);
         __syncwarp();
         if (born) {
           if (!NOLIK)  // likelihood column of the refreshed auxiliary eta, remaining patients
@@ -1094,14 +1125,14 @@ sweep_fast_kernel(DevBatch b, FastArgs fa, uint64_t seed, int iter0, int n_sweep
 
 // ---- launch: instantiation picked from the batch shape (one translation unit per LPU) ----------
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE, int PC, bool CAL1 = false, bool NNIG = false, bool CAT = false,
-          bool DDIP = false>
+          bool DDIP = false, bool R0 = false>
 static cudaError_t fast_launch7(const DevBatch &d, const FastArgs &fa, size_t smem, uint64_t seed, int iter0,
                                 int n_sweeps, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT, DDIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT, DDIP, R0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int upw = 32 / LPU;
   const int grid = (fa.n_units + upw - 1) / upw;
-  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT, DDIP><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
+  sweep_fast_kernel<LPU, XR, DR, NOLIK, BIG, PROBE, PC, CAL1, NNIG, CAT, DDIP, R0><<<grid, 32, smem, stream>>>(d, fa, seed, iter0, n_sweeps);
   return cudaGetLastError();
 }
 template <int LPU, int XR, int DR, bool NOLIK, bool BIG, bool PROBE>
@@ -1109,6 +1140,13 @@ static cudaError_t fast_launch6(const DevBatch &d, const FastArgs &fa, size_t sm
                                 int n_sweeps, cudaStream_t stream) {
   // the package's shape (genmech: 10 predictive covariates, D = 3 outcome categories, two units per warp) is
   // compiled with P as a constant: its dot products unroll into straight-line code
+  if (d.model.reuse == 0) {  // auxiliary eta redrawn per patient: the default similarity only (tppmx.cu:fast_eligible)
+    if constexpr (DR == 3 && !NOLIK && !BIG) {
+      if (d.model.similarity != 1 || d.model.consim != 1 || d.model.calibration == 1 || d.ncat > 0) return cudaErrorInvalidConfiguration;
+      return fast_launch7<LPU, XR, DR, NOLIK, BIG, PROBE, 0, false, false, false, false, true>(d, fa, smem, seed, iter0, n_sweeps, stream);
+    }
+    return cudaErrorInvalidConfiguration;
+  }
   if (d.model.similarity == 2) {  // double dipper (Normal-Normal, no categorical covariates, calibration 0 | 2)
     if constexpr (LPU >= 16 && DR == 3 && !NOLIK && !BIG) {
       if (fa.KS + d.CC > LPU || d.model.calibration == 1 || d.model.consim != 1 || d.ncat > 0) return cudaErrorInvalidConfiguration;

@@ -1046,7 +1046,7 @@ static bool fast_eligible(const tppmx_batch *b, int lpu) {
   if (d.ncat > 0 && (m.calibration == 1 || m.consim != 1 || d.ncat > 16 || d.ncat * d.maxC > 256)) return false;
   if (m.PPMx == 0 && (special || big_arms(d))) return false;  // no similarity term: the plain instantiation with a zero factor
   return (m.PPMx == 1 || m.PPMx == 0) && (m.consim == 1 || m.consim == 2) && (m.similarity == 1 || m.similarity == 2) && m.calibration >= 0 && m.calibration <= 2 &&
-         m.reuse == 1 && d.P >= 1 && d.P <= 4 * lpu;
+         (m.reuse == 1 || (m.reuse == 0 && !special && m.PPMx == 1 && d.D <= 3 && !m.nolik && !big_arms(d))) && d.P >= 1 && d.P <= 4 * lpu;
 }
 // arms too long for the small-arm kernel's shared-memory label / order / cohesion tables (thousands of
 // patients, BASELINE config 4) run the long-arm kernel (sweep_big.cuh): one CTA per (chain, arm)
