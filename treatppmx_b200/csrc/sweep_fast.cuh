@@ -1,6 +1,8 @@
-// sweep_fast.cuh — the production reallocation-sweep kernel for the default model switches
-// (PPMx=1, Normal-Normal auxiliary similarity, calibration 0|2, no categorical covariates,
-// reuse=1): reference src/dm_ppmx_ct.cpp:347-860 with consim==1, similarity==1.
+// sweep_fast.cuh — the production reallocation-sweep kernel: reference src/dm_ppmx_ct.cpp:347-860.
+// The default model switches (PPMx=1, Normal-Normal auxiliary similarity, calibration 0|2, no categorical
+// covariates, reuse=1: consim==1, similarity==1) are what the design below describes; template flags add
+// calibration 1 (CAL1), the NNIG similarity (NNIG), categorical covariates (CAT), the double dipper (DDIP),
+// reuse = 0 (R0) and arms of thousands of patients (BIG) -- each documented at the kernel's template head.
 //
 // Design (B200-first):
 //  * unit = one (chain, arm).  Arms never touch each other's state inside the sweep, so the

@@ -1708,11 +1708,12 @@ extern "C" int tppmx_batch_predict(tppmx_batch *b, uint64_t seed, int32_t iter, 
   return TPPMX_OK;
 }
 
-// Predictive step: the closed-form kernel for the default switches (same eligibility as the fast
-// sweep, any reuse), the generic kernel otherwise or when the clusters do not fit the staged
-// capacity.  The partition size is not known on the host, so the staged capacity is kcap capped
-// at 64; chains with more clusters are rare and handled by the block itself falling back is not
-// possible mid-kernel, hence the cap decides the kernel for the whole launch.
+// Predictive step.  Default switches (Normal-Normal auxiliary similarity, calibration 0 | 2, any reuse), with or
+// without categorical covariates: the closed-form register kernel for arms of at most TPPMX_PRED_KR clusters, and
+// behind it -- each block deciding for itself from its arm's K -- the staged closed-form kernel (no categorical
+// covariates) or the generic kernel for the arms with more.  Every other switch combination: the generic kernel
+// (its NNIG similarity through the per-n table when the batch has one, sim.cuh).  dsum != nullptr: the kernels add
+// every probability to its replicate dataset's sum themselves (summary.cuh).
 static int predict_launch(tppmx_batch *b, int n_chains_launch, uint64_t seed, int iter, double *dpi, double *dy, int *dc,
                           cudaStream_t st, double *dsum, int *launches) {
   int nl_local = 0;
