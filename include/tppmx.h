@@ -237,7 +237,7 @@ int tppmx_batch_sweep_probe(tppmx_batch *b, uint64_t seed, int32_t iter, int32_t
 /* Kernel selection.  The library has three sweep kernels with identical results:
  *   fast    — auxiliary similarity: cluster statistics staged in shared memory,
  *             likelihood terms hoisted into a parallel pre-pass, TPPMX_OPT_LANES_PER_UNIT (8|16|32)
- *             lanes per (chain, arm); 0 = automatic (16; 32 below 300 units and for long arms).
+ *             lanes per (chain, arm); 0 = automatic (16; 32 up to 10 units per SM and for long arms).
  *             Default switches (consim=1, similarity=1, calibration 0|2, ncat=0) for any shape, and
  *             -- for D <= 3 outcome categories, arms short enough for shared-memory label tables,
  *             16|32 lanes and at most lanes - CC staged clusters per arm -- one of: calibration 1;

@@ -69,6 +69,7 @@ struct tppmx_ctx {
   // chain groups of tppmx_batch_run (TPPMX_OPT_CHAIN_GROUPS): each group of chains runs its iterations on its
   // own stream triple, so that the sweep of one group overlaps the updates of another -- chains are independent,
   // and at BASELINE's 1024 chains every kernel of the iteration is latency-bound (2.6 warps per scheduler)
+  int sm_count = 148;
   std::vector<tppmx_ctx *> lanes;
   // device block of the drop-in's traces (tppmx_dm_ppmx_ct), kept across calls
   void *trace = nullptr;
@@ -178,6 +179,7 @@ extern "C" int tppmx_create(tppmx_ctx **out, int device) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return TPPMX_ERR_CUDA;
   tppmx_ctx *c = ctx_new(device);
   if (!c) return TPPMX_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count < 1) c->sm_count = 148;
   *out = c;
   return TPPMX_OK;
 }
@@ -1215,10 +1217,12 @@ static int sweep_launch(tppmx_batch *b, uint64_t seed, int32_t iter0, int32_t n_
   int lpu = b->opt_lpu;
   const bool big = big_arms(b->d);
   if (big) lpu = 32;  // long arms: one CTA per (chain, arm), P <= 128 covariate owners
-  // few units (one ppmxct() call = one chain): latency, not residency, is what counts -- one unit per warp puts
-  // twice the lanes on the sweep's parallel pre-pass
+  // One unit per warp (32 lanes) puts twice the lanes on the sweep's parallel pre-pass; two units per warp (16 lanes)
+  // halve the instruction stream per unit.  While every unit still gets a warp of its own within one wave of the
+  // machine (12 one-warp CTAs per SM; measured on B200: 600 / 1200 units +30 % / +15 % with 32 lanes, 1800 units
+  // -22 %) latency is what counts: 32 lanes up to 10 units per SM, 16 beyond.
   else if (!lpu) {
-    lpu = ((long long)b->d.n_chains * b->d.T <= 296) ? 32 : 16;
+    lpu = ((long long)b->d.n_chains * b->d.T <= 10LL * ctx->sm_count) ? 32 : 16;
     if (b->bail_host) {
       const volatile int *bh = b->bail_host;
       if ((long long)bh[0] * 50 > (long long)b->d.n_chains * b->d.T || bh[1] + b->d.CC + 2 > 16) lpu = 32;
