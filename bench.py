@@ -652,7 +652,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     ctxs = [ctx] + [Context(local_rank) for _ in range(ninfl - 1)]
     for c in ctxs[1:]:
         e2e_call(c, w, seed, 2)  # warm (arena of the extra contexts)
-    pipe_reps = max(8, args.steps)   # steady state of a study that feeds batch after batch: ramp and drain are a small part
+    pipe_reps = max(16, args.steps)   # steady state of a study that feeds batch after batch: ramp and drain are a small part
 
     def pipe_work(c):
         for _ in range(pipe_reps):
