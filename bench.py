@@ -648,7 +648,9 @@ def run_native(args, rank: int, world: int, local_rank: int):
     # its own results out inside the timed region.
     from concurrent.futures import ThreadPoolExecutor
     from treatppmx_b200.engine import Context
-    ninfl = max(2, args.e2e_inflight)
+    # batches in flight = host threads: 0 = automatic, the rank's share of the usable host cores less one, between 2 and 4
+    # (one B200 box: 16 cores -> 4; eight ranks on 32 cores -> 3)
+    ninfl = args.e2e_inflight if args.e2e_inflight > 0 else max(2, min(4, host_cores()["threads_used"] // max(world, 1) - 1))
     ctxs = [ctx] + [Context(local_rank) for _ in range(ninfl - 1)]
     for c in ctxs[1:]:
         e2e_call(c, w, seed, 2)  # warm (arena of the extra contexts)
@@ -816,7 +818,7 @@ def main():
     ap.add_argument("--mixture", type=int, default=0)
     ap.add_argument("--sweep-impl", default="auto", choices=["auto", "generic", "fast"])
     ap.add_argument("--lpu", type=int, default=0, help="lanes per (chain, arm) of the fast kernel: 0=default, 8|16|32")
-    ap.add_argument("--e2e-inflight", type=int, default=3, help="batches in flight of the e2e measurement (host threads)")
+    ap.add_argument("--e2e-inflight", type=int, default=0, help="batches in flight of the e2e measurement (host threads); 0 = automatic (2..4 from the host cores per rank)")
     ap.add_argument("--cpu-scale", type=float, default=1.0, help="scales the time budgets of the CPU legs (tests use a small value)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the sustained leg (one long launch); 0 = off")
